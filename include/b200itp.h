@@ -1,0 +1,220 @@
+/*
+ * b200itp.h — C ABI of libb200itp: the B200 (sm_100a) implementation of the
+ * uniform-grid B-spline hot path of JuliaMath/Interpolations.jl v0.16.3.
+ *
+ * Plain C, `extern "C"`, plain pointers and sizes.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - Arrays are dense, column-major (first index contiguous): exactly
+ *    `parent(coefs)` of the reference (src/b-splines/prefiltering.jl:126-127).
+ *  - All device buffers are owned by the caller.  The library allocates nothing
+ *    that outlives a call except a small per-device scratch cache.
+ *  - Return value: 0 success; <0 CUDA error (text via b200itp_last_error);
+ *    >0 unsupported/invalid argument (B200ITP_E_*).
+ *  - Out-of-bounds queries under `Throw` are not an ABI error: the smallest
+ *    offending query index is returned through `first_oob` and the output there
+ *    is NaN; the host glue raises BoundsError (src/b-splines/indexing.jl:6,
+ *    src/extrapolation/extrapolation.jl:115-129).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - Indices in the reference's index space are 1-based, as in Julia.
+ */
+#ifndef B200ITP_H
+#define B200ITP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ITP_VERSION 100
+#define B200ITP_MAX_DIMS 4
+#define B200ITP_MAX_WOODBURY 8
+
+/* element types of arrays */
+enum { B200ITP_F32 = 0, B200ITP_F64 = 1 };
+
+/* Julia-style promotion tag of a bound / range element: an Int or Rational bound
+ * does not widen a Float32 coordinate, a Float64 bound does
+ * (src/extrapolation/extrapolation.jl:153-156 `maxp/minp`, Base.clamp). */
+enum { B200ITP_TAG_EXACT = 0, B200ITP_TAG_F32 = 1, B200ITP_TAG_F64 = 2 };
+
+/* interpolation degree per axis (src/b-splines/{linear,quadratic,cubic}.jl) */
+enum { B200ITP_LINEAR = 1, B200ITP_QUADRATIC = 2, B200ITP_CUBIC = 3 };
+
+/* boundary conditions (src/Interpolations.jl:89-118); also the extrapolation flags
+ * (src/extrapolation/extrapolation.jl:106-151) */
+enum {
+  B200ITP_BC_THROW = 0,
+  B200ITP_BC_FLAT = 1,
+  B200ITP_BC_LINE = 2, /* == Natural */
+  B200ITP_BC_FREE = 3,
+  B200ITP_BC_PERIODIC = 4,
+  B200ITP_BC_REFLECT = 5
+};
+
+/* grid type (src/Interpolations.jl:53-56) */
+enum { B200ITP_ONGRID = 0, B200ITP_ONCELL = 1 };
+
+/* extrapolation wrapper kind */
+enum { B200ITP_ETP_NONE = 0, B200ITP_ETP_FLAGS = 1, B200ITP_ETP_FILL = 2 };
+
+/* error codes (>0) */
+enum {
+  B200ITP_E_BADARG = 1,
+  B200ITP_E_UNSUPPORTED = 2, /* descriptor outside the hot path: host glue throws ArgumentError */
+  B200ITP_E_DTYPE = 3,
+  B200ITP_E_SIZE = 4
+};
+
+/* bits of the per-query branch record written by b200itp_eval when dbg_branch != NULL.
+ * One nibble per axis d (bits 4d..4d+3) plus global flags.  These are the
+ * "boundary / extrapolation branch choices" that must match the reference bit for bit. */
+#define B200ITP_BR_BELOW 0x1u  /* x < lower bound of the outermost wrapper            */
+#define B200ITP_BR_ABOVE 0x2u  /* x > upper bound                                     */
+#define B200ITP_BR_MOVED 0x4u  /* extrapolation mapped x to a different xs (xs != x)  */
+#define B200ITP_BR_EDGE 0x8u   /* the degree's edge rule fired (cubic.jl:42-43, quadratic
+                                  ceil branch indexing.jl:176, linear.jl:47)           */
+#define B200ITP_BR_SLOWPATH (1u << 16) /* extrapolation.jl:55-57 gradient path taken   */
+#define B200ITP_BR_FILLED (1u << 17)   /* filled.jl:38 fill value returned             */
+#define B200ITP_BR_THROW (1u << 18)    /* BoundsError would be thrown                  */
+
+/*
+ * POD description of `extrapolate(scale(interpolate(A, BSpline(deg(bc(gt)))), ranges...), et)`
+ * after `Adapt.adapt` (src/gpu_support.jl:4-8,32-48).  Supported wrapper order is
+ * BSplineInterpolation [-> ScaledInterpolation] [-> Extrapolation | FilledExtrapolation].
+ * All numbers the host can compute with the reference's own functions
+ * (`lbounds/ubounds`, `first/step` of ranges) are passed down as doubles together
+ * with the Julia type they had, so the kernel reproduces the promotion rules.
+ */
+typedef struct b200itp_desc {
+  int32_t ndims;      /* 1..4                                                         */
+  int32_t coef_dtype; /* B200ITP_F32 / F64 : eltype(itp.coefs)                         */
+  int32_t coord_dtype;/* eltype of the broadcast arguments xs...                       */
+  int32_t etp_pair_mask; /* bit d set: axis d was given an explicit (lo, hi) flag pair   */
+  int64_t size[B200ITP_MAX_DIMS];       /* size(parent(itp.coefs)) (padded)           */
+  int64_t parent_len[B200ITP_MAX_DIMS]; /* length.(itp.parentaxes); parent axes 1:n   */
+  int32_t coef_first[B200ITP_MAX_DIMS]; /* first index of coefs' axis: 0 padded, 1 not
+                                           (cubic.jl:86-87, quadratic.jl:64-65, linear.jl:60) */
+  int32_t degree[B200ITP_MAX_DIMS];
+  int32_t bc[B200ITP_MAX_DIMS];         /* only PERIODIC changes evaluation (modrange taps) */
+  int32_t gridtype[B200ITP_MAX_DIMS];
+  /* bounds(itp::BSplineInterpolation), b-splines.jl:141-158 */
+  double inner_lb[B200ITP_MAX_DIMS], inner_ub[B200ITP_MAX_DIMS];
+  int32_t inner_tag[B200ITP_MAX_DIMS];
+  /* ScaledInterpolation, scaling.jl:5-8,60-75,102-115 */
+  int32_t has_scale;
+  int32_t range_tag[B200ITP_MAX_DIMS]; /* eltype(ranges[d])                            */
+  double range_first[B200ITP_MAX_DIMS], range_step[B200ITP_MAX_DIMS];
+  double outer_lb[B200ITP_MAX_DIMS], outer_ub[B200ITP_MAX_DIMS];
+  int32_t outer_tag[B200ITP_MAX_DIMS];
+  /* Extrapolation / FilledExtrapolation */
+  int32_t etp_kind;
+  int32_t etp_lo[B200ITP_MAX_DIMS], etp_hi[B200ITP_MAX_DIMS]; /* per-axis, per-side flags */
+  int32_t fill_tag; /* Julia type of the fill value                                    */
+  double fill_value;
+} b200itp_desc;
+
+/*
+ * One axis of the prefilter: the factorisation `prefiltering_system` returns
+ * (cubic.jl:114-264, quadratic.jl:84-189): `M = Woodbury(lut!(dl,d,du), U, C, V)`
+ * or a bare LU.  All arrays are HOST pointers of element type `dtype`, read during
+ * the call.  U has unit columns e_{urow[j]}, V unit rows e_{vcol[j]}', Cp is W.Cp.
+ */
+typedef struct b200itp_axis_system {
+  int32_t dtype;
+  int32_t k;       /* Woodbury rank, 0 for a bare LU (quadratic.jl:84-89)               */
+  int64_t n;       /* size(M,1) == size(coefs, axis)                                   */
+  const void *dl;  /* n-1 : F.factors.dl (LU multipliers)                              */
+  const void *d;   /* n   : F.factors.d  (LU pivots)                                   */
+  const void *du;  /* n-1 : F.factors.du (unchanged super-diagonal)                    */
+  const int32_t *urow; /* k, 1-based                                                   */
+  const int32_t *vcol; /* k, 1-based                                                   */
+  const void *Cp;      /* k*k column-major                                             */
+} b200itp_axis_system;
+
+/* ---- library ---------------------------------------------------------------- */
+int b200itp_version(void);
+/* copies the text of the last error of the calling thread; returns its length */
+size_t b200itp_last_error(char *buf, size_t buflen);
+/* number of kernel launches issued by this process so far (bench.py's gpu_launches) */
+uint64_t b200itp_launch_count(void);
+
+/* ---- device memory helpers for hosts without their own CUDA binding ---------- */
+int b200itp_malloc(int dev, size_t bytes, void **out);
+int b200itp_free(int dev, void *p);
+int b200itp_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes, void *stream);
+int b200itp_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes, void *stream);
+int b200itp_sync(int dev, void *stream);
+
+/* ---- construction: interpolate(A, it) ---------------------------------------- */
+
+/* Replaces `copy_with_padding(TC, A, it)` (prefiltering.jl:17-28): `dst` has size
+ * src_size[d] + 2*pad[d]; borders are zero, the interior is `src`. Device pointers. */
+int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
+                              const int64_t *src_size, const int32_t *pad, void *stream);
+
+/* Host-side restatement of `prefiltering_system(T, TC, n, degree)` + `lut!`
+ * (cubic.jl:101-264, quadratic.jl:71-189, b-splines.jl:257) and of the
+ * `Woodbury(A,U,C,V)` constructor's `Cp = inv(inv(C) + V*(A\U))`.  Output buffers:
+ * dl[n-1], d[n], du[n-1], urow/vcol[B200ITP_MAX_WOODBURY], Cp[64]; *k receives the
+ * rank (0: bare LU).  Returns B200ITP_E_UNSUPPORTED when the reference has no
+ * method (e.g. Cubic(Reflect)), in which case the axis is left unfiltered
+ * (prefiltering.jl:124). */
+int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gridtype,
+                                void *dl, void *d, void *du, int32_t *k, int32_t *urow,
+                                int32_t *vcol, void *Cp);
+
+/* Replaces `A_ldiv_B_md!(dest, M, src, dim, b)` with dest === src and b == 0
+ * (filter1d.jl:8-85; called from prefiltering.jl:49-59,108-122): solves M x = v in
+ * place along `axis` (0-based) for every line of the device array `coefs`.
+ * One HBM read and one write of the array. */
+int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
+                           int axis, const b200itp_axis_system *sys, void *stream);
+
+/* Replaces `prefilter!(TW, ret, it)` (prefiltering.jl:49-59,108-122): all axes in
+ * order, systems assembled internally by b200itp_prefiltering_system. `size` is the
+ * padded size. Axes whose degree is LINEAR are skipped (prefiltering.jl:30). */
+int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
+                      const int32_t *degree, const int32_t *bc, const int32_t *gridtype,
+                      void *stream);
+
+/* ---- evaluation: itp.(xs...) and Interpolations.gradient.(Ref(itp), xs...) ---- */
+
+/* Replaces `Base.copy(::Broadcasted)` of `itp.(xs...)` / `gradient.(Ref(itp), xs...)`
+ * reached through src/gpu_support.jl:52-57,75-80; per element it computes what
+ * indexing.jl:5-9,25-31, scaling.jl:78-83,123-128, extrapolation.jl:50-58,71-82 and
+ * filled.jl:31-40,58-67 compute.
+ *   coefs      device, dtype d->coef_dtype, size d->size
+ *   coords     host array of d->ndims DEVICE pointers (SoA), dtype d->coord_dtype, nq each
+ *   out_value  device or NULL, nq elements of b200itp_out_dtype(d)
+ *   out_grad   device or NULL, nq*ndims elements, ndims contiguous per query (SVector)
+ *   first_oob  host out (may be NULL): smallest query index that throws, -1 if none.
+ *              When non-NULL the call synchronises `stream`.
+ *   dbg_index  device or NULL: nq*ndims int32, the base tap index per axis (bit-exact contract)
+ *   dbg_branch device or NULL: nq uint32 branch records (B200ITP_BR_*)
+ */
+int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+                 int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
+                 int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
+
+/* Element type of the outputs of b200itp_eval for this descriptor:
+ * promote(coordinate type after all wrappers, eltype(coefs)). <0 on invalid descriptor. */
+int b200itp_out_dtype(const b200itp_desc *d);
+
+/* Same as b200itp_eval (values only, no debug outputs), but first reorders the
+ * queries on the device by coarse coefficient tile so that neighbouring threads
+ * touch neighbouring coefficients (L2-friendly ordering); results are written in
+ * the original query order.  `scratch` is a device buffer of at least
+ * b200itp_eval_sorted_scratch_bytes(d, nq) bytes. */
+size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq);
+int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs,
+                        const void *const *coords, int64_t nq, void *out_value,
+                        int64_t *first_oob, void *scratch, size_t scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ITP_H */

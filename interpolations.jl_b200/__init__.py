@@ -1,0 +1,21 @@
+"""interpolations.jl_b200 — B200-native drop-in for the B-spline hot path of Interpolations.jl.
+
+Public names mirror the reference (src/Interpolations.jl:3-31).  The directory name contains a
+dot, so it is imported through `b200_loader.load()` (repo root) under the module name
+`interpolations_jl_b200`.
+"""
+from .flags import (BSpline, Cubic, Flat, Free, Line, Linear, Natural, OnCell, OnGrid, Periodic, Quadratic,
+                    Reflect, Throw)
+from .ranges import FloatRange, StepRange, UnitRange, jrange
+from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
+                   bounds, evaluate_debug, evaluate_sorted, extrapolate, gradient, interpolate, lbounds, out_dtype,
+                   prefilter_, scale, ubounds, value_and_gradient)
+from . import _lib
+
+__all__ = [
+    "BSpline", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
+    "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
+    "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_sorted",
+    "extrapolate", "gradient", "interpolate", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
+    "value_and_gradient",
+]

@@ -1,0 +1,555 @@
+"""Host-side mirror of the reference's operator interface for the B-spline hot path.
+
+Same names, argument meaning and error behaviour as Interpolations.jl v0.16.3:
+`interpolate`, `scale`, `extrapolate`, broadcast call `itp(xs...)`, `gradient`,
+`bounds/lbounds/ubounds`.  Everything numeric runs in libb200itp.so (hand-written
+sm_100a CUDA) through the C ABI of include/b200itp.h; this file only flattens the
+wrapper chain into the POD descriptor, exactly what the Julia glue does
+(INTEGRATION.md), and owns the device buffers (torch tensors).
+
+Reference: src/b-splines/b-splines.jl:74-78,141-158,167-193; src/scaling/scaling.jl:5-8,
+33-48,60-83,116-141; src/extrapolation/extrapolation.jl:1-4,45-58,71-82; filled.jl:1-40;
+src/gpu_support.jl:52-80 (the broadcast seam).
+
+Arrays follow Julia's convention: `A[i1, i2, ...]` with the FIRST index contiguous in
+device memory.  A numpy/torch array of shape (n1, ..., nN) is interpreted with that
+index order and stored column-major.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from .flags import (BC_FLAT, BC_LINE, BC_PERIODIC, BC_REFLECT, BC_THROW, CUBIC, ETP_FILL, ETP_FLAGS, ETP_NONE,
+                    F32, F64, LINEAR, ONCELL, ONGRID, QUADRATIC, TAG_EXACT, TAG_F32, TAG_F64, BoundaryCondition,
+                    BSpline, Flat, Free, Line, OnCell, OnGrid, Periodic, Reflect, Throw, iscomplete, needs_padding)
+from .ranges import AbstractRange, UnitRange
+
+MAX_DIMS = _lib.MAX_DIMS
+
+
+class BoundsError(IndexError):
+    """Raised where the reference throws BoundsError (indexing.jl:6, extrapolation.jl:115-129)."""
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_dtype(code):
+    return np.float32 if code == F32 else np.float64
+
+
+def _code_of(dtype) -> int:
+    dt = np.dtype(dtype)
+    if dt == np.dtype(np.float32):
+        return F32
+    if dt == np.dtype(np.float64):
+        return F64
+    raise TypeError(f"only Float32/Float64 reach the GPU kernels, got {dt}")
+
+
+def _tag_of_code(code):
+    return TAG_F32 if code == F32 else TAG_F64
+
+
+def _its_tuple(it, ndims) -> Tuple[BSpline, ...]:
+    if isinstance(it, BSpline):
+        return (it,) * ndims
+    its = tuple(it)
+    if len(its) != ndims or not all(isinstance(i, BSpline) for i in its):
+        raise TypeError("interpolation type must be a BSpline or one BSpline per dimension")
+    return its
+
+
+def stage_tags(D):
+    """Julia type (TAG_F32/TAG_F64) of each axis' coordinate after every wrapper, following the
+    promotion rules of `maxp/minp` (extrapolation.jl:153-156), `coordlookup` (scaling.jl:102-115) and
+    `clamp` (Interpolations.jl:450-452).  Returns (t_after_extrapolation, t_weights) per axis."""
+    t0 = TAG_F32 if D.coord_dtype == F32 else TAG_F64
+    t1, tw = [], []
+    for d in range(D.ndims):
+        t = t0
+        if D.etp_kind == ETP_FLAGS and not (D.etp_lo[d] == BC_THROW and D.etp_hi[d] == BC_THROW):
+            t = max(t, D.outer_tag[d] if D.has_scale else D.inner_tag[d])
+        t1.append(t)
+        if D.has_scale:
+            t = max(t, D.range_tag[d], D.inner_tag[d])
+        tw.append(t)
+    return t1, tw
+
+
+def out_dtype_code(D) -> int:
+    """promote(weights type of every axis, eltype(coefs) [, fill value]) -> F32/F64; mirrors
+    b200itp_out_dtype."""
+    _, tw = stage_tags(D)
+    t = max(tw + [TAG_F32 if D.coef_dtype == F32 else TAG_F64])
+    if D.etp_kind == ETP_FILL:
+        t = max(t, D.fill_tag)
+    return F32 if t == TAG_F32 else F64
+
+
+# ----------------------------------------------------------------------------- interpolants
+class AbstractInterpolation:
+    ndims: int
+
+    # -- pure host logic -------------------------------------------------------
+    def lbounds(self):
+        raise NotImplementedError
+
+    def ubounds(self):
+        raise NotImplementedError
+
+    def bounds(self):
+        """`bounds(itp)`: ((l1,u1), ..., (lN,uN))   (Interpolations.jl:155)."""
+        return tuple(zip(self.lbounds(), self.ubounds()))
+
+    def _chain(self):
+        """(bspline, scaled-or-None, extrapolation-or-None); only this wrapper order is on the hot path."""
+        raise NotImplementedError
+
+    def descriptor(self, coord_dtype) -> _lib.Desc:
+        bsp, sc, et = self._chain()
+        D = _lib.Desc()
+        N = bsp.ndims
+        D.ndims = N
+        D.coef_dtype = bsp.dtype_code
+        D.coord_dtype = _code_of(coord_dtype)
+        D.etp_pair_mask = 0
+        for d in range(N):
+            it = bsp.its[d]
+            D.size[d] = bsp.size[d]
+            D.parent_len[d] = bsp.parent_len[d]
+            D.coef_first[d] = 0 if needs_padding(it) else 1
+            D.degree[d] = it.degree.code
+            D.bc[d] = it.degree.bc.code
+            D.gridtype[d] = it.degree.bc.gt.code
+            lo, hi, tag = bsp._bound(d)
+            D.inner_lb[d], D.inner_ub[d], D.inner_tag[d] = lo, hi, tag
+        D.has_scale = 1 if sc is not None else 0
+        if sc is not None:
+            for d in range(N):
+                r = sc.ranges[d]
+                D.range_tag[d] = r.tag
+                D.range_first[d] = float(r.first)
+                D.range_step[d] = float(r.step)
+                lo, hi, tag = sc._bound(d)
+                D.outer_lb[d], D.outer_ub[d], D.outer_tag[d] = lo, hi, tag
+        D.etp_kind = ETP_NONE
+        if isinstance(et, Extrapolation):
+            D.etp_kind = ETP_FLAGS
+            for d in range(N):
+                f = et.flags[d]
+                if isinstance(f, tuple):
+                    D.etp_pair_mask |= 1 << d
+                    D.etp_lo[d], D.etp_hi[d] = f[0].code, f[1].code
+                else:
+                    D.etp_lo[d] = D.etp_hi[d] = f.code
+        elif isinstance(et, FilledExtrapolation):
+            D.etp_kind = ETP_FILL
+            D.fill_value = float(et.fillvalue)
+            D.fill_tag = et.fill_tag
+        return D
+
+    # -- evaluation through the C ABI -----------------------------------------
+    def __call__(self, *xs):
+        """Broadcast evaluation `itp.(xs...)` (gpu_support.jl:52-57)."""
+        return _broadcast_eval(self, xs, want_value=True, want_grad=False)[0]
+
+    def coefficients(self):
+        return self._chain()[0].coefs
+
+
+class BSplineInterpolation(AbstractInterpolation):
+    """Fields as in b-splines.jl:74-78: `coefs` (device, column-major, padded), `parentaxes`, `it`."""
+
+    def __init__(self, coefs, size, parent_len, its, device_index):
+        self.coefs = coefs  # 1-D torch CUDA tensor (column-major linearisation)
+        self.size = tuple(int(s) for s in size)
+        self.parent_len = tuple(int(s) for s in parent_len)
+        self.its = tuple(its)
+        self.ndims = len(self.size)
+        self.device_index = device_index
+        self.dtype_code = F32 if str(coefs.dtype).endswith("float32") else F64  # torch or numpy dtype
+
+    @property
+    def parentaxes(self):
+        return tuple(UnitRange(1, n) for n in self.parent_len)
+
+    def _bound(self, d):
+        """lbound/ubound (b-splines.jl:141-158): OnGrid -> (first, last) Ints; OnCell -> first-0.5, last+0.5 Float64."""
+        n = self.parent_len[d]
+        gt = self.its[d].degree.bc.gt
+        if isinstance(gt, OnCell):
+            return 0.5, n + 0.5, TAG_F64
+        return 1.0, float(n), TAG_EXACT
+
+    def lbounds(self):
+        return tuple(self._bound(d)[0] if self._bound(d)[2] != TAG_EXACT else int(self._bound(d)[0])
+                     for d in range(self.ndims))
+
+    def ubounds(self):
+        return tuple(self._bound(d)[1] if self._bound(d)[2] != TAG_EXACT else int(self._bound(d)[1])
+                     for d in range(self.ndims))
+
+    def _chain(self):
+        return self, None, None
+
+    def coefs_array(self) -> np.ndarray:
+        """Host copy of the coefficient array with Julia's shape (size) in Fortran order."""
+        return self.coefs.cpu().numpy().reshape(self.size, order="F")
+
+    def __repr__(self):
+        return f"BSplineInterpolation(size={self.parent_len}, coefs={self.size}, it={self.its})"
+
+
+class ScaledInterpolation(AbstractInterpolation):
+    """`scale(itp, ranges...)` (scaling.jl:5-8,33-48)."""
+
+    def __init__(self, itp: BSplineInterpolation, ranges: Sequence[AbstractRange]):
+        if not isinstance(itp, BSplineInterpolation):
+            raise ValueError("scale(): only scale(interpolate(...)) is on the B200 hot path "
+                             "(scale(extrapolate(...)) is not supported; use extrapolate(scale(...)))")
+        ranges = tuple(ranges)
+        if len(ranges) != itp.ndims:
+            raise ValueError("scale(): need one range per dimension")
+        for d, r in enumerate(ranges):  # check_ranges scaling.jl:39-48
+            if not isinstance(r, AbstractRange):
+                raise TypeError("scale(): ranges must be range objects (see ranges.jrange)")
+            if len(r) != itp.parent_len[d]:
+                raise ValueError(f"The range {r} is incommensurate with the corresponding axis 1:{itp.parent_len[d]}")
+            if not r.step > 0:
+                raise ValueError(f"The range {r} is in decreasing order; only ranges with positive steps are supported by scale().")
+        self.itp = itp
+        self.ranges = ranges
+        self.ndims = itp.ndims
+        self.device_index = itp.device_index
+
+    def _bound(self, d):
+        """scaling.jl:60-75,116: OnGrid -> first(r), last(r) in the range's eltype;
+        OnCell -> first(r) - boundstep(r), last(r) + boundstep(r), always Float64."""
+        r = self.ranges[d]
+        gt = self.itp.its[d].degree.bc.gt
+        if isinstance(gt, OnCell):
+            half = 0.5 * float(r.step)  # boundstep: r.step/2, 0.5*step(r) (Float64 arithmetic)
+            return float(r.first) - half, float(r.last) + half, TAG_F64
+        return float(r.first), float(r.last), r.tag
+
+    def lbounds(self):
+        return tuple(self._bound(d)[0] for d in range(self.ndims))
+
+    def ubounds(self):
+        return tuple(self._bound(d)[1] for d in range(self.ndims))
+
+    def _chain(self):
+        return self.itp, self, None
+
+    def __repr__(self):
+        return f"ScaledInterpolation({self.itp!r}, ranges={self.ranges})"
+
+
+def _normalise_etp_flags(et, ndims):
+    """ExtrapDimSpec (extrapolation.jl:15-19): one BC, a per-dim tuple, or per-dim (lo, hi) pairs."""
+    ok = (Throw, Flat, Line, Periodic, Reflect)
+
+    def one(f):
+        if isinstance(f, type) and issubclass(f, BoundaryCondition):
+            raise ValueError(f"cannot create a filled extrapolation with a type {f.__name__}, use a value of this "
+                             f"type instead (e.g., {f.__name__}())")
+        if isinstance(f, BoundaryCondition):
+            if not isinstance(f, ok):
+                raise ValueError(f"extrapolation scheme {f!r} is not supported")
+            return f
+        if isinstance(f, tuple) and len(f) == 2 and all(isinstance(g, ok) for g in f):
+            return (f[0], f[1])
+        raise TypeError(f"bad extrapolation flag {f!r}")
+
+    if isinstance(et, BoundaryCondition):
+        return (one(et),) * ndims
+    if isinstance(et, tuple):
+        if len(et) != ndims:
+            raise ValueError("extrapolate(): need one scheme per dimension")
+        return tuple(one(f) for f in et)
+    return None
+
+
+class Extrapolation(AbstractInterpolation):
+    """`extrapolate(itp, scheme)` (extrapolation.jl:1-4,45-46)."""
+
+    def __init__(self, itp, flags):
+        self.itp = itp
+        self.flags = flags
+        self.ndims = itp.ndims
+        self.device_index = itp.device_index
+
+    def lbounds(self):
+        return self.itp.lbounds()
+
+    def ubounds(self):
+        return self.itp.ubounds()
+
+    def _chain(self):
+        b, s, _ = self.itp._chain()
+        return b, s, self
+
+    def __repr__(self):
+        return f"Extrapolation({self.itp!r}, {self.flags})"
+
+
+class FilledExtrapolation(AbstractInterpolation):
+    """`extrapolate(itp, fillvalue)` (filled.jl:1-4,29)."""
+
+    def __init__(self, itp, fillvalue):
+        self.itp = itp
+        self.fillvalue = fillvalue
+        if isinstance(fillvalue, (bool, int, np.integer)):
+            self.fill_tag = TAG_EXACT
+        elif isinstance(fillvalue, np.float32):
+            self.fill_tag = TAG_F32
+        else:
+            self.fill_tag = TAG_F64
+        self.ndims = itp.ndims
+        self.device_index = itp.device_index
+
+    def lbounds(self):
+        return self.itp.lbounds()
+
+    def ubounds(self):
+        return self.itp.ubounds()
+
+    def _chain(self):
+        b, s, _ = self.itp._chain()
+        return b, s, self
+
+    def __repr__(self):
+        return f"FilledExtrapolation({self.itp!r}, {self.fillvalue!r})"
+
+
+# ----------------------------------------------------------------------------- constructors
+def _device_index(device) -> int:
+    torch = _torch()
+    if device is None:
+        return torch.cuda.current_device()
+    return torch.device(device).index or 0
+
+
+def _to_colmajor_device(A, device_index):
+    """(flat column-major CUDA tensor, shape).  Integer arrays are converted like `tcoef` does
+    (b-splines.jl:229-233): Float32 stays Float32, integers become Float64."""
+    torch = _torch()
+    dev = torch.device("cuda", device_index)
+    if isinstance(A, np.ndarray):
+        if A.dtype not in (np.float32, np.float64):
+            A = A.astype(np.float64)
+        shape = A.shape
+        flat = np.ascontiguousarray(A.reshape(-1, order="F"))
+        return torch.from_numpy(flat).to(dev), shape
+    if isinstance(A, torch.Tensor):
+        if A.dtype not in (torch.float32, torch.float64):
+            A = A.to(torch.float64)
+        shape = tuple(A.shape)
+        t = A.to(dev)
+        if t.dim() > 1:
+            t = t.permute(*reversed(range(t.dim()))).contiguous()
+        flat = t.reshape(-1)
+        if flat.data_ptr() == A.data_ptr():  # never alias the caller's memory: the prefilter is in place
+            flat = flat.clone()
+        return flat, shape
+    return _to_colmajor_device(np.asarray(A), device_index)
+
+
+def _stream_ptr(device_index):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def prefilter_(coefs, size, its, device_index):
+    """`prefilter!(TW, ret, it)` on a padded device array (prefiltering.jl:49-59,108-122)."""
+    L = _lib.lib()
+    N = len(size)
+    sz = (C.c_int64 * N)(*size)
+    deg = (C.c_int32 * N)(*[it.degree.code for it in its])
+    bc = (C.c_int32 * N)(*[it.degree.bc.code for it in its])
+    gt = (C.c_int32 * N)(*[it.degree.bc.gt.code for it in its])
+    code = F32 if str(coefs.dtype).endswith("float32") else F64
+    rc = L.b200itp_prefilter(device_index, C.c_void_p(coefs.data_ptr()), code, N, sz, deg, bc, gt,
+                             _stream_ptr(device_index))
+    _lib.check(rc, "b200itp_prefilter")
+    return coefs
+
+
+def interpolate(A, it, device=None) -> BSplineInterpolation:
+    """`interpolate(A, it)` (b-splines.jl:167-170,191-193): pad (`copy_with_padding`), prefilter on
+    the GPU, wrap.  `A`: numpy array or torch tensor, shape (n1..nN) in Julia index order."""
+    torch = _torch()
+    L = _lib.lib()
+    dev = _device_index(device)
+    src, shape = _to_colmajor_device(A, dev)
+    N = len(shape)
+    if not 1 <= N <= MAX_DIMS:
+        raise ValueError(f"1..{MAX_DIMS} dimensions are supported, got {N}")
+    its = _its_tuple(it, N)
+    for i in its:
+        if not iscomplete(i):
+            raise ValueError(f"OnGrid/OnCell is not supplied for some of the interpolation modes in {it}")
+    for d in range(N):  # is_singleton_ok b-splines.jl:114-121
+        if shape[d] == 1:
+            raise ValueError(f"size {shape} is inconsistent with {it}, use NoInterp along singleton dimensions")
+    pad = [1 if needs_padding(i) else 0 for i in its]
+    psize = tuple(shape[d] + 2 * pad[d] for d in range(N))
+    code = F32 if src.dtype == torch.float32 else F64
+    with torch.cuda.device(dev):
+        if any(pad):
+            coefs = torch.empty(int(np.prod(psize)), dtype=src.dtype, device=src.device)
+            rc = L.b200itp_copy_with_padding(dev, C.c_void_p(src.data_ptr()), C.c_void_p(coefs.data_ptr()), code, N,
+                                             (C.c_int64 * N)(*shape), (C.c_int32 * N)(*pad), _stream_ptr(dev))
+            _lib.check(rc, "b200itp_copy_with_padding")
+        else:
+            coefs = src
+        prefilter_(coefs, psize, its, dev)
+    return BSplineInterpolation(coefs, psize, shape, its, dev)
+
+
+def scale(itp, *ranges) -> ScaledInterpolation:
+    """`scale(itp, ranges...)` (scaling.jl:33-37)."""
+    if len(ranges) == 1 and isinstance(ranges[0], (tuple, list)):
+        ranges = tuple(ranges[0])
+    return ScaledInterpolation(itp, ranges)
+
+
+def extrapolate(itp, et) -> Union[Extrapolation, FilledExtrapolation]:
+    """`extrapolate(itp, scheme)` / `extrapolate(itp, fillvalue)` (extrapolation.jl:45-46, filled.jl:29)."""
+    if isinstance(itp, (Extrapolation, FilledExtrapolation)):
+        raise ValueError("extrapolate(): nested extrapolation is not on the B200 hot path")
+    flags = _normalise_etp_flags(et, itp.ndims)
+    if flags is not None:
+        return Extrapolation(itp, flags)
+    if isinstance(et, (bool, int, float, np.integer, np.floating)):
+        return FilledExtrapolation(itp, et)
+    raise TypeError(f"extrapolate(): bad scheme {et!r}")
+
+
+# ----------------------------------------------------------------------------- evaluation
+def _prepare_coords(itp, xs):
+    """Broadcast the N coordinate arguments (numpy broadcasting == Julia's `itp.(xs, ys')`) and put
+    them on the device as contiguous 1-D arrays of one float type."""
+    torch = _torch()
+    N = itp.ndims
+    if len(xs) != N:
+        raise ValueError(f"expected {N} coordinate arguments, got {len(xs)}")
+    dev = torch.device("cuda", itp.device_index)
+    ts = []
+    for x in xs:
+        if isinstance(x, torch.Tensor):
+            t = x
+        else:
+            a = np.asarray(x)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        ts.append(t.to(dev))
+    dt = torch.float64 if any(t.dtype == torch.float64 for t in ts) else torch.float32
+    ts = [t.to(dt) for t in ts]
+    shape = torch.broadcast_shapes(*[t.shape for t in ts])
+    ts = [t.expand(shape).contiguous().reshape(-1) for t in ts]
+    return ts, tuple(shape), dt
+
+
+def out_dtype(itp, coord_dtype):
+    """Element type of `itp.(xs...)`: promote(coordinate type after all wrappers, eltype(coefs))."""
+    D = itp.descriptor(coord_dtype)
+    code = _lib.lib().b200itp_out_dtype(C.byref(D))
+    if code < 0:
+        raise ValueError("invalid descriptor")
+    return _np_dtype(code)
+
+
+def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=None):
+    torch = _torch()
+    L = _lib.lib()
+    coords, shape, dt = _prepare_coords(itp, xs)
+    nq = coords[0].numel() if coords else 0
+    N = itp.ndims
+    npdt = np.float32 if dt == torch.float32 else np.float64
+    D = itp.descriptor(npdt)
+    ocode = L.b200itp_out_dtype(C.byref(D))
+    if ocode < 0:
+        raise ValueError("invalid descriptor")
+    odt = torch.float32 if ocode == F32 else torch.float64
+    dev = itp.device_index
+    coefs = itp.coefficients()
+    with torch.cuda.device(dev):
+        tdev = coefs.device
+        val = torch.empty(nq, dtype=odt, device=tdev) if want_value else None
+        grad = torch.empty(nq * N, dtype=odt, device=tdev) if want_grad else None
+        dbg_i = torch.empty(nq * N, dtype=torch.int32, device=tdev) if debug else None
+        dbg_b = torch.empty(nq, dtype=torch.int32, device=tdev) if debug else None
+        ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in coords])
+        foob = C.c_int64(-1)
+
+        def p(t):
+            return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(None)
+
+        if nq > 0:
+            if sorted_queries and want_value and not want_grad and not debug:
+                nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq)
+                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=tdev)
+                rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), C.byref(foob), p(scratch),
+                                           nbytes, _stream_ptr(dev))
+                _lib.check(rc, "b200itp_eval_sorted")
+            else:
+                rc = L.b200itp_eval(dev, C.byref(D), p(coefs), ptrs, nq, p(val), p(grad), C.byref(foob), p(dbg_i),
+                                    p(dbg_b), _stream_ptr(dev))
+                _lib.check(rc, "b200itp_eval")
+    if foob.value >= 0:
+        q = foob.value
+        xq = tuple(float(c[q].item()) for c in coords)
+        raise BoundsError(f"attempt to access {itp!r} at index {xq}")
+    out = [None, None, None, None]
+    if want_value:
+        out[0] = val.reshape(shape)
+    if want_grad:
+        out[1] = grad.reshape(shape + (N,))
+    if debug:
+        out[2] = dbg_i.reshape(shape + (N,))
+        out[3] = dbg_b.reshape(shape)
+    return out
+
+
+def gradient(itp, *xs):
+    """`Interpolations.gradient.(Ref(itp), xs...)`: result has a trailing axis of length N holding the
+    SVector components contiguously (indexing.jl:25-31, scaling.jl:123-128, extrapolation.jl:71-82)."""
+    return _broadcast_eval(itp, xs, want_value=False, want_grad=True)[1]
+
+
+def value_and_gradient(itp, *xs):
+    r = _broadcast_eval(itp, xs, want_value=True, want_grad=True)
+    return r[0], r[1]
+
+
+def evaluate_debug(itp, *xs, want_grad=False):
+    """value (+gradient) plus the bit-exact contract: base tap index per axis and branch record."""
+    return _broadcast_eval(itp, xs, want_value=True, want_grad=want_grad, debug=True)
+
+
+def evaluate_sorted(itp, *xs):
+    """`itp.(xs...)` with on-device L2-friendly query reordering (results in the caller's order)."""
+    return _broadcast_eval(itp, xs, want_value=True, want_grad=False, sorted_queries=True)[0]
+
+
+def bounds(itp):
+    return itp.bounds()
+
+
+def lbounds(itp):
+    return itp.lbounds()
+
+
+def ubounds(itp):
+    return itp.ubounds()
