@@ -29,6 +29,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define B200ITP_API __attribute__((visibility("default")))
+#else
+#define B200ITP_API
+#endif
+
 #define B200ITP_VERSION 100
 #define B200ITP_MAX_DIMS 4
 #define B200ITP_MAX_WOODBURY 8
@@ -136,24 +142,24 @@ typedef struct b200itp_axis_system {
 } b200itp_axis_system;
 
 /* ---- library ---------------------------------------------------------------- */
-int b200itp_version(void);
+B200ITP_API int b200itp_version(void);
 /* copies the text of the last error of the calling thread; returns its length */
-size_t b200itp_last_error(char *buf, size_t buflen);
+B200ITP_API size_t b200itp_last_error(char *buf, size_t buflen);
 /* number of kernel launches issued by this process so far (bench.py's gpu_launches) */
-uint64_t b200itp_launch_count(void);
+B200ITP_API uint64_t b200itp_launch_count(void);
 
 /* ---- device memory helpers for hosts without their own CUDA binding ---------- */
-int b200itp_malloc(int dev, size_t bytes, void **out);
-int b200itp_free(int dev, void *p);
-int b200itp_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes, void *stream);
-int b200itp_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes, void *stream);
-int b200itp_sync(int dev, void *stream);
+B200ITP_API int b200itp_malloc(int dev, size_t bytes, void **out);
+B200ITP_API int b200itp_free(int dev, void *p);
+B200ITP_API int b200itp_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes, void *stream);
+B200ITP_API int b200itp_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes, void *stream);
+B200ITP_API int b200itp_sync(int dev, void *stream);
 
 /* ---- construction: interpolate(A, it) ---------------------------------------- */
 
 /* Replaces `copy_with_padding(TC, A, it)` (prefiltering.jl:17-28): `dst` has size
  * src_size[d] + 2*pad[d]; borders are zero, the interior is `src`. Device pointers. */
-int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
+B200ITP_API int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
                               const int64_t *src_size, const int32_t *pad, void *stream);
 
 /* Host-side restatement of `prefiltering_system(T, TC, n, degree)` + `lut!`
@@ -163,7 +169,7 @@ int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, in
  * rank (0: bare LU).  Returns B200ITP_E_UNSUPPORTED when the reference has no
  * method (e.g. Cubic(Reflect)), in which case the axis is left unfiltered
  * (prefiltering.jl:124). */
-int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gridtype,
+B200ITP_API int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gridtype,
                                 void *dl, void *d, void *du, int32_t *k, int32_t *urow,
                                 int32_t *vcol, void *Cp);
 
@@ -171,13 +177,13 @@ int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gr
  * (filter1d.jl:8-85; called from prefiltering.jl:49-59,108-122): solves M x = v in
  * place along `axis` (0-based) for every line of the device array `coefs`.
  * One HBM read and one write of the array. */
-int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
+B200ITP_API int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
                            int axis, const b200itp_axis_system *sys, void *stream);
 
 /* Replaces `prefilter!(TW, ret, it)` (prefiltering.jl:49-59,108-122): all axes in
  * order, systems assembled internally by b200itp_prefiltering_system. `size` is the
  * padded size. Axes whose degree is LINEAR are skipped (prefiltering.jl:30). */
-int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
+B200ITP_API int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
                       const int32_t *degree, const int32_t *bc, const int32_t *gridtype,
                       void *stream);
 
@@ -196,21 +202,21 @@ int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t 
  *   dbg_index  device or NULL: nq*ndims int32, the base tap index per axis (bit-exact contract)
  *   dbg_branch device or NULL: nq uint32 branch records (B200ITP_BR_*)
  */
-int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
                  int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
                  int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
 
 /* Element type of the outputs of b200itp_eval for this descriptor:
  * promote(coordinate type after all wrappers, eltype(coefs)). <0 on invalid descriptor. */
-int b200itp_out_dtype(const b200itp_desc *d);
+B200ITP_API int b200itp_out_dtype(const b200itp_desc *d);
 
 /* Same as b200itp_eval (values only, no debug outputs), but first reorders the
  * queries on the device by coarse coefficient tile so that neighbouring threads
  * touch neighbouring coefficients (L2-friendly ordering); results are written in
  * the original query order.  `scratch` is a device buffer of at least
  * b200itp_eval_sorted_scratch_bytes(d, nq) bytes. */
-size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq);
-int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs,
+B200ITP_API size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq);
+B200ITP_API int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs,
                         const void *const *coords, int64_t nq, void *out_value,
                         int64_t *first_oob, void *scratch, size_t scratch_bytes, void *stream);
 

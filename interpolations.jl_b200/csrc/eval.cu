@@ -1,0 +1,245 @@
+// Host side of b200itp_eval / b200itp_out_dtype / b200itp_eval_sorted (include/b200itp.h):
+// validates the descriptor, derives the Julia promotion chain, fills EvalParams and launches the
+// kernels of eval.cuh.
+#include "eval.cuh"
+
+#include <climits>
+#include <cmath>
+
+namespace b200itp {
+
+template <typename TC, typename TX, typename TW>
+int launch_eval_combo(const EvalParams &P, int deg, int mode, int blocks, cudaStream_t st);
+
+namespace {
+
+struct Chain {
+  int t0;          // coordinate tag
+  int t1[4];       // after the extrapolation stage
+  int t2[4];       // after coordlookup
+  int tw[4];       // weights type
+  int out_f64;
+  bool homogeneous;
+  int e_wide, s_wide, w_wide;
+};
+
+inline int tmax(int a, int b) { return a > b ? a : b; }
+
+// Julia's promotion through maxp/minp (extrapolation.jl:153-156), coordlookup (scaling.jl:102-115) and
+// clamp (Interpolations.jl:450-452)
+int derive_chain(const b200itp_desc *D, Chain &c) {
+  if (!D) return B200ITP_E_BADARG;
+  if (D->ndims < 1 || D->ndims > B200ITP_MAX_DIMS) return B200ITP_E_BADARG;
+  if ((D->coef_dtype != B200ITP_F32 && D->coef_dtype != B200ITP_F64) ||
+      (D->coord_dtype != B200ITP_F32 && D->coord_dtype != B200ITP_F64))
+    return B200ITP_E_DTYPE;
+  c.t0 = D->coord_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
+  int tacc = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
+  c.homogeneous = true;
+  for (int d = 0; d < D->ndims; ++d) {
+    int t = c.t0;
+    if (D->etp_kind == B200ITP_ETP_FLAGS &&
+        !(D->etp_lo[d] == B200ITP_BC_THROW && D->etp_hi[d] == B200ITP_BC_THROW))
+      t = tmax(t, D->has_scale ? D->outer_tag[d] : D->inner_tag[d]);
+    c.t1[d] = t;
+    if (D->has_scale) t = tmax(t, D->range_tag[d]);
+    c.t2[d] = t;
+    if (D->has_scale) t = tmax(t, D->inner_tag[d]);
+    c.tw[d] = t;
+    tacc = tmax(tacc, t);
+    if (c.t1[d] != c.t1[0] || c.t2[d] != c.t2[0] || c.tw[d] != c.tw[0]) c.homogeneous = false;
+  }
+  if (D->etp_kind == B200ITP_ETP_FILL) tacc = tmax(tacc, D->fill_tag);
+  c.out_f64 = tacc == B200ITP_TAG_F64;
+  c.e_wide = c.t1[0] == B200ITP_TAG_F64;
+  c.s_wide = c.t2[0] == B200ITP_TAG_F64;
+  c.w_wide = c.tw[0] == B200ITP_TAG_F64;
+  return 0;
+}
+
+inline double round_tag(int tag, double v) { return tag == B200ITP_TAG_F32 ? (double)(float)v : v; }
+
+int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const void *const *coords, int64_t nq,
+                void *out_value, void *out_grad, int32_t *dbg_index, uint32_t *dbg_branch,
+                unsigned long long *first_oob_dev, EvalParams &P) {
+  memset(&P, 0, sizeof P);
+  P.ndims = D->ndims;
+  long long stride = 1;
+  for (int d = 0; d < D->ndims; ++d) {
+    if (D->size[d] < 1 || D->parent_len[d] < 1) B200_FAIL(B200ITP_E_SIZE, "eval: empty axis %d", d);
+    if (D->parent_len[d] > INT_MAX / 2) B200_FAIL(B200ITP_E_SIZE, "eval: axis %d too long", d);
+    const int deg = D->degree[d];
+    if (deg < B200ITP_LINEAR || deg > B200ITP_CUBIC) B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: degree %d on axis %d is not on the hot path", deg, d);
+    const int cf = D->coef_first[d];
+    if (cf != 0 && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: coef_first must be 0 or 1");
+    const int64_t need = D->parent_len[d] + (cf == 0 ? 2 : 0);
+    if (D->size[d] != need) B200_FAIL(B200ITP_E_SIZE, "eval: size[%d]=%lld inconsistent with parent length %lld", d, (long long)D->size[d], (long long)D->parent_len[d]);
+    if (D->bc[d] == B200ITP_BC_PERIODIC && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: periodic axes are unpadded");
+    P.n[d] = (int)D->parent_len[d];
+    P.coef_first[d] = cf;
+    P.degree[d] = deg;
+    P.periodic[d] = D->bc[d] == B200ITP_BC_PERIODIC;
+    P.stride[d] = stride;
+    stride *= D->size[d];
+    const double lo = D->has_scale ? D->outer_lb[d] : D->inner_lb[d];
+    const double hi = D->has_scale ? D->outer_ub[d] : D->inner_ub[d];
+    const int bt = D->has_scale ? D->outer_tag[d] : D->inner_tag[d];
+    if (!(lo < hi)) B200_FAIL(B200ITP_E_BADARG, "eval: empty bounds on axis %d", d);
+    P.lb[d] = lo;
+    P.ub[d] = hi;
+    P.span[d] = round_tag(bt, hi - lo);
+    P.span2[d] = round_tag(bt, 2.0 * P.span[d]);
+    P.ub2[d] = round_tag(bt, 2.0 * hi);
+    P.inner_lb[d] = D->inner_lb[d];
+    P.inner_ub[d] = D->inner_ub[d];
+    if (D->has_scale) {
+      if (!(D->range_step[d] > 0)) B200_FAIL(B200ITP_E_BADARG, "eval: ranges must have positive steps (scaling.jl:48)");
+      P.rfirst[d] = D->range_first[d];
+      P.rstep[d] = D->range_step[d];
+    }
+    P.etp_lo[d] = D->etp_lo[d];
+    P.etp_hi[d] = D->etp_hi[d];
+    if (D->etp_kind == B200ITP_ETP_FLAGS) {
+      for (int f : {D->etp_lo[d], D->etp_hi[d]})
+        if (f != B200ITP_BC_THROW && f != B200ITP_BC_FLAT && f != B200ITP_BC_LINE && f != B200ITP_BC_PERIODIC &&
+            f != B200ITP_BC_REFLECT)
+          B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: extrapolation flag %d is not supported", f);
+      if (D->etp_lo[d] == B200ITP_BC_LINE || D->etp_hi[d] == B200ITP_BC_LINE) P.any_line = 1;
+      if (!((D->etp_pair_mask >> d) & 1) && D->etp_lo[d] != D->etp_hi[d])
+        B200_FAIL(B200ITP_E_BADARG, "eval: axis %d has two different flags but is not marked as a pair", d);
+    }
+  }
+  P.total = stride;
+  P.vec_ok = ((uintptr_t)coefs % 16) == 0;
+  P.has_scale = D->has_scale != 0;
+  P.e_wide = c.e_wide;
+  P.s_wide = c.s_wide;
+  P.etp_kind = D->etp_kind;
+  P.pair_mask = D->etp_kind == B200ITP_ETP_FLAGS ? D->etp_pair_mask : 0;
+  P.fill = D->fill_value;
+  P.out_f64 = c.out_f64;
+  for (int d = 0; d < D->ndims; ++d) P.coords[d] = coords[d];
+  P.coefs = coefs;
+  P.out_value = out_value;
+  P.out_grad = out_grad;
+  P.dbg_index = dbg_index;
+  P.dbg_branch = dbg_branch;
+  P.first_oob = first_oob_dev;
+  P.nq = nq;
+  P.perm = nullptr;
+  return 0;
+}
+
+int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mode, int blocks, cudaStream_t st) {
+  int deg = D->degree[0];
+  for (int d = 1; d < D->ndims; ++d)
+    if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
+  const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
+  int rc;
+  if (cf32 && xf32 && wf32)
+    rc = launch_eval_combo<float, float, float>(P, deg, mode, blocks, st);
+  else if (cf32 && xf32 && !wf32)
+    rc = launch_eval_combo<float, float, double>(P, deg, mode, blocks, st);
+  else if (cf32 && !xf32)
+    rc = launch_eval_combo<float, double, double>(P, deg, mode, blocks, st);
+  else if (!cf32 && !xf32)
+    rc = launch_eval_combo<double, double, double>(P, deg, mode, blocks, st);
+  else if (!cf32 && xf32 && wf32)
+    rc = launch_eval_combo<double, float, float>(P, deg, mode, blocks, st);
+  else
+    rc = launch_eval_combo<double, float, double>(P, deg, mode, blocks, st);
+  if (rc) B200_FAIL(rc, "eval: no kernel for ndims=%d degree=%d", D->ndims, deg);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+}  // namespace b200itp
+
+using namespace b200itp;
+
+extern "C" int b200itp_out_dtype(const b200itp_desc *d) {
+  Chain c;
+  if (derive_chain(d, c)) return -1;
+  return c.out_f64 ? B200ITP_F64 : B200ITP_F32;
+}
+
+static int eval_common(int dev, const b200itp_desc *D, const void *coefs, const void *const *coords, int64_t nq,
+                       void *out_value, void *out_grad, int64_t *first_oob, int32_t *dbg_index, uint32_t *dbg_branch,
+                       const int *perm, cudaStream_t st) {
+  if (!D || !coefs || !coords) B200_FAIL(B200ITP_E_BADARG, "eval: null pointer");
+  if (nq < 0) B200_FAIL(B200ITP_E_BADARG, "eval: negative query count");
+  Chain c;
+  int rc = derive_chain(D, c);
+  if (rc) B200_FAIL(rc, "eval: invalid descriptor");
+  if (!c.homogeneous)
+    B200_FAIL(B200ITP_E_UNSUPPORTED,
+              "eval: Float32 coordinates that are widened to Float64 on some axes only (mixed OnGrid/OnCell or mixed "
+              "range element types) are not on the hot path; pass Float64 coordinates");
+  if (D->etp_kind != B200ITP_ETP_NONE && D->etp_kind != B200ITP_ETP_FLAGS && D->etp_kind != B200ITP_ETP_FILL)
+    B200_FAIL(B200ITP_E_BADARG, "eval: bad etp_kind");
+  if (out_grad && D->etp_kind == B200ITP_ETP_FLAGS && D->etp_pair_mask)
+    B200_FAIL(B200ITP_E_UNSUPPORTED,
+              "eval: gradient with per-side extrapolation pairs has no method in the reference (extrapolation.jl:184-185)");
+  for (int d = 0; d < D->ndims; ++d)
+    if (!coords[d]) B200_FAIL(B200ITP_E_BADARG, "eval: null coordinate array %d", d);
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval: cannot select device %d", dev);
+  if (first_oob) *first_oob = -1;
+  if (nq == 0 || (!out_value && !out_grad)) return 0;
+
+  void *flag = nullptr;
+  rc = scratch_get(dev, 2, 256, &flag);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
+
+  EvalParams P;
+  const int blocks = (int)std::min<int64_t>((nq + 255) / 256, (int64_t)sm_count(dev) * 32);
+  if (out_value) {
+    rc = fill_params(D, c, coefs, coords, nq, out_value, nullptr, dbg_index, dbg_branch, (unsigned long long *)flag, P);
+    if (rc) return rc;
+    P.perm = perm;
+    rc = dispatch(D, c, P, 0, blocks, st);
+    if (rc) return rc;
+  }
+  if (out_grad) {
+    // when both outputs are requested the debug record describes the value evaluation
+    rc = fill_params(D, c, coefs, coords, nq, nullptr, out_grad, out_value ? nullptr : dbg_index,
+                     out_value ? nullptr : dbg_branch, (unsigned long long *)flag, P);
+    if (rc) return rc;
+    P.perm = perm;
+    rc = dispatch(D, c, P, 1, blocks, st);
+    if (rc) return rc;
+  }
+  if (first_oob) {
+    unsigned long long h = ~0ULL;
+    B200_CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    *first_oob = h == ~0ULL ? -1 : (int64_t)h;
+  }
+  return 0;
+}
+
+extern "C" int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords, int64_t nq,
+                            void *out_value, void *out_grad, int64_t *first_oob, int32_t *dbg_index,
+                            uint32_t *dbg_branch, void *stream) {
+  return eval_common(dev, d, coefs, coords, nq, out_value, out_grad, first_oob, dbg_index, dbg_branch, nullptr,
+                     (cudaStream_t)stream);
+}
+
+extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
+  (void)d;
+  return nq > 0 ? (size_t)nq * 4 * 3 + 4096 * 8 : 0;
+}
+
+extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+                                   int64_t nq, void *out_value, int64_t *first_oob, void *scratch,
+                                   size_t scratch_bytes, void *stream) {
+  // v1: the ordering pass is not wired in yet; results are identical either way
+  (void)scratch;
+  (void)scratch_bytes;
+  return eval_common(dev, d, coefs, coords, nq, out_value, nullptr, first_oob, nullptr, nullptr, nullptr,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,584 @@
+// Evaluation of `extrapolate(scale(interpolate(A, BSpline(...)), ranges...), et)` at scattered
+// query points: `itp.(xs...)` and `Interpolations.gradient.(Ref(itp), xs...)`.
+//
+// One thread per query computes, entirely in registers, what the reference computes per element of
+// the broadcast (paths relative to the Interpolations.jl v0.16.3 checkout):
+//   extrapolation  src/extrapolation/extrapolation.jl:50-58,71-82,106-185, filled.jl:31-40,58-67
+//   scaling        src/scaling/scaling.jl:78-83,102-141 ; clamp src/Interpolations.jl:450-452
+//   positions      src/b-splines/cubic.jl:40-61, quadratic.jl:39-43,57-60, linear.jl:43-54,
+//                  src/b-splines/indexing.jl:168-199, src/utils.jl:7,40
+//   weights        cubic.jl:63-77, quadratic.jl:45-53, linear.jl:56-57
+//   reduction      src/Interpolations.jl:304-316 (axis 1 outermost, taps accumulated w*v + acc)
+// The arithmetic follows the reference operation by operation in the reference's types (this file is
+// compiled with -fmad=false: Julia never contracts a*b+c), so stencil indices, branch choices AND
+// values are bit-identical to the CPU path given the same coefficients.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200itp {
+
+struct EvalParams {
+  int ndims;
+  int n[4];           // parent length per axis
+  int coef_first[4];  // 0 padded, 1 unpadded
+  int degree[4];
+  int periodic[4];
+  long long stride[4];  // element stride of each axis in the coefficient array
+  long long total;      // number of coefficients
+  int vec_ok;           // coefficient base pointer is 16-byte aligned
+  // bounds seen by the outermost wrapper (scaled bounds if has_scale, else the B-spline's)
+  double lb[4], ub[4];
+  double span[4], span2[4], ub2[4];  // u-l, 2(u-l), 2u rounded in the bounds' own Julia type
+  // scale
+  int has_scale;
+  double rfirst[4], rstep[4];
+  double inner_lb[4], inner_ub[4];
+  // where a Float32 coordinate becomes Float64 (only meaningful when TX=float, TW=double)
+  int e_wide;  // extrapolation stage runs in TW
+  int s_wide;  // coordlookup runs in TW
+  // extrapolation
+  int etp_kind;
+  int etp_lo[4], etp_hi[4];
+  int pair_mask;
+  int any_line;
+  double fill;
+  int out_f64;  // output element type
+  // buffers
+  const void *coords[4];
+  const void *coefs;
+  void *out_value;
+  void *out_grad;
+  int *dbg_index;
+  unsigned *dbg_branch;
+  unsigned long long *first_oob;
+  long long nq;
+  const int *perm;  // optional: query q reads coordinates / writes results at perm[q]
+};
+
+template <typename A, typename B>
+struct Promote {
+  using type = double;
+};
+template <>
+struct Promote<float, float> {
+  using type = float;
+};
+
+template <typename S>
+__device__ __forceinline__ S s_floor(S x) {
+  return floor(x);
+}
+template <>
+__device__ __forceinline__ float s_floor<float>(float x) {
+  return floorf(x);
+}
+template <typename S>
+__device__ __forceinline__ S s_ceil(S x) {
+  return ceil(x);
+}
+template <>
+__device__ __forceinline__ float s_ceil<float>(float x) {
+  return ceilf(x);
+}
+template <typename S>
+__device__ __forceinline__ S s_fmod(S a, S b) {
+  return fmod(a, b);
+}
+template <>
+__device__ __forceinline__ float s_fmod<float>(float a, float b) {
+  return fmodf(a, b);
+}
+
+// Julia `mod(a, b)` for b > 0: rem, then shifted into [0, b)   (Base.mod for floats)
+template <typename S>
+__device__ __forceinline__ S julia_mod_pos(S a, S b) {
+  S r = s_fmod<S>(a, b);
+  if (r < S(0)) r = r + b;
+  return r;
+}
+
+// periodic / reflect (extrapolation.jl:158-163)
+template <typename S>
+__device__ __forceinline__ S etp_periodic(const EvalParams &P, int d, S y) {
+  const S l = (S)P.lb[d];
+  return julia_mod_pos<S>(y - l, (S)P.span[d]) + l;
+}
+template <typename S>
+__device__ __forceinline__ S etp_reflect(const EvalParams &P, int d, S y) {
+  const S l = (S)P.lb[d], u = (S)P.ub[d];
+  const S yr = julia_mod_pos<S>(y - l, (S)P.span2[d]) + l;
+  return yr > u ? (S)P.ub2[d] - yr : yr;
+}
+
+// inbounds_index (extrapolation.jl:106-151) in type S; returns true when BoundsError
+template <typename S>
+__device__ __forceinline__ bool etp_inbounds(const EvalParams &P, int d, S x, S &xs) {
+  const S l = (S)P.lb[d], u = (S)P.ub[d];
+  const int flo = P.etp_lo[d], fhi = P.etp_hi[d];
+  const bool pair = (P.pair_mask >> d) & 1;
+  xs = x;
+  if (!pair) {
+    if (flo == B200ITP_BC_THROW) return !(l <= x && x <= u);
+    if (flo == B200ITP_BC_PERIODIC) {
+      xs = etp_periodic<S>(P, d, x);
+      return false;
+    }
+    if (flo == B200ITP_BC_REFLECT) {
+      xs = etp_reflect<S>(P, d, x);
+      return false;
+    }
+  }
+  if (flo == B200ITP_BC_THROW) {
+    if (!(l <= x)) return true;
+  } else if (flo == B200ITP_BC_FLAT || flo == B200ITP_BC_LINE) {
+    x = l > x ? l : x;
+  } else if (flo == B200ITP_BC_PERIODIC) {
+    x = etp_periodic<S>(P, d, x);
+  } else if (flo == B200ITP_BC_REFLECT) {
+    x = etp_reflect<S>(P, d, x);
+  }
+  if (fhi == B200ITP_BC_THROW) {
+    if (!(x <= u)) {
+      xs = x;
+      return true;
+    }
+  } else if (fhi == B200ITP_BC_FLAT || fhi == B200ITP_BC_LINE) {
+    x = x < u ? x : u;
+  } else if (fhi == B200ITP_BC_PERIODIC) {
+    x = etp_periodic<S>(P, d, x);
+  } else if (fhi == B200ITP_BC_REFLECT) {
+    x = etp_reflect<S>(P, d, x);
+  }
+  xs = x;
+  return false;
+}
+
+__device__ __forceinline__ int modrange1(int i, int n) {  // utils.jl:7 with r = 1:n
+  int m = (i - 1) % n;
+  if (m < 0) m += n;
+  return m + 1;
+}
+
+// positions + weights of one axis.  LMAX taps; L = number actually used (LMAX unless DEG == 0).
+template <int DEG, typename TW>
+struct AxisTaps {
+  static constexpr int LMAX = DEG == 0 ? 4 : DEG + 1;
+  int pos[LMAX];  // 0-based position along the axis of the coefficient array
+  TW wv[LMAX], wg[LMAX];
+  int L;
+  bool edge;
+  bool contiguous;  // pos[k] == pos[0] + k
+};
+
+template <int DEG, typename TW, bool GRAD>
+__device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, AxisTaps<DEG, TW> &A) {
+  const int deg = DEG == 0 ? P.degree[d] : DEG;
+  const int n = P.n[d];
+  const bool per = P.periodic[d] != 0;
+  const int cf = P.coef_first[d];
+  A.edge = false;
+  int first;  // index of the first tap in the parent index space
+  if (deg == B200ITP_CUBIC) {
+    TW xf;
+    if (!per) {  // cubic.jl:40-46, floorbounds indexing.jl:183-187
+      if (x < TW(1)) {
+        xf = s_floor<TW>(x + TW(0.5));
+        A.edge = true;
+      } else {
+        xf = s_floor<TW>(x + TW(0));
+      }
+      if (xf > TW(n - 1)) {
+        xf = xf - TW(1);
+        A.edge = true;
+      }
+    } else {  // cubic.jl:50-57
+      xf = s_floor<TW>(x);
+    }
+    const TW dx = x - xf;
+    first = (int)xf - 1;
+    A.L = 4;
+    // value_weights cubic.jl:63-69, constants convert(T, SimpleRatio) = T(p)/T(q)
+    const TW omd = TW(1) - dx;
+    const TW x3 = (dx * dx) * dx, xc3 = (omd * omd) * omd;
+    const TW r16 = TW(1) / TW(6), r23 = TW(2) / TW(3);
+    A.wv[0] = r16 * xc3;
+    A.wv[1] = (r23 - dx * dx) + TW(0.5) * x3;
+    A.wv[2] = (r23 - omd * omd) + TW(0.5) * xc3;
+    A.wv[3] = r16 * x3;
+    if (GRAD) {  // cubic.jl:71-77
+      const TW x2 = dx * dx, xc2 = omd * omd;
+      A.wg[0] = TW(-0.5) * xc2;
+      A.wg[1] = TW(-2) * dx + TW(1.5) * x2;
+      A.wg[2] = TW(2) * omd - TW(1.5) * xc2;
+      A.wg[3] = TW(0.5) * x2;
+    }
+  } else if (deg == B200ITP_QUADRATIC) {
+    // quadratic.jl:39-43, roundbounds indexing.jl:172-177
+    const TW xh = x + TW(0.5);
+    TW xm;
+    if ((double)x < (double)n + 0.5) {
+      xm = s_floor<TW>(xh);
+    } else {
+      xm = s_ceil<TW>(xh) - TW(1);
+      A.edge = true;
+    }
+    const TW dx = x - xm;
+    first = (int)xm - 1;
+    A.L = 3;
+    const TW a = dx - TW(0.5), b = dx + TW(0.5);  // quadratic.jl:45-53
+    A.wv[0] = (a * a) / TW(2);
+    A.wv[1] = TW(0.75) - dx * dx;
+    A.wv[2] = (b * b) / TW(2);
+    if (GRAD) {
+      A.wg[0] = a;
+      A.wg[1] = TW(-2) * dx;
+      A.wg[2] = b;
+    }
+    if (DEG == 0) {
+      A.wv[3] = TW(0);
+      A.wg[3] = TW(0);
+    }
+  } else {  // linear.jl:43-58
+    TW f = s_floor<TW>(x);
+    if (x == TW(n)) {
+      f = f - TW(1);
+      A.edge = true;
+    }
+    const TW dx = x - f;
+    first = (int)f;
+    A.L = 2;
+    A.wv[0] = TW(1) - dx;
+    A.wv[1] = dx;
+    if (GRAD) {
+      A.wg[0] = TW(-1);
+      A.wg[1] = TW(1);
+    }
+    if (DEG == 0) {
+      A.wv[2] = A.wv[3] = TW(0);
+      A.wg[2] = A.wg[3] = TW(0);
+    }
+  }
+  A.contiguous = true;
+#pragma unroll
+  for (int k = 0; k < AxisTaps<DEG, TW>::LMAX; ++k) {
+    int idx = first + k;
+    if (per) {
+      idx = modrange1(idx, n);
+      if (k > 0 && idx - cf != A.pos[0] + k) A.contiguous = false;
+    }
+    A.pos[k] = idx - cf;
+  }
+  if (DEG == 0)
+    for (int k = A.L; k < 4; ++k) A.pos[k] = A.pos[0];
+}
+
+// Nested tensor-product reduction (Interpolations.jl:304-316).  Returns the value of the sub-product over
+// axes D..N-1 and, if GRAD, the gradient components of those axes (sharing the value partial sums is
+// exact: component j of the gradient uses value weights on every axis but j).
+template <int N, int DEG, typename TC, typename TW, bool GRAD, int D>
+struct Reduce {
+  using TA = typename Promote<TW, TC>::type;
+  static constexpr int LMAX = AxisTaps<DEG, TW>::LMAX;
+  __device__ __forceinline__ static void run(const EvalParams &P, const AxisTaps<DEG, TW> (&ax)[N], const TC *base,
+                                             TA &val, TA (&g)[N]) {
+    const AxisTaps<DEG, TW> &A = ax[D];
+    TA gv = TA(0);
+#pragma unroll
+    for (int k = 0; k < LMAX; ++k) {
+      if (DEG != 0 || k < A.L) {
+        TA vk;
+        TA gk[N];
+        const TC *b = base + (long long)A.pos[k] * P.stride[D];
+        if constexpr (D == N - 1) {
+          vk = (TA)__ldg(b);
+        } else {
+          Reduce<N, DEG, TC, TW, GRAD, D + 1>::run(P, ax, b, vk, gk);
+        }
+        const TA w = (TA)A.wv[k];
+        if (k == 0) {
+          val = w * vk;
+        } else {
+          val = w * vk + val;
+        }
+        if (GRAD) {
+          const TA wgk = (TA)A.wg[k];
+          if (k == 0)
+            gv = wgk * vk;
+          else
+            gv = wgk * vk + gv;
+          if constexpr (D < N - 1) {
+#pragma unroll
+            for (int j = D + 1; j < N; ++j) {
+              if (k == 0)
+                g[j] = w * gk[j];
+              else
+                g[j] = w * gk[j] + g[j];
+            }
+          }
+        }
+      }
+    }
+    if (GRAD) g[D] = gv;
+  }
+};
+
+// Value-only fast path for Float32 coefficients whose axis-1 taps are adjacent in memory: every
+// (axis 2..N) row is fetched with two aligned 128-bit loads instead of 3-4 scalar loads, then the
+// reduction runs in the reference order from registers.
+template <int N, int DEG, typename TW>
+__device__ __forceinline__ void load_row4(const float *coefs, long long lin, long long total, float (&c)[4]) {
+  const long long a = lin & ~3LL;
+  const int sft = (int)(lin - a);
+  const float4 q0 = __ldg(reinterpret_cast<const float4 *>(coefs + a));
+  float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sft != 0) {
+    if (a + 8 <= total) {
+      q1 = __ldg(reinterpret_cast<const float4 *>(coefs + a + 4));
+    } else {  // last few elements of the array: stay inside the allocation
+      if (a + 4 < total) q1.x = __ldg(coefs + a + 4);
+      if (a + 5 < total) q1.y = __ldg(coefs + a + 5);
+      if (a + 6 < total) q1.z = __ldg(coefs + a + 6);
+    }
+  }
+  const float w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v = w[k];
+    v = sft == 1 ? w[k + 1] : v;
+    v = sft == 2 ? w[k + 2] : v;
+    v = sft == 3 ? w[k + 3] : v;
+    c[k] = v;
+  }
+}
+
+template <typename TO>
+__device__ __forceinline__ void store_out(void *p, long long i, TO v, int out_f64) {
+  if (out_f64)
+    reinterpret_cast<double *>(p)[i] = (double)v;
+  else
+    reinterpret_cast<float *>(p)[i] = (float)v;
+}
+
+// MODE 0: values; MODE 1: gradients
+template <int N, int DEG, typename TC, typename TX, typename TW, int MODE>
+__global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalParams P) {
+  using TA = typename Promote<TW, TC>::type;
+  const TC *coefs = reinterpret_cast<const TC *>(P.coefs);
+  const long long stride_q = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P.nq; t += stride_q) {
+    const long long q = P.perm ? (long long)P.perm[t] : t;
+    TX x[N];
+    unsigned br = 0;
+    bool inb = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      x[d] = reinterpret_cast<const TX *>(P.coords[d])[q];
+      const double xd = (double)x[d];
+      if (!(P.lb[d] <= xd)) {
+        br |= B200ITP_BR_BELOW << (4 * d);
+        inb = false;
+      }
+      if (!(xd <= P.ub[d])) {
+        br |= B200ITP_BR_ABOVE << (4 * d);
+        inb = false;
+      }
+    }
+    // ---- extrapolation stage: xs (in TW; exact widening when the stage ran in TX)
+    TW xs[N];
+    bool threw = false, filled = false, moved = false;
+    bool use_x = false;  // gradient of an in-bounds query ignores the mapping (extrapolation.jl:73-74)
+    if (P.etp_kind == B200ITP_ETP_FLAGS) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        bool th;
+        if (sizeof(TX) == sizeof(TW) || !P.e_wide) {
+          TX y;
+          th = etp_inbounds<TX>(P, d, x[d], y);
+          xs[d] = (TW)y;
+          if (y != x[d]) {
+            moved = true;
+            br |= B200ITP_BR_MOVED << (4 * d);
+          }
+        } else {
+          TW y;
+          th = etp_inbounds<TW>(P, d, (TW)x[d], y);
+          xs[d] = y;
+          if (y != (TW)x[d]) {
+            moved = true;
+            br |= B200ITP_BR_MOVED << (4 * d);
+          }
+        }
+        threw = threw || th;
+      }
+      if (MODE == 1 && inb) use_x = true;
+    } else {
+#pragma unroll
+      for (int d = 0; d < N; ++d) xs[d] = (TW)x[d];
+      if (!inb) {
+        if (P.etp_kind == B200ITP_ETP_FILL)
+          filled = true;
+        else
+          threw = true;
+      }
+    }
+
+    TA val = TA(0);
+    TA grad[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) grad[d] = TA(0);
+    int first_idx[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) first_idx[d] = INT_MIN;
+
+    if (!threw && !filled) {
+      // ---- scale stage: coordlookup + clamp (scaling.jl:78-83,102-115)
+      TW xl[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        TW xv = use_x ? (TW)x[d] : xs[d];
+        if (P.has_scale) {
+          if (sizeof(TX) == sizeof(TW) || P.s_wide) {
+            xv = (xv - (TW)P.rfirst[d]) / (TW)P.rstep[d] + TW(1);
+          } else {
+            const TX y = ((TX)xv - (TX)P.rfirst[d]) / (TX)P.rstep[d] + TX(1);
+            xv = (TW)y;
+          }
+          const TW lo = (TW)P.inner_lb[d], hi = (TW)P.inner_ub[d];
+          xv = xv > hi ? hi : (xv < lo ? lo : xv);
+        }
+        xl[d] = xv;
+      }
+      // ---- B-spline stage
+      const bool need_grad = MODE == 1 || (moved && P.any_line);
+      AxisTaps<DEG, TW> ax[N];
+      if (need_grad) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) axis_setup<DEG, TW, true>(P, d, xl[d], ax[d]);
+        Reduce<N, DEG, TC, TW, true, 0>::run(P, ax, coefs, val, grad);
+        if (P.has_scale) {
+#pragma unroll
+          for (int d = 0; d < N; ++d) grad[d] = grad[d] / (TA)P.rstep[d];  // rescale_gradient scaling.jl:116,137
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < N; ++d) axis_setup<DEG, TW, false>(P, d, xl[d], ax[d]);
+        bool done = false;
+        if constexpr (sizeof(TC) == 4 && N <= 3 && (DEG == 2 || DEG == 3)) {
+          if (ax[0].contiguous && P.vec_ok) {
+            // rows of axis-1 taps through aligned 128-bit loads, reduction in the reference order
+            constexpr int L = DEG + 1;
+            constexpr int ROWS = N == 1 ? 1 : (N == 2 ? L : L * L);
+            float c[ROWS][4];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+              long long lin = ax[0].pos[0];
+              if (N >= 2) lin += (long long)ax[1].pos[N == 2 ? r : r % L] * P.stride[1];
+              if (N >= 3) lin += (long long)ax[2].pos[r / L] * P.stride[2];
+              load_row4<N, DEG, TW>(reinterpret_cast<const float *>(coefs), lin, P.total, c[r]);
+            }
+            // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )
+#pragma unroll
+            for (int k0 = 0; k0 < L; ++k0) {
+              TA v0;
+              if (N == 1) {
+                v0 = (TA)c[0][k0];
+              } else {
+#pragma unroll
+                for (int k1 = 0; k1 < L; ++k1) {
+                  TA v1;
+                  if (N == 2) {
+                    v1 = (TA)c[k1][k0];
+                  } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < L; ++k2) {
+                      const TA t2 = (TA)ax[2].wv[k2] * (TA)c[k2 * L + k1][k0];
+                      v1 = k2 == 0 ? t2 : t2 + v1;
+                    }
+                  }
+                  const TA t1 = (TA)ax[1].wv[k1] * v1;
+                  v0 = k1 == 0 ? t1 : t1 + v0;
+                }
+              }
+              const TA t0 = (TA)ax[0].wv[k0] * v0;
+              val = k0 == 0 ? t0 : t0 + val;
+            }
+            done = true;
+          }
+        }
+        if (!done) Reduce<N, DEG, TC, TW, false, 0>::run(P, ax, coefs, val, grad);
+      }
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        first_idx[d] = ax[d].pos[0] + P.coef_first[d];
+        if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
+      }
+      // ---- extrapolate_value / extrapolate_gradient (extrapolation.jl:166-185)
+      if (P.etp_kind == B200ITP_ETP_FLAGS) {
+        if (MODE == 0) {
+          if (moved) {
+            br |= B200ITP_BR_SLOWPATH;
+            if (P.any_line) {
+#pragma unroll
+              for (int d = 0; d < N; ++d) {
+                const bool pair = (P.pair_mask >> d) & 1;
+                TW dxs;  // x - xs in the type the extrapolation stage ran in
+                if (sizeof(TX) == sizeof(TW) || !P.e_wide)
+                  dxs = (TW)(x[d] - (TX)xs[d]);
+                else
+                  dxs = (TW)x[d] - xs[d];
+                const bool lo_line = P.etp_lo[d] == B200ITP_BC_LINE, hi_line = P.etp_hi[d] == B200ITP_BC_LINE;
+                if (!pair) {
+                  if (lo_line) val = val + (TA)dxs * grad[d];
+                } else {
+                  if (lo_line && (TW)x[d] < xs[d]) val = val + (TA)dxs * grad[d];
+                  if (hi_line && (TW)x[d] > xs[d]) val = val + (TA)dxs * grad[d];
+                }
+              }
+            }
+          }
+        } else if (!inb) {
+#pragma unroll
+          for (int d = 0; d < N; ++d)
+            if (P.etp_lo[d] == B200ITP_BC_FLAT && xs[d] != (TW)x[d]) grad[d] = TA(0);
+        }
+      }
+    }
+    if (filled) {
+      br |= B200ITP_BR_FILLED;
+    }
+    if (threw) {
+      br |= B200ITP_BR_THROW;
+      atomicMin(P.first_oob, (unsigned long long)q);
+    }
+    // ---- outputs
+    if (MODE == 0) {
+      if (threw) {
+        store_out<double>(P.out_value, q, nan(""), P.out_f64);
+      } else if (filled) {
+        store_out<double>(P.out_value, q, P.fill, P.out_f64);
+      } else {
+        store_out<TA>(P.out_value, q, val, P.out_f64);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        if (threw)
+          store_out<double>(P.out_grad, q * N + d, nan(""), P.out_f64);
+        else
+          store_out<TA>(P.out_grad, q * N + d, filled ? TA(0) : grad[d], P.out_f64);
+      }
+    }
+    if (P.dbg_index) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) P.dbg_index[q * N + d] = first_idx[d];
+    }
+    if (P.dbg_branch) P.dbg_branch[q] = br;
+  }
+}
+
+// one translation unit per (TC, TX, TW) combination instantiates and launches its kernels
+template <typename TC, typename TX, typename TW>
+int launch_eval_combo(const EvalParams &P, int uniform_degree, int mode, int blocks, cudaStream_t st);
+
+}  // namespace b200itp

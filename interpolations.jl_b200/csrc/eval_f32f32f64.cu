@@ -1,0 +1,5 @@
+// eval kernels for coefficients=float, coordinates=float, weights=double (see eval.cuh)
+#include "eval_combo_impl.cuh"
+namespace b200itp {
+template int launch_eval_combo<float, float, double>(const EvalParams &, int, int, int, cudaStream_t);
+}

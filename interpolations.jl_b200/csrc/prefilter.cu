@@ -1,0 +1,689 @@
+// B-spline prefilter for sm_100a: batched tridiagonal (LU) + Woodbury solve along one axis of a
+// column-major array, one HBM read and one HBM write of the array per axis pass.
+//
+// Replaces (paths relative to the Interpolations.jl v0.16.3 checkout)
+//   copy_with_padding                       src/b-splines/prefiltering.jl:17-28
+//   A_ldiv_B_md! / _A_ldiv_B_md!(LU)        src/filter1d.jl:8-73
+//   _A_ldiv_B_md!(Woodbury)                 src/filter1d.jl:77-85
+//   prefilter!                              src/b-splines/prefiltering.jl:49-59,108-122
+//
+// Algorithm.  The reference solves  x = A\v  by an LU forward sweep
+//   y[r] = v[r] - L[r]*y[r-1]            and a backward sweep   x[r] = (y[r] - U[r]*x[r+1]) * Dinv[r],
+// then applies the rank-k Woodbury correction through a full-size temporary and a second full sweep.
+// Here a line is streamed once in register blocks of B rows:
+//   * the forward recurrence is carried exactly from block to block;
+//   * the backward recurrence of block b starts one block further down with x := 0; both recurrences
+//     contract by |L|,|U*Dinv| ~ 0.268 (cubic) / 0.172 (quadratic) per row, so after B rows the
+//     start-up error is below round-off (0.268^16 ~ 7e-10 for Float32 with B = 16, 0.268^32 ~ 5e-19
+//     for Float64 with B = 32);
+//   * the Woodbury correction is  x -= z1*c1 + zn*cn  with z1 = A\e_1, zn = A\e_n (decaying within
+//     Hz <= 48 rows of each end, tabulated on the host) and c = Cp*V*x computed per line from a short
+//     look at both ends of the line before streaming starts.
+// Lines along a non-contiguous axis are mapped one per thread, neighbouring threads on neighbouring
+// addresses (every warp access is a full 128-byte line).  Lines along the contiguous axis go through
+// a shared-memory tile: 128-bit coalesced global accesses, 128-bit conflict-free shared accesses.
+// Long lines in arrays with few lines are cut into segments with one warm-up and one look-ahead
+// block (out of place, so that no segment reads rows another segment has already overwritten).
+#include "common.cuh"
+#include "systems.hpp"
+
+#include <mutex>
+
+namespace b200itp {
+
+// ================================================================== per-block primitives
+template <typename T>
+__device__ __forceinline__ T fmsub_(T a, T b, T c) {  // c - a*b
+  return fma(-a, b, c);
+}
+
+template <typename T>
+__device__ __forceinline__ void row_coef(const AxisPlan<T> &p, int r, T &L, T &U, T &Di) {
+  const bool head = r <= p.P;
+  const int i = head ? r - 1 : 0;
+  L = head ? p.Lh[i] : p.Linf;
+  U = head ? p.Uh[i] : p.Uinf;
+  Di = head ? p.Dh[i] : p.Dinf;
+  if (r == p.n) {
+    L = p.Llast;
+    Di = p.Dlast;
+    U = T(0);
+  }
+}
+
+// forward sweep over rows r0 .. r0+cnt-1 held in v[0..cnt); carry = y[r0-1] in, y[r0+cnt-1] out
+template <typename T, int B>
+__device__ __forceinline__ void fwd_generic(const AxisPlan<T> &p, int r0, int cnt, T (&v)[B], T &carry) {
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    if (j < cnt) {
+      T L, U, Di;
+      row_coef(p, r0 + j, L, U, Di);
+      v[j] = fmsub_(L, carry, v[j]);
+      carry = v[j];
+    }
+  }
+}
+template <typename T, int B>
+__device__ __forceinline__ void fwd_steady(T L, T (&v)[B], T &carry) {
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    v[j] = fmsub_(L, carry, v[j]);
+    carry = v[j];
+  }
+}
+
+// backward sweep; xn = x[r0+cnt] in (0 starts a truncated, or the exact end-of-line, recurrence)
+template <typename T, int B, bool STORE>
+__device__ __forceinline__ void bwd_generic(const AxisPlan<T> &p, int r0, int cnt, T (&v)[B], T &xn) {
+#pragma unroll
+  for (int j = B - 1; j >= 0; --j) {
+    if (j < cnt) {
+      T L, U, Di;
+      row_coef(p, r0 + j, L, U, Di);
+      xn = fmsub_(U, xn, v[j]) * Di;
+      if (STORE) v[j] = xn;
+    }
+  }
+}
+template <typename T, int B, bool STORE>
+__device__ __forceinline__ void bwd_steady(T U, T Di, T (&v)[B], T &xn) {
+#pragma unroll
+  for (int j = B - 1; j >= 0; --j) {
+    xn = fmsub_(U, xn, v[j]) * Di;
+    if (STORE) v[j] = xn;
+  }
+}
+
+// Woodbury correction of the rows of one block (filter1d.jl:79-84 collapsed to x -= z1*c1 + zn*cn)
+template <typename T, int B>
+__device__ __forceinline__ void correct_block(const AxisPlan<T> &p, int r0, int cnt, T (&x)[B], T c1, T cn) {
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    const int r = r0 + j;
+    if (j < cnt) {
+      if (r <= p.Hz) x[j] = fmsub_(p.z1[r - 1], c1, x[j]);
+      const int q = r - (p.n - p.Hz) - 1;
+      if (q >= 0) x[j] = fmsub_(p.zn[q], cn, x[j]);
+    }
+  }
+}
+
+template <typename T, int B>
+__device__ __forceinline__ bool block_is_steady(const AxisPlan<T> &p, int r0) {
+  return r0 > p.P && r0 + B - 1 < p.n;
+}
+template <typename T, int B>
+__device__ __forceinline__ bool block_needs_correction(const AxisPlan<T> &p, int r0) {
+  return p.nv > 0 && (r0 <= p.Hz || r0 + B - 1 > p.n - p.Hz);
+}
+
+// c1 = W1 . x[vrow], cn = Wn . x[vrow] with x = A\v (uncorrected), from TP rows at each end of the line.
+// `ld(r)` returns v[r] (1-based).  Start: exact forward from row 1, backward started TP rows in;
+// end: forward started TP rows before n, exact backward from row n.
+template <typename T, int TP, typename Load>
+__device__ __forceinline__ void woodbury_coeffs(const AxisPlan<T> &p, Load ld, T &c1, T &cn) {
+  c1 = T(0);
+  cn = T(0);
+  T y[TP];
+#pragma unroll 1
+  for (int end = 0; end < 2; ++end) {
+    const int rb = end ? p.n - TP + 1 : 1;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) y[j] = ld(rb + j);
+    T carry = T(0);
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+      T L, U, Di;
+      row_coef(p, rb + j, L, U, Di);
+      y[j] = fmsub_(L, carry, y[j]);
+      carry = y[j];
+    }
+    T xn = T(0);
+#pragma unroll
+    for (int j = TP - 1; j >= 0; --j) {
+      T L, U, Di;
+      row_coef(p, rb + j, L, U, Di);
+      xn = fmsub_(U, xn, y[j]) * Di;
+      if (end ? (j >= TP - 8) : (j < 8)) {
+#pragma unroll
+        for (int q = 0; q < B200ITP_MAX_WOODBURY; ++q)
+          if (q < p.nv && p.vrow[q] == rb + j) {
+            c1 = fma(p.W1[q], xn, c1);
+            cn = fma(p.Wn[q], xn, cn);
+          }
+      }
+    }
+  }
+}
+
+template <typename T>
+struct Tune;
+template <>
+struct Tune<float> {
+  static constexpr int B = 16;       // block rows == look-ahead rows
+  static constexpr int TP = 24;      // rows examined at each end for the Woodbury coefficients
+  static constexpr int ITEMS = 128;  // lines per CTA in the contiguous-axis kernel
+};
+template <>
+struct Tune<double> {
+  static constexpr int B = 32;
+  static constexpr int TP = 40;
+  static constexpr int ITEMS = 64;
+};
+
+// One step of the block pipeline shared by both streaming kernels.
+//   v      : the rows of block bi (already loaded, cnt valid)
+//   yprev  : forward values of block bi-1 (cnt_prev valid); on return holds the finished x of block bi-1
+//            if `emit`, and afterwards is overwritten by v's forward values if `keep`.
+template <typename T, int B>
+__device__ __forceinline__ void pipeline_step(const AxisPlan<T> &p, int r0, int cnt, T (&v)[B], T (&yprev)[B],
+                                              int cnt_prev, T &carry, bool emit, T c1, T cn, T (&xout)[B]) {
+  const bool steady = block_is_steady<T, B>(p, r0) && cnt == B;
+  if (steady)
+    fwd_steady<T, B>(p.Linf, v, carry);
+  else
+    fwd_generic<T, B>(p, r0, cnt, v, carry);
+  if (emit) {
+    T xn = T(0);
+    if (steady)
+      bwd_steady<T, B, false>(p.Uinf, p.Dinf, v, xn);
+    else
+      bwd_generic<T, B, false>(p, r0, cnt, v, xn);
+    const int rp = r0 - B;
+#pragma unroll
+    for (int j = 0; j < B; ++j) xout[j] = yprev[j];
+    if (block_is_steady<T, B>(p, rp) && cnt_prev == B)
+      bwd_steady<T, B, true>(p.Uinf, p.Dinf, xout, xn);
+    else
+      bwd_generic<T, B, true>(p, rp, cnt_prev, xout, xn);
+    if (block_needs_correction<T, B>(p, rp)) correct_block<T, B>(p, rp, cnt_prev, xout, c1, cn);
+  }
+}
+
+// ================================================================== kernel: axis > 1 (strided lines)
+// Work item = (i1 in [0,R1), segment, i2 in [0,R2)); thread <-> i1 so a warp touches 32 consecutive
+// addresses in every row.  Rows [s, e] of the segment, s = 1 + seg*seglen (seglen multiple of B).
+template <typename T>
+__global__ void __launch_bounds__(128) prefilter_strided_kernel(const T *src, T *dst,
+                                                                const __grid_constant__ AxisPlan<T> p, int64_t R1,
+                                                                int nb1, int seglen, int nseg) {
+  constexpr int B = Tune<T>::B;
+  int64_t bid = blockIdx.x;
+  const int b1 = (int)(bid % nb1);
+  bid /= nb1;
+  const int seg = (int)(bid % nseg);
+  const int64_t i2 = bid / nseg;
+  const int64_t i1 = (int64_t)b1 * blockDim.x + threadIdx.x;
+  if (i1 >= R1) return;
+  const int n = p.n;
+  const int64_t off = i1 + R1 * (int64_t)n * i2;
+  const T *in = src + off;
+  T *out = dst + off;
+  const int s = 1 + seg * seglen;
+  const int e = min(n, s + seglen - 1);
+
+  T c1 = T(0), cn = T(0);
+  if (p.nv > 0 && (s <= p.Hz || e > n - p.Hz))
+    woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[(int64_t)(r - 1) * R1]; }, c1, cn);
+
+  const int bs = (s - 1) / B, be = (e - 1) / B;
+  T yprev[B], v[B], xout[B];
+  T carry = T(0);
+  int cnt_prev = 0;
+#pragma unroll 1
+  for (int bi = (bs > 0 ? bs - 1 : bs); bi <= be + 1; ++bi) {
+    const int r0 = 1 + bi * B;
+    const int cnt = max(0, min(B, n - r0 + 1));
+    if (cnt == B) {
+#pragma unroll
+      for (int j = 0; j < B; ++j) v[j] = in[(int64_t)(r0 - 1 + j) * R1];
+    } else {
+#pragma unroll
+      for (int j = 0; j < B; ++j) v[j] = j < cnt ? in[(int64_t)(r0 - 1 + j) * R1] : T(0);
+    }
+    const bool emit = bi > bs;
+    pipeline_step<T, B>(p, r0, cnt, v, yprev, cnt_prev, carry, emit, c1, cn, xout);
+    if (emit) {
+      const int rp = r0 - B;
+      if (cnt_prev == B) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) out[(int64_t)(rp - 1 + j) * R1] = xout[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+          if (j < cnt_prev) out[(int64_t)(rp - 1 + j) * R1] = xout[j];
+      }
+    }
+    if (bi >= bs) {
+#pragma unroll
+      for (int j = 0; j < B; ++j) yprev[j] = v[j];
+      cnt_prev = cnt;
+    }
+  }
+}
+
+// ================================================================== kernel: axis 1 (contiguous lines)
+// A CTA owns ITEMS consecutive lines and walks them in chunks of 32 rows staged through shared memory.
+// Tile layout: row of 16-byte vectors per item with a pitch of VPI+1 vectors (odd), so that
+//   * the cooperative copy (8 or 16 consecutive threads per item) is conflict-free and coalesced,
+//   * each thread's 128-bit reads/writes of its own item are conflict-free (8 consecutive items hit 8
+//     different 16-byte bank groups).
+template <typename T, bool VEC16>
+__global__ void __launch_bounds__(Tune<T>::ITEMS) prefilter_contig_kernel(const T *src, T *dst,
+                                                                           const __grid_constant__ AxisPlan<T> p,
+                                                                           int64_t nlines, int nlb, int seglen,
+                                                                           int nseg) {
+  constexpr int B = Tune<T>::B;
+  constexpr int ITEMS = Tune<T>::ITEMS;
+  constexpr int CH = 32;                       // rows per chunk
+  constexpr int K = CH / B;                    // blocks per chunk
+  constexpr int EPV = 16 / (int)sizeof(T);     // elements per 16-byte vector
+  constexpr int VPI = CH / EPV;                // vectors per item per chunk
+  constexpr int PITCH = VPI + 1;               // in vectors
+  constexpr int VPB = B / EPV;                 // vectors per block
+  __shared__ uint4 tin[ITEMS * PITCH];
+  __shared__ uint4 tout[ITEMS * PITCH];
+
+  const int tid = threadIdx.x;
+  int64_t bid = blockIdx.x;
+  const int lb = (int)(bid % nlb);
+  const int seg = (int)(bid / nlb);
+  (void)nseg;
+  const int64_t l0 = (int64_t)lb * ITEMS;
+  const int64_t line = l0 + tid;
+  const bool active = line < nlines;
+  const int n = p.n;
+  const int s = 1 + seg * seglen;
+  const int e = min(n, s + seglen - 1);
+
+  T c1 = T(0), cn = T(0);
+  if (active && p.nv > 0 && (s <= p.Hz || e > n - p.Hz)) {
+    const T *in = src + line * (int64_t)n;
+    woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[r - 1]; }, c1, cn);
+  }
+
+  const int bs = (s - 1) / B, be = (e - 1) / B;
+  const int bfirst = bs > 0 ? bs - 1 : bs;
+  T yprev[B], v[B], xout[B];
+  T carry = T(0);
+  int cnt_prev = 0;
+
+#pragma unroll 1
+  for (int ci = bfirst / K; ci <= (be + 1) / K; ++ci) {
+    const int rc0 = 1 + ci * CH;
+    // ---- cooperative load of rows [rc0, rc0+32) of ITEMS lines
+    if (VEC16) {
+#pragma unroll
+      for (int it = 0; it < VPI; ++it) {
+        const int idx = it * ITEMS + tid;
+        const int item = idx / VPI, vj = idx % VPI;
+        const int row = rc0 + vj * EPV;
+        const int64_t ln = l0 + item;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (ln < nlines && row <= n) val = *reinterpret_cast<const uint4 *>(src + ln * (int64_t)n + (row - 1));
+        tin[item * PITCH + vj] = val;
+      }
+    } else {
+      T *tin_s = reinterpret_cast<T *>(tin);
+#pragma unroll 4
+      for (int it = 0; it < CH; ++it) {
+        const int idx = it * ITEMS + tid;
+        const int item = idx / CH, j = idx % CH;
+        const int row = rc0 + j;
+        const int64_t ln = l0 + item;
+        T val = T(0);
+        if (ln < nlines && row <= n) val = src[ln * (int64_t)n + (row - 1)];
+        tin_s[item * (PITCH * EPV) + j] = val;
+      }
+    }
+    __syncthreads();
+    // ---- per-thread block pipeline on this chunk
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int bi = ci * K + k;
+        if (bi < bfirst || bi > be + 1) continue;
+        const int r0 = 1 + bi * B;
+        const int cnt = max(0, min(B, n - r0 + 1));
+        const uint4 *rowp = tin + tid * PITCH + k * VPB;
+#pragma unroll
+        for (int q = 0; q < VPB; ++q) {
+          const uint4 u = rowp[q];
+          if constexpr (sizeof(T) == 4) {
+            v[q * 4 + 0] = __uint_as_float(u.x);
+            v[q * 4 + 1] = __uint_as_float(u.y);
+            v[q * 4 + 2] = __uint_as_float(u.z);
+            v[q * 4 + 3] = __uint_as_float(u.w);
+          } else {
+            v[q * 2 + 0] = __hiloint2double((int)u.y, (int)u.x);
+            v[q * 2 + 1] = __hiloint2double((int)u.w, (int)u.z);
+          }
+        }
+        const bool emit = bi > bs;
+        pipeline_step<T, B>(p, r0, cnt, v, yprev, cnt_prev, carry, emit, c1, cn, xout);
+        if (emit) {
+          uint4 *op = tout + tid * PITCH + k * VPB;
+#pragma unroll
+          for (int q = 0; q < VPB; ++q) {
+            uint4 u;
+            if constexpr (sizeof(T) == 4) {
+              u.x = __float_as_uint(xout[q * 4 + 0]);
+              u.y = __float_as_uint(xout[q * 4 + 1]);
+              u.z = __float_as_uint(xout[q * 4 + 2]);
+              u.w = __float_as_uint(xout[q * 4 + 3]);
+            } else {
+              const double a = xout[q * 2 + 0], b = xout[q * 2 + 1];
+              u.x = (unsigned)__double2loint(a);
+              u.y = (unsigned)__double2hiint(a);
+              u.z = (unsigned)__double2loint(b);
+              u.w = (unsigned)__double2hiint(b);
+            }
+            op[q] = u;
+          }
+        }
+        if (bi >= bs) {
+#pragma unroll
+          for (int j = 0; j < B; ++j) yprev[j] = v[j];
+          cnt_prev = cnt;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- cooperative store of the rows finished in this chunk: [rc0-B, rc0-B+32) ∩ [s, e]
+    const int ro0 = rc0 - B;
+    if (VEC16) {
+#pragma unroll
+      for (int it = 0; it < VPI; ++it) {
+        const int idx = it * ITEMS + tid;
+        const int item = idx / VPI, vj = idx % VPI;
+        const int row = ro0 + vj * EPV;
+        const int64_t ln = l0 + item;
+        if (ln < nlines && row >= s && row <= e)
+          *reinterpret_cast<uint4 *>(dst + ln * (int64_t)n + (row - 1)) = tout[item * PITCH + vj];
+      }
+    } else {
+      const T *tout_s = reinterpret_cast<const T *>(tout);
+#pragma unroll 4
+      for (int it = 0; it < CH; ++it) {
+        const int idx = it * ITEMS + tid;
+        const int item = idx / CH, j = idx % CH;
+        const int row = ro0 + j;
+        const int64_t ln = l0 + item;
+        if (ln < nlines && row >= s && row <= e) dst[ln * (int64_t)n + (row - 1)] = tout_s[item * (PITCH * EPV) + j];
+      }
+    }
+    // the next iteration's first __syncthreads orders these tile reads before the next tile writes
+  }
+}
+
+// ================================================================== kernel: any n, any system
+// One thread per line, sweeps in global memory (2 reads + 2 writes): used for short lines (n < 128)
+// and for systems whose factors do not settle (never the case for the reference's systems).
+// Exact algebra of filter1d.jl:21-85 with the correction collapsed to x -= z1*c1 + zn*cn.
+template <typename T>
+__global__ void __launch_bounds__(128) prefilter_general_kernel(const T *src, T *dst, int n, int64_t R1, int64_t R2,
+                                                                const T *__restrict__ L, const T *__restrict__ U,
+                                                                const T *__restrict__ Dinv,
+                                                                const T *__restrict__ z1, const T *__restrict__ zn,
+                                                                const __grid_constant__ AxisPlan<T> p) {
+  const int64_t lid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid >= R1 * R2) return;
+  const int64_t i1 = lid % R1, i2 = lid / R1;
+  const int64_t off = i1 + R1 * (int64_t)n * i2;
+  const T *in = src + off;
+  T *out = dst + off;
+  T carry = T(0);
+  for (int r = 0; r < n; ++r) {
+    carry = fmsub_(L[r], carry, in[(int64_t)r * R1]);
+    out[(int64_t)r * R1] = carry;
+  }
+  T xn = T(0);
+  for (int r = n - 1; r >= 0; --r) {
+    xn = fmsub_(U[r], xn, out[(int64_t)r * R1]) * Dinv[r];
+    out[(int64_t)r * R1] = xn;
+  }
+  if (p.nv > 0) {
+    T c1 = T(0), cn = T(0);
+    for (int q = 0; q < p.nv; ++q) {
+      const T xv = out[(int64_t)(p.vrow[q] - 1) * R1];
+      c1 = fma(p.W1[q], xv, c1);
+      cn = fma(p.Wn[q], xv, cn);
+    }
+    for (int r = 0; r < n; ++r) {
+      T x = out[(int64_t)r * R1];
+      x = fmsub_(z1[r], c1, x);
+      x = fmsub_(zn[r], cn, x);
+      out[(int64_t)r * R1] = x;
+    }
+  }
+}
+
+// ================================================================== kernel: copy_with_padding
+template <typename T>
+__global__ void __launch_bounds__(256) pad_copy_kernel(const T *__restrict__ src, T *__restrict__ dst, int ndims,
+                                                       int64_t d0, int64_t d1, int64_t d2, int64_t d3, int p0, int p1,
+                                                       int p2, int p3, int64_t total) {
+  const int64_t ds[4] = {d0, d1, d2, d3};
+  const int ps[4] = {p0, p1, p2, p3};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, soff = 0, smul = 1;
+    bool inside = true;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (d < ndims) {
+        const int64_t c = rem % ds[d];
+        rem /= ds[d];
+        const int64_t sc = c - ps[d];
+        const int64_t sd = ds[d] - 2 * ps[d];
+        inside = inside && sc >= 0 && sc < sd;
+        soff += sc * smul;
+        smul *= sd;
+      }
+    }
+    dst[i] = inside ? src[soff] : T(0);
+  }
+}
+
+// ================================================================== host drivers
+template <typename T>
+static int run_axis(int dev, T *coefs, int ndims, const int64_t *size, int axis, int64_t n, const T *dl, const T *d,
+                    const T *du, int k, const int32_t *urow, const int32_t *vcol, const T *Cp, cudaStream_t st) {
+  AxisPlan<T> plan;
+  FullTables<T> F;
+  bool fast_ok = false;
+  int rc = build_plan<T>(n, dl, d, du, k, urow, vcol, Cp, plan, F, fast_ok);
+  if (rc) B200_FAIL(rc, "prefilter: cannot build the axis plan (n=%lld, k=%d)", (long long)n, k);
+  int64_t R1 = 1, R2 = 1;
+  for (int i = 0; i < axis; ++i) R1 *= size[i];
+  for (int i = axis + 1; i < ndims; ++i) R2 *= size[i];
+  const int64_t lines = R1 * R2;
+  if (lines == 0) return 0;
+  constexpr int B = Tune<T>::B;
+
+  if (!fast_ok) {
+    // tables to the device (small: this path is for short lines)
+    void *tab = nullptr;
+    const size_t bytes = sizeof(T) * (size_t)n * 5;
+    rc = scratch_get(dev, 1, bytes, &tab);
+    if (rc) return rc;
+    std::vector<T> h((size_t)n * 5);
+    std::copy(F.L.begin(), F.L.end(), h.begin());
+    std::copy(F.U.begin(), F.U.end(), h.begin() + n);
+    std::copy(F.Dinv.begin(), F.Dinv.end(), h.begin() + 2 * n);
+    std::copy(F.z1.begin(), F.z1.end(), h.begin() + 3 * n);
+    std::copy(F.zn.begin(), F.zn.end(), h.begin() + 4 * n);
+    B200_CUDA_OK(cudaMemcpyAsync(tab, h.data(), bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));  // h is a stack-owned staging buffer
+    const T *t = (const T *)tab;
+    const int64_t nb = (lines + 127) / 128;
+    prefilter_general_kernel<T><<<(unsigned)nb, 128, 0, st>>>(coefs, coefs, (int)n, R1, R2, t, t + n, t + 2 * n,
+                                                               t + 3 * n, t + 4 * n, plan);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  // segmentation: only when there are too few lines to fill the machine
+  const int sms = sm_count(dev);
+  const int64_t want = (int64_t)sms * 1024;
+  int nseg = 1;
+  if (lines < want / 2) {
+    const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
+    nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
+  }
+  int seglen = (int)(((n + nseg - 1) / nseg + B - 1) / B * B);
+  nseg = (int)((n + seglen - 1) / seglen);
+  const T *src = coefs;
+  T *dst = coefs;
+  void *tmp = nullptr;
+  const size_t abytes = sizeof(T) * (size_t)lines * (size_t)n;
+  if (nseg > 1) {  // out of place: segments read each other's rows
+    rc = scratch_get(dev, 0, abytes, &tmp);
+    if (rc) return rc;
+    dst = (T *)tmp;
+  }
+  if (axis == 0) {
+    constexpr int ITEMS = Tune<T>::ITEMS;
+    const int64_t nlb = (lines + ITEMS - 1) / ITEMS;
+    const int64_t blocks = nlb * nseg;
+    if (blocks > 0x7fffffff || nlb > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
+    const bool vec = (n % (16 / (int)sizeof(T)) == 0) && ((uintptr_t)coefs % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (vec)
+      prefilter_contig_kernel<T, true><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, plan, lines, (int)nlb, seglen, nseg);
+    else
+      prefilter_contig_kernel<T, false><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, plan, lines, (int)nlb, seglen, nseg);
+  } else {
+    const int64_t nb1 = (R1 + 127) / 128;
+    const int64_t blocks = nb1 * nseg * R2;
+    if (blocks > 0x7fffffff || nb1 > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
+    prefilter_strided_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(src, dst, plan, R1, (int)nb1, seglen, nseg);
+  }
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  if (nseg > 1) {
+    B200_CUDA_OK(cudaMemcpyAsync(coefs, tmp, abytes, cudaMemcpyDeviceToDevice, st));
+    count_launch();
+  }
+  return 0;
+}
+
+template <typename T>
+static int prefilter_axis_typed(int dev, void *coefs, int ndims, const int64_t *size, int axis,
+                                const b200itp_axis_system *sys, cudaStream_t st) {
+  return run_axis<T>(dev, (T *)coefs, ndims, size, axis, sys->n, (const T *)sys->dl, (const T *)sys->d,
+                     (const T *)sys->du, sys->k, sys->urow, sys->vcol, (const T *)sys->Cp, st);
+}
+
+template <typename T>
+static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
+                               const int32_t *bc, const int32_t *grid, cudaStream_t st) {
+  for (int ax = 0; ax < ndims; ++ax) {
+    if (degree[ax] == B200ITP_LINEAR) continue;  // prefiltering.jl:30
+    HostSystem<T> S;
+    int rc = assemble_system<T>(size[ax], degree[ax], bc[ax], grid[ax], S);
+    if (rc == B200ITP_E_UNSUPPORTED) {
+      if (degree[ax] == B200ITP_CUBIC || degree[ax] == B200ITP_QUADRATIC) continue;  // M === nothing: left unfiltered
+      B200_FAIL(rc, "prefilter: unsupported degree %d on axis %d", degree[ax], ax);
+    }
+    if (rc) B200_FAIL(rc, "prefilter: axis %d of length %lld is too short for this boundary condition", ax,
+                      (long long)size[ax]);
+    rc = woodbury_cp<T>(S);
+    if (rc) B200_FAIL(rc, "prefilter: singular Woodbury capacitance matrix on axis %d", ax);
+    rc = run_axis<T>(dev, (T *)coefs, ndims, size, ax, S.n, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol,
+                     S.Cp, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace b200itp
+
+using namespace b200itp;
+
+extern "C" int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gridtype, void *dl, void *d,
+                                           void *du, int32_t *k, int32_t *urow, int32_t *vcol, void *Cp) {
+  if (!dl || !d || !du || !k || !urow || !vcol || !Cp) B200_FAIL(B200ITP_E_BADARG, "prefiltering_system: null pointer");
+  auto run = [&](auto tag) -> int {
+    using T = decltype(tag);
+    HostSystem<T> S;
+    int rc = assemble_system<T>(n, degree, bc, gridtype, S);
+    if (rc) B200_FAIL(rc, "prefiltering_system: no system for degree=%d bc=%d grid=%d n=%lld", degree, bc, gridtype,
+                      (long long)n);
+    rc = woodbury_cp<T>(S);
+    if (rc) B200_FAIL(rc, "prefiltering_system: singular capacitance matrix");
+    std::copy(S.dl.begin(), S.dl.end(), (T *)dl);
+    std::copy(S.d.begin(), S.d.end(), (T *)d);
+    std::copy(S.du.begin(), S.du.end(), (T *)du);
+    *k = S.k;
+    for (int j = 0; j < S.k; ++j) {
+      urow[j] = S.urow[j];
+      vcol[j] = S.vcol[j];
+    }
+    std::copy(S.Cp, S.Cp + S.k * S.k, (T *)Cp);
+    return 0;
+  };
+  if (dtype == B200ITP_F32) return run(float());
+  if (dtype == B200ITP_F64) return run(double());
+  B200_FAIL(B200ITP_E_DTYPE, "prefiltering_system: dtype must be F32 or F64");
+}
+
+extern "C" int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndims, const int64_t *size, int axis,
+                                      const b200itp_axis_system *sys, void *stream) {
+  if (!coefs || !size || !sys) B200_FAIL(B200ITP_E_BADARG, "prefilter_axis: null pointer");
+  if (ndims < 1 || ndims > B200ITP_MAX_DIMS || axis < 0 || axis >= ndims)
+    B200_FAIL(B200ITP_E_BADARG, "The chosen dimension %d is larger than %d", axis + 1, ndims);  // filter1d.jl:9
+  if (sys->n != size[axis])
+    B200_FAIL(B200ITP_E_SIZE, "Sizes %lld and %lld do not match", (long long)sys->n, (long long)size[axis]);  // :11
+  if (sys->dtype != dtype) B200_FAIL(B200ITP_E_DTYPE, "prefilter_axis: factor dtype differs from the array dtype");
+  if (sys->k < 0 || sys->k > B200ITP_MAX_WOODBURY) B200_FAIL(B200ITP_E_BADARG, "prefilter_axis: bad Woodbury rank");
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "prefilter_axis: cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200ITP_F32) return prefilter_axis_typed<float>(dev, coefs, ndims, size, axis, sys, st);
+  if (dtype == B200ITP_F64) return prefilter_axis_typed<double>(dev, coefs, ndims, size, axis, sys, st);
+  B200_FAIL(B200ITP_E_DTYPE, "prefilter_axis: dtype must be F32 or F64");
+}
+
+extern "C" int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
+                                 const int32_t *degree, const int32_t *bc, const int32_t *gridtype, void *stream) {
+  if (!coefs || !size || !degree || !bc || !gridtype) B200_FAIL(B200ITP_E_BADARG, "prefilter: null pointer");
+  if (ndims < 1 || ndims > B200ITP_MAX_DIMS) B200_FAIL(B200ITP_E_BADARG, "prefilter: ndims must be 1..4");
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "prefilter: cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200ITP_F32) return prefilter_all_typed<float>(dev, coefs, ndims, size, degree, bc, gridtype, st);
+  if (dtype == B200ITP_F64) return prefilter_all_typed<double>(dev, coefs, ndims, size, degree, bc, gridtype, st);
+  B200_FAIL(B200ITP_E_DTYPE, "prefilter: dtype must be F32 or F64");
+}
+
+extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
+                                         const int64_t *src_size, const int32_t *pad, void *stream) {
+  if (!src || !dst || !src_size || !pad) B200_FAIL(B200ITP_E_BADARG, "copy_with_padding: null pointer");
+  if (ndims < 1 || ndims > B200ITP_MAX_DIMS) B200_FAIL(B200ITP_E_BADARG, "copy_with_padding: ndims must be 1..4");
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "copy_with_padding: cannot select device %d", dev);
+  int64_t ds[4] = {1, 1, 1, 1};
+  int ps[4] = {0, 0, 0, 0};
+  int64_t total = 1;
+  for (int i = 0; i < ndims; ++i) {
+    if (pad[i] < 0 || src_size[i] < 0) B200_FAIL(B200ITP_E_BADARG, "copy_with_padding: negative size");
+    ps[i] = pad[i];
+    ds[i] = src_size[i] + 2 * pad[i];
+    total *= ds[i];
+  }
+  if (total == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count(dev) * 16);
+  if (dtype == B200ITP_F32)
+    pad_copy_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)src, (float *)dst, ndims, ds[0], ds[1],
+                                                              ds[2], ds[3], ps[0], ps[1], ps[2], ps[3], total);
+  else if (dtype == B200ITP_F64)
+    pad_copy_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)src, (double *)dst, ndims, ds[0], ds[1],
+                                                               ds[2], ds[3], ps[0], ps[1], ps[2], ps[3], total);
+  else
+    B200_FAIL(B200ITP_E_DTYPE, "copy_with_padding: dtype must be F32 or F64");
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}

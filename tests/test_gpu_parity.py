@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * stencil base indices and boundary / extrapolation branch records: bit-exact;
+  * evaluation given the same coefficients: bit-exact values (stronger than the 1e-12 / 1e-5 bar — the
+    kernels follow the reference operation by operation, no FMA contraction);
+  * prefilter coefficients: |gpu - ref| <= tol * max|ref| with tol = 1e-5 (Float32) / 1e-12 (Float64)
+    (the streaming solve uses a different operation order than the reference's LU + Woodbury sweeps).
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+def specs(m):
+    out = []
+    for GT in (m.OnGrid, m.OnCell):
+        out += [m.BSpline(m.Cubic(BC(GT()))) for BC in (m.Flat, m.Line, m.Free, m.Periodic)]
+        out += [m.BSpline(m.Quadratic(BC(GT()))) for BC in (m.Flat, m.Line, m.Free, m.Periodic, m.Reflect)]
+    out.append(m.BSpline(m.Linear()))
+    out.append(m.BSpline(m.Linear(m.Periodic())))
+    return out
+
+
+def rel_err(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------- prefilter
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(10,), (300,), (20000,), (30, 10), (150, 200), (131, 1300), (24, 20, 18),
+                                   (160, 136, 130), (9, 8, 7, 6)])
+def test_prefilter_matches_oracle(pkg, orc, dtype, shape):
+    """interpolate(A, it).coefs for every (degree, BC, grid) the reference has a system for; covers the
+    general kernel (short lines), the streaming kernels along contiguous and strided axes, partial
+    blocks (n % 16 != 0), unaligned lines (scalar tile path) and segmented long lines."""
+    m = pkg
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    A = rng.standard_normal(shape).astype(dtype)
+    for it in specs(m):
+        if it.degree.code == 1:
+            continue
+        if min(shape) < 6:
+            continue
+        ref = orc.prefilter(A, it)
+        itp = m.interpolate(A, it)
+        got = itp.coefs_array()
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert rel_err(got, ref) <= TOL[np.dtype(dtype)], (it, shape, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_prefilter_mixed_axes(pkg, orc, dtype):
+    """Per-axis tuples (prefiltering.jl:108-122): Linear axes are skipped, each axis gets its own system."""
+    m = pkg
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((140, 133, 12)).astype(dtype)
+    it = (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), m.BSpline(m.Linear()))
+    ref = orc.prefilter(A, it)
+    got = m.interpolate(A, it).coefs_array()
+    assert got.shape == ref.shape == (142, 135, 12)
+    assert rel_err(got, ref) <= TOL[np.dtype(dtype)]
+
+
+def test_prefilter_axis_with_host_factors(pkg, orc):
+    """b200itp_prefilter_axis with the factorisation computed by the host (here: the oracle's restatement of
+    `prefiltering_system`, in Julia: the reference's own) equals the all-in-one b200itp_prefilter."""
+    import ctypes as C
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(3)
+    for dtype, code in ((np.float32, 0), (np.float64, 1)):
+        A = rng.standard_normal((200, 170)).astype(dtype)
+        it = m.BSpline(m.Cubic(m.Flat(m.OnCell())))
+        ref = m.interpolate(A, it).coefs_array()
+        padded = np.zeros((202, 172), dtype)
+        padded[1:-1, 1:-1] = A
+        t = torch.from_numpy(np.ascontiguousarray(padded.reshape(-1, order="F"))).cuda()
+        size = (C.c_int64 * 2)(202, 172)
+        for axis, n in ((0, 202), (1, 172)):
+            dl, d, du, urow, vcol, Cp = orc.prefiltering_system(dtype, n, 3, 1, 1)
+            Cpf = np.ascontiguousarray(Cp.reshape(-1, order="F"))
+            sysd = m._lib.AxisSystem(dtype=code, k=len(urow), n=n, dl=dl.ctypes.data, d=d.ctypes.data,
+                                     du=du.ctypes.data, urow=(C.c_int32 * len(urow))(*urow),
+                                     vcol=(C.c_int32 * len(vcol))(*vcol), Cp=Cpf.ctypes.data)
+            rc = L.b200itp_prefilter_axis(0, C.c_void_p(t.data_ptr()), code, 2, size, axis, C.byref(sysd), None)
+            assert rc == 0, m._lib.last_error()
+        torch.cuda.synchronize()
+        got = t.cpu().numpy().reshape((202, 172), order="F")
+        assert rel_err(got, ref) <= 1e-6 if dtype == np.float32 else rel_err(got, ref) <= 1e-14
+
+
+def test_prefilter_c3_property_full_size(pkg):
+    """BASELINE config C3 at full size (512^3 Float32, Cubic(Periodic(OnGrid()))): the oracle would take minutes,
+    so check the size-independent property instead: applying the periodic (1/6, 2/3, 1/6) stencil along every
+    axis to the coefficients gives back the samples (M c = v, cubic.jl:218-228)."""
+    import torch
+    m = pkg
+    n = 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn((n, n, n), device="cuda", dtype=torch.float32, generator=g)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
+    c = itp.coefs.reshape(n, n, n)  # memory order: (i3, i2, i1) since i1 is contiguous
+    back = c
+    for dim in range(3):
+        back = (torch.roll(back, 1, dim) + torch.roll(back, -1, dim)) / 6 + back * (2.0 / 3.0)
+    ref = A.permute(2, 1, 0)
+    err = (back - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-6, err
+
+
+# ------------------------------------------------------------------------------------------- evaluation
+def adversarial_coords(rng, lb, ub, n, count, dtype):
+    """Uniform points plus every edge case SURVEY §7 step 4 lists: integers, half-integers, bounds, n, n +- eps."""
+    eps = np.finfo(dtype).eps
+    special = [lb, ub, 1.0, float(n), n - 1.0, n - 0.5, n + 0.5, 0.5, 1.5, 2.0, n / 2.0, lb + (ub - lb) * eps,
+               ub * (1 - eps), 1 + eps, 1 - eps / 2, n * (1 - eps / 2), n - 1 + 8 * eps * n, 0.9999999, 1.0000001]
+    special = [s for s in special if lb <= dtype(s) <= ub]
+    x = rng.uniform(lb, ub, count).astype(dtype)
+    x[: len(special)] = np.array(special, dtype)
+    k = len(special)
+    ints = rng.integers(int(np.ceil(lb)), int(np.floor(ub)) + 1, count // 8)
+    x[k:k + len(ints)] = ints.astype(dtype)
+    halves = ints[: count // 16].astype(np.float64) + 0.5
+    halves = halves[(halves >= lb) & (halves <= ub)]
+    x[k + len(ints):k + len(ints) + len(halves)] = halves.astype(dtype)
+    x = np.clip(x, dtype(lb), dtype(ub))
+    return x[(x >= lb) & (x <= ub)] if (dtype(lb) < lb or dtype(ub) > ub) else x
+
+
+def check_eval(pkg, orc, itp, coords, grad=True):
+    """GPU vs oracle on the GPU's coefficients: values, gradients, base indices, branch records all `==`."""
+    m = pkg
+    host = orc.with_coefs(itp, itp.coefficients().cpu().numpy())
+    v, _, bi, br = m.evaluate_debug(itp, *coords)
+    ov, og, obi, obr, _ = orc.evaluate(host, *coords, want_grad=grad, debug=True)
+    odt = m.out_dtype(itp, coords[0].dtype)
+    assert v.cpu().numpy().dtype == odt
+    assert np.array_equal(bi.cpu().numpy(), obi), "stencil base indices differ"
+    assert np.array_equal(br.cpu().numpy().view(np.uint32), obr), "branch records differ"
+    assert np.array_equal(v.cpu().numpy(), ov.astype(odt), equal_nan=True), "values differ"
+    if grad:
+        g = m.gradient(itp, *coords).cpu().numpy()
+        assert np.array_equal(g, og.astype(odt), equal_nan=True), "gradients differ"
+
+
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("ndims", [1, 2, 3])
+def test_eval_bare_interpolant_bit_exact(pkg, orc, coef_dtype, coord_dtype, ndims):
+    m = pkg
+    rng = np.random.default_rng(100 + ndims)
+    shape = {1: (301,), 2: (37, 29), 3: (19, 17, 13)}[ndims]
+    A = rng.standard_normal(shape).astype(coef_dtype)
+    for it in specs(m):
+        itp = m.interpolate(A, it)
+        coords = []
+        for d in range(ndims):
+            lb, ub = itp.bounds()[d]
+            coords.append(adversarial_coords(rng, float(lb), float(ub), shape[d], 4000, coord_dtype))
+        check_eval(pkg, orc, itp, coords)
+
+
+def test_eval_4d_linear_and_cubic(pkg, orc):
+    """BASELINE config C5 shape family (4-D Linear, Float64) plus a 4-D cubic and a mixed-degree tuple."""
+    m = pkg
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((12, 11, 10, 9))
+    for it in (m.BSpline(m.Linear()), m.BSpline(m.Cubic(m.Line(m.OnGrid()))),
+               (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Linear()), m.BSpline(m.Quadratic(m.Flat(m.OnGrid()))),
+                m.BSpline(m.Linear()))):
+        itp = m.interpolate(A, it)
+        coords = [adversarial_coords(rng, float(b[0]), float(b[1]), A.shape[d], 3000, np.float64)
+                  for d, b in enumerate(itp.bounds())]
+        check_eval(pkg, orc, itp, coords)
+
+
+def test_gpu_support_reference_testset(pkg, orc):
+    """The reference's own acceptance template test/gpu_support.jl:4-91 with the B200 array in place of JLArray:
+    1-D Cubic(Line(OnGrid())) and 2-D (Cubic, Linear), bare / scaled / extrapolate(Flat()) / extrapolate(0.0),
+    value and gradient, CPU == device bit for bit."""
+    m = pkg
+    A_x = m.jrange(1.0, 40.0, step=2.0)
+    ax = A_x.collect()
+    A = np.log(ax)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+    check_eval(pkg, orc, itp, [np.arange(2.0, 19.0, 0.17)])
+    sitp = m.scale(itp, A_x)
+    check_eval(pkg, orc, sitp, [np.arange(1.0, 39.0, 0.4)])
+    idx = np.arange(-1.0, 41.0, 0.84)
+    check_eval(pkg, orc, m.extrapolate(sitp, m.Flat()), [idx])
+    check_eval(pkg, orc, m.extrapolate(sitp, 0.0), [idx])
+    A2 = np.log(ax[:, None] + ax[None, :])
+    itp2 = m.interpolate(A2, (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Linear())))
+    i1 = np.arange(2.0, 19.0, 0.17)
+    check_eval(pkg, orc, itp2, [i1[:, None], i1[None, :]])
+    sitp2 = m.scale(itp2, A_x, A_x)
+    i2 = np.arange(1.0, 39.0, 0.4)
+    check_eval(pkg, orc, sitp2, [i2[:, None], i2[None, :]])
+    check_eval(pkg, orc, m.extrapolate(sitp2, m.Flat()), [idx[:, None], idx[None, :]])
+    check_eval(pkg, orc, m.extrapolate(sitp2, 0.0), [idx[:, None], idx[None, :]])
+
+
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+def test_eval_extrapolation_flags_bit_exact(pkg, orc, coord_dtype):
+    """Every extrapolation scheme, per-dimension tuples and per-side pairs, in and far out of bounds, +-Inf."""
+    m = pkg
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((23, 19)).astype(np.float32)
+    flags = [m.Flat(), m.Line(), m.Periodic(), m.Reflect(), (m.Line(), m.Flat()), (m.Periodic(), m.Reflect()),
+             ((m.Line(), m.Flat()), m.Flat()), ((m.Flat(), m.Line()), (m.Periodic(), m.Periodic())),
+             ((m.Reflect(), m.Flat()), (m.Line(), m.Reflect()))]
+    for it in (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))),
+               m.BSpline(m.Linear()), m.BSpline(m.Cubic(m.Periodic(m.OnCell())))):
+        itp = m.interpolate(A, it)
+        for et in flags:
+            etp = m.extrapolate(itp, et)
+            coords = []
+            for d in range(2):
+                x = rng.uniform(-3 * A.shape[d], 4 * A.shape[d], 6000)
+                x[:8] = [1.0, A.shape[d], 0.5, A.shape[d] + 0.5, -np.inf, np.inf, 1e30, -1e30]
+                x[8:2000] = rng.uniform(0.4, A.shape[d] + 0.6, 1992)
+                coords.append(x.astype(coord_dtype))
+            pair = any(isinstance(f, tuple) for f in (et if isinstance(et, tuple) else (et,)))
+            check_eval(pkg, orc, etp, coords, grad=not pair)
+
+
+@pytest.mark.parametrize("coef_dtype,coord_dtype,range_dtype", [(np.float32, np.float32, np.float32),
+                                                                 (np.float32, np.float32, np.float64),
+                                                                 (np.float64, np.float64, np.float64),
+                                                                 (np.float32, np.float64, np.float32),
+                                                                 (np.float64, np.float32, np.float32)])
+def test_eval_scaled_extrapolated_c4_family(pkg, orc, coef_dtype, coord_dtype, range_dtype):
+    """BASELINE config C4 family: 2-D Quadratic(Reflect(OnCell())) with scale(ranges) and extrapolate(Line()),
+    ~30 % of the queries out of bounds; also OnGrid cubic, Float32/Float64 range element types (promotion)."""
+    m = pkg
+    rng = np.random.default_rng(33)
+    nx, ny = 61, 47
+    A = rng.standard_normal((nx, ny)).astype(coef_dtype)
+    rx = m.jrange(range_dtype(0), range_dtype(1), length=nx, dtype=range_dtype)
+    ry = m.jrange(range_dtype(-2), range_dtype(3), length=ny, dtype=range_dtype)
+    for it in (m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))),
+               m.BSpline(m.Linear())):
+        sitp = m.scale(m.interpolate(A, it), rx, ry)
+        qx = rng.uniform(-0.1, 1.1, 8000).astype(coord_dtype)
+        qy = rng.uniform(-2.5, 3.5, 8000).astype(coord_dtype)
+        for et in (m.Line(), m.Flat(), m.Periodic(), m.Reflect(), 0.0, np.float32(1.5)):
+            check_eval(pkg, orc, m.extrapolate(sitp, et), [qx, qy])
+        (l1, u1), (l2, u2) = sitp.bounds()
+        inx = rng.uniform(l1, u1, 4000).astype(coord_dtype).clip(l1, u1)
+        iny = rng.uniform(l2, u2, 4000).astype(coord_dtype).clip(l2, u2)
+        inx[:2] = [l1, u1]
+        iny[:2] = [l2, u2]
+        ok = (inx >= l1) & (inx <= u1) & (iny >= l2) & (iny <= u2)
+        check_eval(pkg, orc, sitp, [inx[ok], iny[ok]])
+
+
+def test_bounds_error_and_first_oob(pkg):
+    """Throw: bare interpolants, scaled interpolants and extrapolate(itp, Throw()) raise BoundsError for the first
+    offending query (indexing.jl:6, scaling.jl:80, extrapolation.jl:115-129)."""
+    m = pkg
+    A = np.arange(1.0, 11.0) ** 2
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+    x = np.linspace(1, 10, 1000)
+    assert np.isfinite(itp(x).cpu().numpy()).all()
+    x[417] = 10.5
+    x[800] = 0.2
+    with pytest.raises(m.BoundsError, match="10.5"):
+        itp(x)
+    with pytest.raises(m.BoundsError):
+        m.gradient(itp, x)
+    with pytest.raises(m.BoundsError):
+        m.extrapolate(itp, m.Throw())(x)
+    sitp = m.scale(itp, m.jrange(0.0, 9.0, step=1.0))
+    with pytest.raises(m.BoundsError):
+        sitp(np.array([9.1]))
+    assert sitp(np.array([9.0])).item() == pytest.approx(100.0)
+
+
+def test_reference_property_battery_on_gpu(pkg):
+    """The reference's own assertions (test/b-splines/cubic.jl:15-37,81-109) run through the GPU path: node
+    reproduction, Flat boundary gradient ~ 0, Free exact on cubics, Periodic OnCell itp(lb) == itp(ub)."""
+    m = pkg
+    n = 10
+    A = np.sin((np.arange(1, n + 1) - 3) * 2 * np.pi / (n - 1) - 1)
+    for GT in (m.OnGrid, m.OnCell):
+        for BC in (m.Line, m.Flat, m.Free, m.Periodic):
+            itp = m.interpolate(A, m.BSpline(m.Cubic(BC(GT()))))
+            assert np.allclose(itp(np.arange(1.0, n + 1)).cpu().numpy(), A, rtol=1.5e-8, atol=1e-14)
+        itp = m.interpolate(A, m.BSpline(m.Cubic(m.Flat(GT()))))
+        lb, ub = itp.bounds()[0]
+        g = m.gradient(itp, np.array([lb, ub], float)).cpu().numpy()
+        assert np.all(np.abs(g) <= 4 * np.finfo(float).eps)
+    xs = np.arange(1.0, 16)
+    p3 = lambda x: 1.5 + 0.3 * x - 0.07 * x**2 + 0.011 * x**3
+    itp = m.interpolate(p3(xs), m.BSpline(m.Cubic(m.Free(m.OnGrid()))))
+    q = np.linspace(1, 15, 301)
+    assert np.allclose(itp(q).cpu().numpy(), p3(q), rtol=1e-11, atol=1e-11)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnCell()))))
+    v = itp(np.array([0.5, n + 0.5])).cpu().numpy()
+    assert v[0] == pytest.approx(v[1], rel=1e-12)
+
+
+def test_devdocs_known_answer_on_gpu(pkg):
+    """docs/src/devdocs.md:96-190 through the GPU path."""
+    m = pkg
+    A = np.arange(1, 28, dtype=np.float64).reshape(3, 3, 3, order="F")
+    itp = m.interpolate(A, m.BSpline(m.Linear()))
+    v = itp(np.array([1.2]), np.array([1.4]), np.array([1.7])).cpu().numpy()
+    g = m.gradient(itp, np.array([1.2]), np.array([1.4]), np.array([1.7])).cpu().numpy()
+    assert v[0] == 8.7
+    assert tuple(g[0]) == (1.0, 3.000000000000001, 9.0)
+
+
+def test_unsupported_descriptors_are_reported(pkg):
+    """Outside the hot path the ABI returns a positive code and the host raises ValueError (ArgumentError)."""
+    m = pkg
+    A = np.random.default_rng(0).standard_normal((20, 20)).astype(np.float32)
+    itp = m.interpolate(A, (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Cubic(m.Line(m.OnCell())))))
+    etp = m.extrapolate(itp, m.Flat())
+    q = np.linspace(1, 20, 50, dtype=np.float32)
+    with pytest.raises(ValueError):
+        etp(q, q)  # Float32 coordinates widened on one axis only
+    assert np.isfinite(etp(q.astype(np.float64), q.astype(np.float64)).cpu().numpy()).all()
+    with pytest.raises(ValueError):
+        m.gradient(m.extrapolate(itp, ((m.Flat(), m.Line()), m.Flat())), q.astype(np.float64), q.astype(np.float64))
+
+
+def test_empty_and_broadcast_shapes(pkg, orc):
+    m = pkg
+    A = np.random.default_rng(1).standard_normal((15, 12))
+    itp = m.interpolate(A, m.BSpline(m.Quadratic(m.Line(m.OnGrid()))))
+    assert itp(np.zeros((0,)), np.zeros((0,))).shape == (0,)
+    x = np.linspace(1, 15, 7)[:, None]
+    y = np.linspace(1, 12, 5)[None, :]
+    out = itp(x, y)
+    assert out.shape == (7, 5)
+    host = orc.with_coefs(itp, itp.coefs.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), orc.evaluate(host, x, y)[0])
+    assert m.gradient(itp, x, y).shape == (7, 5, 2)
