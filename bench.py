@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B-spline hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+  3-D tricubic `Cubic(Periodic(OnGrid()))`, 512^3 Float32 volume: prefilter + 10^9 scattered queries.
+One step = `interpolate(A, it)` (copy + 3 prefilter passes) followed by `itp.(xs, ys, zs)` over one batch of
+queries per GPU.  `value` = queries evaluated by all ranks / step time (Gevals/s), inputs resident in HBM.
+`e2e` = the same through the public API with HOST buffers (pinned): H2D of the step's coordinates and D2H of
+its results inside the timed region.  The prefilter's own GB/s is reported beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--queries Q] [--impl reference]
+N > 1 is launched by torchrun (one rank per GPU, NCCL): the coefficient array is computed on rank 0 and
+replicated with an NCCL broadcast inside the timed step; queries are sharded (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 512
+DEFAULT_QUERIES = 10**9
+METRIC = "Gevals/s tricubic + prefilter GB/s (512^3 f32) at 1/2/4/8 B200 vs HBM peak"
+
+
+def measured_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                               "-i", str(self.gpu)], text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synthetic_volume(torch, dev, seed=20240601):
+    """Smooth sin-product field plus uniform noise, generated on the device."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    ax = torch.arange(1, N_GRID + 1, device=dev, dtype=torch.float32)
+    s = torch.sin(ax * (2 * np.pi * 3 / N_GRID))
+    A = s[:, None, None] * torch.cos(ax * (2 * np.pi * 5 / N_GRID))[None, :, None] * s[None, None, :]
+    A = A + 0.1 * (torch.rand((N_GRID,) * 3, device=dev, dtype=torch.float32, generator=g) - 0.5)
+    return A.contiguous()
+
+
+def synthetic_queries(torch, dev, nq, rank, seed=20240602):
+    g = torch.Generator(device=dev).manual_seed(seed + rank)
+    out = []
+    for _ in range(3):
+        x = torch.rand(nq, device=dev, dtype=torch.float32, generator=g) * (N_GRID - 1) + 1.0
+        out.append(x.clamp_(1.0, float(N_GRID)))
+    return out
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU path (C restatement in oracle/, all host threads) on a bounded
+    sample of the same workload.  Julia is not in the image, so kind = "port"."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    m = orc.pkg
+    threads = orc.num_threads()
+    n_s = 256                       # prefilter sample: 256^3 (1/8 of the volume)
+    nq_s = 2_000_000                # query sample per step
+    rng = np.random.default_rng(20240601)
+    A_s = rng.standard_normal((n_s,) * 3).astype(np.float32)
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    # evaluation sample runs on a full-size 512^3 coefficient array (random: timing only)
+    coefs = rng.standard_normal(N_GRID**3).astype(np.float32)
+    from interpolations_jl_b200.core import BSplineInterpolation
+    itp = BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, None)
+    q = [rng.uniform(1, N_GRID, nq_s).astype(np.float32) for _ in range(3)]
+    times_p, times_e = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.prefilter(A_s, it, nthreads=threads, fast=True)
+        t1 = time.perf_counter()
+        orc.evaluate(itp, *q, nthreads=threads, fast=True)
+        t2 = time.perf_counter()
+        if i >= args.warmup:
+            times_p.append(t1 - t0)
+            times_e.append(t2 - t1)
+    tp, te = float(np.median(times_p)), float(np.median(times_e))
+    gevals = nq_s / te / 1e9
+    pre_gbs = 2 * 4 * n_s**3 * 3 / tp / 1e9
+    # a step of the full workload = prefilter(512^3) + 1e9 queries; extrapolate linearly from the sample
+    step_s = tp * (N_GRID / n_s) ** 3 + te * (args.queries / nq_s)
+    value = args.queries / step_s / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gevals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: 3-D Cubic(Periodic(OnGrid())) 512^3 Float32, prefilter + 1e9 scattered queries",
+                   "queries_per_step": args.queries, "sampled": True},
+        "cpu_baseline": {"value": value, "unit": "Gevals/s", "cores": threads, "kind": "port",
+                         "sample": f"prefilter 256^3 f32 ({tp*1e3:.0f} ms, {pre_gbs:.2f} GB/s) + {nq_s} queries on a "
+                                   f"512^3 volume ({gevals*1e3:.2f} Mevals/s), scaled to 512^3 + {args.queries} queries; "
+                                   "Julia absent: C restatement of the reference (oracle/), OpenMP over lines/queries",
+                         "prefilter_gbs": pre_gbs, "eval_gevals": gevals},
+        "e2e": {"value": value, "unit": "Gevals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """Bounded CPU timing of the oracle port on the box's host cores (rank 0, N = 1 only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    m = orc.pkg
+    threads = orc.num_threads()
+    rng = np.random.default_rng(1)
+    n_s, nq_s = 256, 2_000_000
+    A_s = rng.standard_normal((n_s,) * 3).astype(np.float32)
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    coefs = rng.standard_normal(N_GRID**3).astype(np.float32)
+    from interpolations_jl_b200.core import BSplineInterpolation
+    itp = BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, None)
+    q = [rng.uniform(1, N_GRID, nq_s).astype(np.float32) for _ in range(3)]
+    orc.evaluate(itp, *[c[:1000] for c in q], nthreads=threads, fast=True)
+    t0 = time.perf_counter()
+    orc.prefilter(A_s, it, nthreads=threads, fast=True)
+    t1 = time.perf_counter()
+    orc.evaluate(itp, *q, nthreads=threads, fast=True)
+    t2 = time.perf_counter()
+    t3 = time.perf_counter()
+    orc.evaluate(itp, *[c[:200_000] for c in q], nthreads=1, fast=True)
+    t4 = time.perf_counter()
+    return {"value": nq_s / (t2 - t1) / 1e9, "unit": "Gevals/s", "cores": threads, "kind": "port",
+            "sample": f"{nq_s} tricubic queries on a random 512^3 Float32 volume, {threads} OpenMP threads "
+                      f"(1 thread: {0.2 / (t4 - t3):.2f} Mevals/s); prefilter 256^3: {(t1-t0)*1e3:.0f} ms = "
+                      f"{2*4*n_s**3*3/(t1-t0)/1e9:.2f} GB/s. Julia absent: C restatement of the reference (oracle/)",
+            "prefilter_gbs": 2 * 4 * n_s**3 * 3 / (t1 - t0) / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--queries", type=int, default=DEFAULT_QUERIES, help="queries per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sorted", type=int, default=1, help="use the L2-friendly ordered evaluation path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import b200_loader
+    m = b200_loader.load()
+    L = m._lib.lib()  # raises if the CUDA library is missing: there is no fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    nq = args.queries
+    A = synthetic_volume(torch, dev)
+    coords = synthetic_queries(torch, dev, nq, rank)
+
+    def step():
+        # rank 0 prefilters; the coefficient array is replicated over NVLink; every rank evaluates its shard
+        if rank == 0:
+            itp = m.interpolate(A, it, device=dev)
+            coefs = itp.coefs
+        else:
+            coefs = torch.empty(N_GRID**3, dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(coefs, src=0)
+        itp = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
+        if args.sorted:
+            return m.evaluate_sorted(itp, *coords)
+        return itp(*coords)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = L.b200itp_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        out = step()
+    ev[1].record()
+    barrier()
+    launches = L.b200itp_launch_count() - l0
+    t_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = t_ms.item() / args.steps
+    value = nq * world / (ms_per_step * 1e-3) / 1e9
+    checksum = float(out.double().sum().item())
+
+    # ---- kernel-level timings on this rank: evaluation kernel (dominant) and the prefilter passes
+    itp = m.interpolate(A, it, device=dev)
+
+    def time_fn(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    eval_fn = (lambda: m.evaluate_sorted(itp, *coords)) if args.sorted else (lambda: itp(*coords))
+    eval_ms = time_fn(eval_fn, max(2, args.steps))
+    work = itp.coefs.clone()
+    pre_ms = time_fn(lambda: m.prefilter_(work, itp.size, itp.its, local_rank), 10)
+    peak, peak_kind = measured_peak()
+    eval_bytes = nq * (12 + 4) + 4 * N_GRID**3          # coordinates in, results out, coefficients once
+    pre_bytes = 2 * 4 * N_GRID**3 * 3                   # one read + one write per axis pass
+    roof = {"bound": "hbm", "kernel": "evaluation (eval_kernel / ordered pipeline)",
+            "achieved": eval_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": None,
+            "algorithmic_bytes": eval_bytes, "ms": eval_ms}
+    roof_pre = {"bound": "hbm", "kernel": "prefilter (3 axis passes, 512^3 f32)",
+                "achieved": pre_bytes / (pre_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": pre_bytes / (pre_ms * 1e-3) / 1e9 / 8000,
+                "traffic": None, "algorithmic_bytes": pre_bytes, "ms": pre_ms}
+
+    # ---- end to end through the public API with host buffers (pinned): H2D coords + D2H result per step
+    del out
+    nq_e = nq
+    host_coords = [torch.empty(nq_e, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+    for h, c in zip(host_coords, coords):
+        h.copy_(c)
+    host_A = torch.empty((N_GRID,) * 3, dtype=torch.float32, pin_memory=True)
+    host_A.copy_(A)
+    host_out = torch.empty(nq_e, dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step_e2e():
+        if rank == 0:
+            Ad = host_A.to(dev, non_blocking=True)
+            coefs = m.interpolate(Ad, it, device=dev).coefs
+        else:
+            coefs = torch.empty(N_GRID**3, dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(coefs, src=0)
+        itp2 = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
+        dc = [h.to(dev, non_blocking=True) for h in host_coords]
+        r = m.evaluate_sorted(itp2, *dc) if args.sorted else itp2(*dc)
+        host_out.copy_(r, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_steps = max(2, min(args.steps, 3))
+    e0.record()
+    for _ in range(e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = nq_e * world / (te.item() / e_steps * 1e-3) / 1e9
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gevals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: 3-D Cubic(Periodic(OnGrid())) 512^3 Float32, prefilter + 1e9 scattered queries",
+                       "queries_per_gpu_per_step": nq, "ordered_eval": bool(args.sorted),
+                       "l2": "inputs larger than L2 (coefficients 512 MiB, coordinates 12 B/query)",
+                       "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
+            "prefilter_gbs": roof_pre["achieved"], "prefilter_ms": pre_ms, "eval_gevals_kernel": nq / (eval_ms * 1e-3) / 1e9,
+            "roofline": roof, "roofline_prefilter": roof_pre,
+            "e2e": {"value": e2e_val, "unit": "Gevals/s", "h2d_bytes_per_step": 12 * nq_e + (4 * N_GRID**3 if True else 0),
+                    "d2h_bytes_per_step": 4 * nq_e},
+            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ struct Chain {
   int out_f64;
   bool homogeneous;
   int e_wide, s_wide, w_wide;
+  int s_wide_x, w_wide_x;  // the in-bounds gradient path of an Extrapolation uses x itself
 };
 
 inline int tmax(int a, int b) { return a > b ? a : b; }
@@ -54,6 +55,13 @@ int derive_chain(const b200itp_desc *D, Chain &c) {
   c.e_wide = c.t1[0] == B200ITP_TAG_F64;
   c.s_wide = c.t2[0] == B200ITP_TAG_F64;
   c.w_wide = c.tw[0] == B200ITP_TAG_F64;
+  {
+    int t = c.t0;
+    if (D->has_scale) t = tmax(t, D->range_tag[0]);
+    c.s_wide_x = t == B200ITP_TAG_F64;
+    if (D->has_scale) t = tmax(t, D->inner_tag[0]);
+    c.w_wide_x = t == B200ITP_TAG_F64;
+  }
   return 0;
 }
 
@@ -114,6 +122,8 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
   P.has_scale = D->has_scale != 0;
   P.e_wide = c.e_wide;
   P.s_wide = c.s_wide;
+  P.s_wide_x = c.s_wide_x;
+  P.w_wide_x = c.w_wide_x;
   P.etp_kind = D->etp_kind;
   P.pair_mask = D->etp_kind == B200ITP_ETP_FLAGS ? D->etp_pair_mask : 0;
   P.fill = D->fill_value;

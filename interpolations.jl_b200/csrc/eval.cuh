@@ -37,6 +37,8 @@ struct EvalParams {
   // where a Float32 coordinate becomes Float64 (only meaningful when TX=float, TW=double)
   int e_wide;  // extrapolation stage runs in TW
   int s_wide;  // coordlookup runs in TW
+  int s_wide_x;  // same, for the in-bounds gradient path that bypasses the extrapolation mapping
+  int w_wide_x;  // weights of that path are computed in TW (else in TX)
   // extrapolation
   int etp_kind;
   int etp_lo[4], etp_hi[4];
@@ -360,6 +362,79 @@ __device__ __forceinline__ void store_out(void *p, long long i, TO v, int out_f6
     reinterpret_cast<float *>(p)[i] = (float)v;
 }
 
+// B-spline stage of one query: positions, weights (type TWW) and the nested reduction; results are
+// widened (exactly) to TAO.
+template <int N, int DEG, typename TC, typename TWW, typename TAO>
+__device__ __forceinline__ void bspline_stage(const EvalParams &P, const TC *coefs, const TWW (&xl)[N], bool need_grad,
+                                              TAO &val_out, TAO (&grad_out)[N], int (&first_idx)[N], unsigned &br) {
+  using TW = TWW;
+  using TA = typename Promote<TWW, TC>::type;
+  TA val = TA(0);
+  TA grad[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) grad[d] = TA(0);
+  AxisTaps<DEG, TW> ax[N];
+  if (need_grad) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) axis_setup<DEG, TW, true>(P, d, xl[d], ax[d]);
+    Reduce<N, DEG, TC, TW, true, 0>::run(P, ax, coefs, val, grad);
+  } else {
+#pragma unroll
+    for (int d = 0; d < N; ++d) axis_setup<DEG, TW, false>(P, d, xl[d], ax[d]);
+    bool done = false;
+    if constexpr (sizeof(TC) == 4 && N <= 3 && (DEG == 2 || DEG == 3)) {
+      if (ax[0].contiguous && P.vec_ok) {
+        // rows of axis-1 taps through aligned 128-bit loads, reduction in the reference order
+        constexpr int L = DEG + 1;
+        constexpr int ROWS = N == 1 ? 1 : (N == 2 ? L : L * L);
+        float c[ROWS][4];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          long long lin = ax[0].pos[0];
+          if (N >= 2) lin += (long long)ax[1].pos[N == 2 ? r : r % L] * P.stride[1];
+          if (N >= 3) lin += (long long)ax[2].pos[r / L] * P.stride[2];
+          load_row4<N, DEG, TW>(reinterpret_cast<const float *>(coefs), lin, P.total, c[r]);
+        }
+        // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )
+#pragma unroll
+        for (int k0 = 0; k0 < L; ++k0) {
+          TA v0;
+          if (N == 1) {
+            v0 = (TA)c[0][k0];
+          } else {
+#pragma unroll
+            for (int k1 = 0; k1 < L; ++k1) {
+              TA v1;
+              if (N == 2) {
+                v1 = (TA)c[k1][k0];
+              } else {
+#pragma unroll
+                for (int k2 = 0; k2 < L; ++k2) {
+                  const TA t2 = (TA)ax[2].wv[k2] * (TA)c[k2 * L + k1][k0];
+                  v1 = k2 == 0 ? t2 : t2 + v1;
+                }
+              }
+              const TA t1 = (TA)ax[1].wv[k1] * v1;
+              v0 = k1 == 0 ? t1 : t1 + v0;
+            }
+          }
+          const TA t0 = (TA)ax[0].wv[k0] * v0;
+          val = k0 == 0 ? t0 : t0 + val;
+        }
+        done = true;
+      }
+    }
+    if (!done) Reduce<N, DEG, TC, TW, false, 0>::run(P, ax, coefs, val, grad);
+  }
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    first_idx[d] = ax[d].pos[0] + P.coef_first[d];
+    if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
+    grad_out[d] = (TAO)grad[d];
+  }
+  val_out = (TAO)val;
+}
+
 // MODE 0: values; MODE 1: gradients
 template <int N, int DEG, typename TC, typename TX, typename TW, int MODE>
 __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalParams P) {
@@ -438,7 +513,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalP
       for (int d = 0; d < N; ++d) {
         TW xv = use_x ? (TW)x[d] : xs[d];
         if (P.has_scale) {
-          if (sizeof(TX) == sizeof(TW) || P.s_wide) {
+          if (sizeof(TX) == sizeof(TW) || (use_x ? P.s_wide_x : P.s_wide)) {
             xv = (xv - (TW)P.rfirst[d]) / (TW)P.rstep[d] + TW(1);
           } else {
             const TX y = ((TX)xv - (TX)P.rfirst[d]) / (TX)P.rstep[d] + TX(1);
@@ -449,69 +524,24 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalP
         }
         xl[d] = xv;
       }
-      // ---- B-spline stage
+      // ---- B-spline stage (weights in TW; the in-bounds gradient of an extrapolated Float32 query whose
+      //      only widening came from the extrapolation bounds is computed in TX, as the reference does)
       const bool need_grad = MODE == 1 || (moved && P.any_line);
-      AxisTaps<DEG, TW> ax[N];
-      if (need_grad) {
+      bool narrow = false;
+      if constexpr (MODE == 1 && sizeof(TX) != sizeof(TW)) narrow = use_x && !P.w_wide_x;
+      if (narrow) {
+        if constexpr (MODE == 1 && sizeof(TX) != sizeof(TW)) {
+          TX xn[N];
 #pragma unroll
-        for (int d = 0; d < N; ++d) axis_setup<DEG, TW, true>(P, d, xl[d], ax[d]);
-        Reduce<N, DEG, TC, TW, true, 0>::run(P, ax, coefs, val, grad);
-        if (P.has_scale) {
-#pragma unroll
-          for (int d = 0; d < N; ++d) grad[d] = grad[d] / (TA)P.rstep[d];  // rescale_gradient scaling.jl:116,137
+          for (int d = 0; d < N; ++d) xn[d] = (TX)xl[d];
+          bspline_stage<N, DEG, TC, TX, TA>(P, coefs, xn, true, val, grad, first_idx, br);
         }
       } else {
-#pragma unroll
-        for (int d = 0; d < N; ++d) axis_setup<DEG, TW, false>(P, d, xl[d], ax[d]);
-        bool done = false;
-        if constexpr (sizeof(TC) == 4 && N <= 3 && (DEG == 2 || DEG == 3)) {
-          if (ax[0].contiguous && P.vec_ok) {
-            // rows of axis-1 taps through aligned 128-bit loads, reduction in the reference order
-            constexpr int L = DEG + 1;
-            constexpr int ROWS = N == 1 ? 1 : (N == 2 ? L : L * L);
-            float c[ROWS][4];
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-              long long lin = ax[0].pos[0];
-              if (N >= 2) lin += (long long)ax[1].pos[N == 2 ? r : r % L] * P.stride[1];
-              if (N >= 3) lin += (long long)ax[2].pos[r / L] * P.stride[2];
-              load_row4<N, DEG, TW>(reinterpret_cast<const float *>(coefs), lin, P.total, c[r]);
-            }
-            // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )
-#pragma unroll
-            for (int k0 = 0; k0 < L; ++k0) {
-              TA v0;
-              if (N == 1) {
-                v0 = (TA)c[0][k0];
-              } else {
-#pragma unroll
-                for (int k1 = 0; k1 < L; ++k1) {
-                  TA v1;
-                  if (N == 2) {
-                    v1 = (TA)c[k1][k0];
-                  } else {
-#pragma unroll
-                    for (int k2 = 0; k2 < L; ++k2) {
-                      const TA t2 = (TA)ax[2].wv[k2] * (TA)c[k2 * L + k1][k0];
-                      v1 = k2 == 0 ? t2 : t2 + v1;
-                    }
-                  }
-                  const TA t1 = (TA)ax[1].wv[k1] * v1;
-                  v0 = k1 == 0 ? t1 : t1 + v0;
-                }
-              }
-              const TA t0 = (TA)ax[0].wv[k0] * v0;
-              val = k0 == 0 ? t0 : t0 + val;
-            }
-            done = true;
-          }
-        }
-        if (!done) Reduce<N, DEG, TC, TW, false, 0>::run(P, ax, coefs, val, grad);
+        bspline_stage<N, DEG, TC, TW, TA>(P, coefs, xl, need_grad, val, grad, first_idx, br);
       }
+      if (need_grad && P.has_scale) {
 #pragma unroll
-      for (int d = 0; d < N; ++d) {
-        first_idx[d] = ax[d].pos[0] + P.coef_first[d];
-        if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
+        for (int d = 0; d < N; ++d) grad[d] = grad[d] / (TA)P.rstep[d];  // rescale_gradient scaling.jl:116,137
       }
       // ---- extrapolate_value / extrapolate_gradient (extrapolation.jl:166-185)
       if (P.etp_kind == B200ITP_ETP_FLAGS) {

@@ -486,83 +486,130 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(const T *__restrict__ src
 }
 
 // ================================================================== host drivers
+// Factor arrays longer than kSurrogate rows are represented by their first and last kSurrogate/2 rows:
+// the LU factors of the reference's systems are constant in between (checked by the caller), the
+// Woodbury columns have decayed long before, so the plan built from the short system is the plan of
+// the long one (host work O(1) instead of O(n) for 10^6-sample lines).
+constexpr int64_t kSurrogate = 1024;
+
 template <typename T>
-static int run_axis(int dev, T *coefs, int ndims, const int64_t *size, int axis, int64_t n, const T *dl, const T *d,
-                    const T *du, int k, const int32_t *urow, const int32_t *vcol, const T *Cp, cudaStream_t st) {
+struct AxisJob {
   AxisPlan<T> plan;
   FullTables<T> F;
   bool fast_ok = false;
-  int rc = build_plan<T>(n, dl, d, du, k, urow, vcol, Cp, plan, F, fast_ok);
+};
+
+template <typename T>
+static int make_job(int64_t n, int64_t ns, const T *dl, const T *d, const T *du, int k, const int32_t *urow,
+                    const int32_t *vcol, const T *Cp, AxisJob<T> &job) {
+  // urow/vcol are given in the index space of the length-ns arrays
+  int rc = build_plan<T>(ns, dl, d, du, k, urow, vcol, Cp, job.plan, job.F, job.fast_ok);
   if (rc) B200_FAIL(rc, "prefilter: cannot build the axis plan (n=%lld, k=%d)", (long long)n, k);
+  if (ns != n) {
+    if (!job.fast_ok) B200_FAIL(B200ITP_E_UNSUPPORTED, "prefilter: factors of a long axis do not settle");
+    job.plan.n = (int)n;
+    for (int j = 0; j < k; ++j)
+      if (job.plan.vrow[j] > ns / 2) job.plan.vrow[j] += (int)(n - ns);
+  }
+  return 0;
+}
+
+// one axis pass: src -> dst (dst may equal src when the pass is not segmented); *segmented tells the caller
+template <typename T>
+static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *size, int axis, const AxisJob<T> &job,
+                       int nseg, int seglen, cudaStream_t st) {
+  const int64_t n = size[axis];
   int64_t R1 = 1, R2 = 1;
   for (int i = 0; i < axis; ++i) R1 *= size[i];
   for (int i = axis + 1; i < ndims; ++i) R2 *= size[i];
   const int64_t lines = R1 * R2;
-  if (lines == 0) return 0;
-  constexpr int B = Tune<T>::B;
-
-  if (!fast_ok) {
-    // tables to the device (small: this path is for short lines)
+  if (!job.fast_ok) {
     void *tab = nullptr;
     const size_t bytes = sizeof(T) * (size_t)n * 5;
-    rc = scratch_get(dev, 1, bytes, &tab);
+    int rc = scratch_get(dev, 1, bytes, &tab);
     if (rc) return rc;
     std::vector<T> h((size_t)n * 5);
-    std::copy(F.L.begin(), F.L.end(), h.begin());
-    std::copy(F.U.begin(), F.U.end(), h.begin() + n);
-    std::copy(F.Dinv.begin(), F.Dinv.end(), h.begin() + 2 * n);
-    std::copy(F.z1.begin(), F.z1.end(), h.begin() + 3 * n);
-    std::copy(F.zn.begin(), F.zn.end(), h.begin() + 4 * n);
+    std::copy(job.F.L.begin(), job.F.L.end(), h.begin());
+    std::copy(job.F.U.begin(), job.F.U.end(), h.begin() + n);
+    std::copy(job.F.Dinv.begin(), job.F.Dinv.end(), h.begin() + 2 * n);
+    std::copy(job.F.z1.begin(), job.F.z1.end(), h.begin() + 3 * n);
+    std::copy(job.F.zn.begin(), job.F.zn.end(), h.begin() + 4 * n);
     B200_CUDA_OK(cudaMemcpyAsync(tab, h.data(), bytes, cudaMemcpyHostToDevice, st));
-    B200_CUDA_OK(cudaStreamSynchronize(st));  // h is a stack-owned staging buffer
+    B200_CUDA_OK(cudaStreamSynchronize(st));  // h is a function-local staging buffer
     const T *t = (const T *)tab;
     const int64_t nb = (lines + 127) / 128;
-    prefilter_general_kernel<T><<<(unsigned)nb, 128, 0, st>>>(coefs, coefs, (int)n, R1, R2, t, t + n, t + 2 * n,
-                                                               t + 3 * n, t + 4 * n, plan);
+    prefilter_general_kernel<T><<<(unsigned)nb, 128, 0, st>>>(src, dst, (int)n, R1, R2, t, t + n, t + 2 * n, t + 3 * n,
+                                                               t + 4 * n, job.plan);
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
-  }
-
-  // segmentation: only when there are too few lines to fill the machine
-  const int sms = sm_count(dev);
-  const int64_t want = (int64_t)sms * 1024;
-  int nseg = 1;
-  if (lines < want / 2) {
-    const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
-    nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
-  }
-  int seglen = (int)(((n + nseg - 1) / nseg + B - 1) / B * B);
-  nseg = (int)((n + seglen - 1) / seglen);
-  const T *src = coefs;
-  T *dst = coefs;
-  void *tmp = nullptr;
-  const size_t abytes = sizeof(T) * (size_t)lines * (size_t)n;
-  if (nseg > 1) {  // out of place: segments read each other's rows
-    rc = scratch_get(dev, 0, abytes, &tmp);
-    if (rc) return rc;
-    dst = (T *)tmp;
   }
   if (axis == 0) {
     constexpr int ITEMS = Tune<T>::ITEMS;
     const int64_t nlb = (lines + ITEMS - 1) / ITEMS;
     const int64_t blocks = nlb * nseg;
     if (blocks > 0x7fffffff || nlb > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
-    const bool vec = (n % (16 / (int)sizeof(T)) == 0) && ((uintptr_t)coefs % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    const bool vec = (n % (16 / (int)sizeof(T)) == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
     if (vec)
-      prefilter_contig_kernel<T, true><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, plan, lines, (int)nlb, seglen, nseg);
+      prefilter_contig_kernel<T, true><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, job.plan, lines, (int)nlb, seglen, nseg);
     else
-      prefilter_contig_kernel<T, false><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, plan, lines, (int)nlb, seglen, nseg);
+      prefilter_contig_kernel<T, false><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, job.plan, lines, (int)nlb, seglen, nseg);
   } else {
     const int64_t nb1 = (R1 + 127) / 128;
     const int64_t blocks = nb1 * nseg * R2;
     if (blocks > 0x7fffffff || nb1 > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
-    prefilter_strided_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(src, dst, plan, R1, (int)nb1, seglen, nseg);
+    prefilter_strided_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(src, dst, job.plan, R1, (int)nb1, seglen, nseg);
   }
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
-  if (nseg > 1) {
-    B200_CUDA_OK(cudaMemcpyAsync(coefs, tmp, abytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// segmentation: only when there are too few lines to fill the machine
+template <typename T>
+static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int &nseg, int &seglen) {
+  constexpr int B = Tune<T>::B;
+  nseg = 1;
+  const int64_t want = (int64_t)sm_count(dev) * 1024;
+  if (fast_ok && lines < want / 2) {
+    const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
+    nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
+  }
+  seglen = (int)(((n + nseg - 1) / nseg + B - 1) / B * B);
+  nseg = (int)((n + seglen - 1) / seglen);
+}
+
+// Runs the axis passes described by jobs[] (nullptr = skip).  Segmented passes are out of place and
+// ping-pong between `coefs` and a scratch array; the result always ends in `coefs`.
+template <typename T>
+static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const AxisJob<T> *const *jobs,
+                      cudaStream_t st) {
+  int64_t total = 1;
+  for (int i = 0; i < ndims; ++i) total *= size[i];
+  if (total == 0) return 0;
+  T *cur = coefs;
+  T *other = nullptr;
+  for (int ax = 0; ax < ndims; ++ax) {
+    if (!jobs[ax]) continue;
+    const int64_t n = size[ax];
+    int nseg, seglen;
+    choose_segments<T>(dev, total / n, n, jobs[ax]->fast_ok, nseg, seglen);
+    T *dst = cur;
+    if (nseg > 1) {
+      if (!other) {
+        void *tmp = nullptr;
+        int rc = scratch_get(dev, 0, sizeof(T) * (size_t)total, &tmp);
+        if (rc) return rc;
+        other = (T *)tmp;
+      }
+      dst = cur == coefs ? other : coefs;
+    }
+    int rc = launch_axis<T>(dev, cur, dst, ndims, size, ax, *jobs[ax], nseg, seglen, st);
+    if (rc) return rc;
+    cur = dst;
+  }
+  if (cur != coefs) {
+    B200_CUDA_OK(cudaMemcpyAsync(coefs, cur, sizeof(T) * (size_t)total, cudaMemcpyDeviceToDevice, st));
     count_launch();
   }
   return 0;
@@ -571,17 +618,59 @@ static int run_axis(int dev, T *coefs, int ndims, const int64_t *size, int axis,
 template <typename T>
 static int prefilter_axis_typed(int dev, void *coefs, int ndims, const int64_t *size, int axis,
                                 const b200itp_axis_system *sys, cudaStream_t st) {
-  return run_axis<T>(dev, (T *)coefs, ndims, size, axis, sys->n, (const T *)sys->dl, (const T *)sys->d,
-                     (const T *)sys->du, sys->k, sys->urow, sys->vcol, (const T *)sys->Cp, st);
+  const int64_t n = sys->n;
+  const T *dl = (const T *)sys->dl, *d = (const T *)sys->d, *du = (const T *)sys->du;
+  AxisJob<T> job;
+  int rc;
+  if (n <= kSurrogate) {
+    rc = make_job<T>(n, n, dl, d, du, sys->k, sys->urow, sys->vcol, (const T *)sys->Cp, job);
+  } else {
+    const int64_t h = kSurrogate / 2;
+    // the middle rows must equal the settled values
+    const T tol = T(8) * std::numeric_limits<T>::epsilon();
+    for (int64_t r = h; r < n - h; ++r)
+      if (std::fabs(dl[r - 1] - dl[h - 1]) > tol * std::fabs(dl[h - 1]) || std::fabs(d[r] - d[h]) > tol * std::fabs(d[h]) ||
+          du[r] != du[h])
+        B200_FAIL(B200ITP_E_UNSUPPORTED, "prefilter_axis: LU factors of a long axis do not settle (row %lld)", (long long)r);
+    std::vector<T> sdl(kSurrogate - 1), sd(kSurrogate), sdu(kSurrogate - 1);
+    for (int64_t i = 0; i < kSurrogate; ++i) sd[i] = i < h ? d[i] : d[n - kSurrogate + i];
+    for (int64_t i = 0; i < kSurrogate - 1; ++i) {
+      sdl[i] = i <= h - 2 ? dl[i] : dl[n - kSurrogate + i];
+      sdu[i] = i <= h - 1 ? du[i] : du[n - kSurrogate + i];
+    }
+    int32_t ur[B200ITP_MAX_WOODBURY], vc[B200ITP_MAX_WOODBURY];
+    for (int j = 0; j < sys->k; ++j) {
+      auto remap = [&](int32_t r, int32_t &out) {
+        if (r >= 1 && r <= h)
+          out = r;
+        else if (r > n - h && r <= n)
+          out = (int32_t)(r - (n - kSurrogate));
+        else
+          return false;
+        return true;
+      };
+      if (!remap(sys->urow[j], ur[j]) || !remap(sys->vcol[j], vc[j]))
+        B200_FAIL(B200ITP_E_UNSUPPORTED, "prefilter_axis: Woodbury entries must be near the ends of the axis");
+    }
+    rc = make_job<T>(n, kSurrogate, sdl.data(), sd.data(), sdu.data(), sys->k, ur, vc, (const T *)sys->Cp, job);
+  }
+  if (rc) return rc;
+  const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
+  jobs[axis] = &job;
+  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st);
 }
 
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
                                const int32_t *bc, const int32_t *grid, cudaStream_t st) {
+  AxisJob<T> store[B200ITP_MAX_DIMS];
+  const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int ax = 0; ax < ndims; ++ax) {
     if (degree[ax] == B200ITP_LINEAR) continue;  // prefiltering.jl:30
+    const int64_t n = size[ax];
+    const int64_t ns = n > kSurrogate ? kSurrogate : n;
     HostSystem<T> S;
-    int rc = assemble_system<T>(size[ax], degree[ax], bc[ax], grid[ax], S);
+    int rc = assemble_system<T>(ns, degree[ax], bc[ax], grid[ax], S);
     if (rc == B200ITP_E_UNSUPPORTED) {
       if (degree[ax] == B200ITP_CUBIC || degree[ax] == B200ITP_QUADRATIC) continue;  // M === nothing: left unfiltered
       B200_FAIL(rc, "prefilter: unsupported degree %d on axis %d", degree[ax], ax);
@@ -590,11 +679,11 @@ static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *s
                       (long long)size[ax]);
     rc = woodbury_cp<T>(S);
     if (rc) B200_FAIL(rc, "prefilter: singular Woodbury capacitance matrix on axis %d", ax);
-    rc = run_axis<T>(dev, (T *)coefs, ndims, size, ax, S.n, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol,
-                     S.Cp, st);
+    rc = make_job<T>(n, ns, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol, S.Cp, store[ax]);
     if (rc) return rc;
+    jobs[ax] = &store[ax];
   }
-  return 0;
+  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st);
 }
 
 }  // namespace b200itp
