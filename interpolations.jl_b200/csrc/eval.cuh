@@ -181,6 +181,9 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
   const int cf = P.coef_first[d];
   A.edge = false;
   int first;  // index of the first tap in the parent index space
+  // NaN coordinates (undefined in the reference: unsafe_trunc(Int, NaN)) must not fault: the taps are
+  // taken at node 1 and the NaN weights make the result NaN.
+  const bool isnan_x = !(x == x);
   if (deg == B200ITP_CUBIC) {
     TW xf;
     if (!per) {  // cubic.jl:40-46, floorbounds indexing.jl:183-187
@@ -198,7 +201,7 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       xf = s_floor<TW>(x);
     }
     const TW dx = x - xf;
-    first = (int)xf - 1;
+    first = isnan_x ? 0 : (int)xf - 1;
     A.L = 4;
     // value_weights cubic.jl:63-69, constants convert(T, SimpleRatio) = T(p)/T(q)
     const TW omd = TW(1) - dx;
@@ -226,7 +229,7 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       A.edge = true;
     }
     const TW dx = x - xm;
-    first = (int)xm - 1;
+    first = isnan_x ? 0 : (int)xm - 1;
     A.L = 3;
     const TW a = dx - TW(0.5), b = dx + TW(0.5);  // quadratic.jl:45-53
     A.wv[0] = (a * a) / TW(2);
@@ -248,7 +251,7 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       A.edge = true;
     }
     const TW dx = x - f;
-    first = (int)f;
+    first = isnan_x ? 1 : (int)f;
     A.L = 2;
     A.wv[0] = TW(1) - dx;
     A.wv[1] = dx;

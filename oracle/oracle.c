@@ -196,7 +196,7 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
       xf = floor(x.v); /* cubic.jl:50-57 */
     }
     dx = mk(rnd(t, x.v - xf), t);
-    xi = (int64_t)xf; /* fast_trunc, utils.jl:40 */
+    xi = isnan(x.v) ? 1 : (int64_t)xf; /* fast_trunc, utils.jl:40 (NaN is undefined there: node 1, result NaN) */
     A->L = 4;
     for (int j = 0; j < 4; j++) { /* expand_index cubic.jl:59-61 */
       int64_t idx = xi - 1 + j;
@@ -230,7 +230,7 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
       A->edge = 1;
     }
     dx = mk(rnd(t, x.v - xm), t);
-    xi = (int64_t)xm;
+    xi = isnan(x.v) ? 1 : (int64_t)xm;
     A->L = 3;
     for (int j = 0; j < 3; j++) { /* quadratic.jl:57-60 */
       int64_t idx = xi - 1 + j;
@@ -253,7 +253,7 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
       f = rnd(t, f - 1.0);
       A->edge = 1;
     }
-    xi = (int64_t)f;
+    xi = isnan(x.v) ? 1 : (int64_t)f;
     dx = mk(rnd(t, x.v - f), t);
     A->L = 2;
     for (int j = 0; j < 2; j++) {

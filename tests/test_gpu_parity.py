@@ -224,7 +224,11 @@ def test_eval_extrapolation_flags_bit_exact(pkg, orc, coord_dtype):
             coords = []
             for d in range(2):
                 x = rng.uniform(-3 * A.shape[d], 4 * A.shape[d], 6000)
-                x[:8] = [1.0, A.shape[d], 0.5, A.shape[d] + 0.5, -np.inf, np.inf, 1e30, -1e30]
+                # +-Inf is defined for Flat/Line (test/scaling/withextrap.jl:12-13); under Periodic/Reflect it
+                # gives mod(Inf, T) = NaN, which the reference leaves undefined: checked separately below
+                names = repr(et)
+                big = [-np.inf, np.inf] if ("Periodic" not in names and "Reflect" not in names) else [-1e6, 1e6]
+                x[:8] = [1.0, A.shape[d], 0.5, A.shape[d] + 0.5, big[0], big[1], 1e30, -1e30]
                 x[8:2000] = rng.uniform(0.4, A.shape[d] + 0.6, 1992)
                 coords.append(x.astype(coord_dtype))
             pair = any(isinstance(f, tuple) for f in (et if isinstance(et, tuple) else (et,)))
@@ -344,3 +348,20 @@ def test_empty_and_broadcast_shapes(pkg, orc):
     host = orc.with_coefs(itp, itp.coefs.cpu().numpy())
     assert np.array_equal(out.cpu().numpy(), orc.evaluate(host, x, y)[0])
     assert m.gradient(itp, x, y).shape == (7, 5, 2)
+
+
+def test_nan_and_inf_coordinates_never_fault(pkg):
+    """NaN coordinates (and +-Inf under Periodic/Reflect, where mod(Inf, T) = NaN) are undefined in the reference
+    (`unsafe_trunc(Int, NaN)`, utils.jl:40); the kernels must return NaN without faulting."""
+    m = pkg
+    A = np.random.default_rng(2).standard_normal((16, 14)).astype(np.float32)
+    bad = np.array([np.nan, np.inf, -np.inf, 3.0], np.float32)
+    ok = np.array([2.5, 2.5, 2.5, 2.5], np.float32)
+    for it in (m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Quadratic(m.Flat(m.OnCell()))), m.BSpline(m.Linear())):
+        itp = m.interpolate(A, it)
+        for et in (m.Periodic(), m.Reflect(), m.Flat(), m.Line()):
+            etp = m.extrapolate(itp, et)
+            v = etp(bad, ok).cpu().numpy()
+            g = m.gradient(etp, bad, ok).cpu().numpy()
+            assert np.isnan(v[0]) and np.isfinite(v[3])
+            assert np.isnan(g[0]).any() and np.isfinite(g[3]).all()
