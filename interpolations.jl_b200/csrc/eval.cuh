@@ -134,7 +134,7 @@ __device__ __forceinline__ bool etp_inbounds(const EvalParams &P, int d, S x, S 
   if (flo == B200ITP_BC_THROW) {
     if (!(l <= x)) return true;
   } else if (flo == B200ITP_BC_FLAT || flo == B200ITP_BC_LINE) {
-    x = l > x ? l : x;
+    x = x < l ? l : x;  // max(l, x); NaN propagates like Julia's max
   } else if (flo == B200ITP_BC_PERIODIC) {
     x = etp_periodic<S>(P, d, x);
   } else if (flo == B200ITP_BC_REFLECT) {
@@ -146,7 +146,7 @@ __device__ __forceinline__ bool etp_inbounds(const EvalParams &P, int d, S x, S 
       return true;
     }
   } else if (fhi == B200ITP_BC_FLAT || fhi == B200ITP_BC_LINE) {
-    x = x < u ? x : u;
+    x = x > u ? u : x;  // min(x, u)
   } else if (fhi == B200ITP_BC_PERIODIC) {
     x = etp_periodic<S>(P, d, x);
   } else if (fhi == B200ITP_BC_REFLECT) {

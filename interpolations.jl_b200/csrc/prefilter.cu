@@ -27,7 +27,10 @@
 #include "common.cuh"
 #include "systems.hpp"
 
+#include <map>
+#include <memory>
 #include <mutex>
+#include <tuple>
 
 namespace b200itp {
 
@@ -204,6 +207,8 @@ __device__ __forceinline__ void pipeline_step(const AxisPlan<T> &p, int r0, int 
 // ================================================================== kernel: axis > 1 (strided lines)
 // Work item = (i1 in [0,R1), segment, i2 in [0,R2)); thread <-> i1 so a warp touches 32 consecutive
 // addresses in every row.  Rows [s, e] of the segment, s = 1 + seg*seglen (seglen multiple of B).
+// The loads of block b+1 are issued before block b is processed (register double buffering), so
+// every thread keeps B independent loads in flight while it runs the two recurrences.
 template <typename T>
 __global__ void __launch_bounds__(128) prefilter_strided_kernel(const T *src, T *dst,
                                                                 const __grid_constant__ AxisPlan<T> p, int64_t R1,
@@ -228,31 +233,48 @@ __global__ void __launch_bounds__(128) prefilter_strided_kernel(const T *src, T 
     woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[(int64_t)(r - 1) * R1]; }, c1, cn);
 
   const int bs = (s - 1) / B, be = (e - 1) / B;
-  T yprev[B], v[B], xout[B];
+  const int bfirst = bs > 0 ? bs - 1 : bs;
+  T yprev[B], v[B], xout[B], nxt[B];
   T carry = T(0);
   int cnt_prev = 0;
-#pragma unroll 1
-  for (int bi = (bs > 0 ? bs - 1 : bs); bi <= be + 1; ++bi) {
+
+  auto load_block = [&](int bi, T(&dstv)[B]) {
     const int r0 = 1 + bi * B;
     const int cnt = max(0, min(B, n - r0 + 1));
+    const T *pr = in + (int64_t)(r0 - 1) * R1;
     if (cnt == B) {
 #pragma unroll
-      for (int j = 0; j < B; ++j) v[j] = in[(int64_t)(r0 - 1 + j) * R1];
+      for (int j = 0; j < B; ++j) dstv[j] = pr[(int64_t)j * R1];
     } else {
 #pragma unroll
-      for (int j = 0; j < B; ++j) v[j] = j < cnt ? in[(int64_t)(r0 - 1 + j) * R1] : T(0);
+      for (int j = 0; j < B; ++j) dstv[j] = j < cnt ? pr[(int64_t)j * R1] : T(0);
+    }
+  };
+
+  constexpr bool PREFETCH = sizeof(T) == 4;  // Float64: 4 arrays of 32 doubles would spill
+  if (PREFETCH) load_block(bfirst, nxt);
+#pragma unroll 1
+  for (int bi = bfirst; bi <= be + 1; ++bi) {
+    const int r0 = 1 + bi * B;
+    const int cnt = max(0, min(B, n - r0 + 1));
+    if (PREFETCH) {
+#pragma unroll
+      for (int j = 0; j < B; ++j) v[j] = nxt[j];
+      if (bi <= be) load_block(bi + 1, nxt);  // prefetch: in flight during the recurrences below
+    } else {
+      load_block(bi, v);
     }
     const bool emit = bi > bs;
     pipeline_step<T, B>(p, r0, cnt, v, yprev, cnt_prev, carry, emit, c1, cn, xout);
     if (emit) {
-      const int rp = r0 - B;
+      T *po = out + (int64_t)(r0 - B - 1) * R1;
       if (cnt_prev == B) {
 #pragma unroll
-        for (int j = 0; j < B; ++j) out[(int64_t)(rp - 1 + j) * R1] = xout[j];
+        for (int j = 0; j < B; ++j) po[(int64_t)j * R1] = xout[j];
       } else {
 #pragma unroll
         for (int j = 0; j < B; ++j)
-          if (j < cnt_prev) out[(int64_t)(rp - 1 + j) * R1] = xout[j];
+          if (j < cnt_prev) po[(int64_t)j * R1] = xout[j];
       }
     }
     if (bi >= bs) {
@@ -264,89 +286,121 @@ __global__ void __launch_bounds__(128) prefilter_strided_kernel(const T *src, T 
 }
 
 // ================================================================== kernel: axis 1 (contiguous lines)
-// A CTA owns ITEMS consecutive lines and walks them in chunks of 32 rows staged through shared memory.
-// Tile layout: row of 16-byte vectors per item with a pitch of VPI+1 vectors (odd), so that
-//   * the cooperative copy (8 or 16 consecutive threads per item) is conflict-free and coalesced,
+// Work item = (line, segment).  A CTA owns ITEMS consecutive items and walks them in chunks of 32 rows.
+// Input chunks are staged through a STAGES-deep ring of shared-memory tiles filled with cp.async
+// (LDGSTS, no register staging) two chunks ahead of the chunk being processed; results go through one
+// more tile and leave with vector stores.  Tile layout: one row of 16-byte vectors per item with a
+// pitch of VPI+1 vectors (odd), so that
+//   * the cooperative copies (consecutive threads on consecutive pieces of an item) are coalesced and
+//     conflict-free,
 //   * each thread's 128-bit reads/writes of its own item are conflict-free (8 consecutive items hit 8
 //     different 16-byte bank groups).
-template <typename T, bool VEC16>
+// VW = global vector width in bytes (16 when every line starts 16-byte aligned, else 8 or 4).
+__device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gsrc, int vw, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? vw : 0;
+  if (vw == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+  else if (vw == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T>
+struct ContigCfg {
+  static constexpr int B = Tune<T>::B;
+  static constexpr int ITEMS = Tune<T>::ITEMS;
+  static constexpr int CH = 32;
+  static constexpr int K = CH / B;
+  static constexpr int EPV = 16 / (int)sizeof(T);
+  static constexpr int VPI = CH / EPV;
+  static constexpr int PITCH = VPI + 1;
+  static constexpr int VPB = B / EPV;
+  static constexpr int STAGES = 3;
+  static constexpr size_t smem_bytes = (size_t)(STAGES + 1) * ITEMS * PITCH * 16 + (size_t)ITEMS * 16;
+};
+
+template <typename T, int VW>
 __global__ void __launch_bounds__(Tune<T>::ITEMS) prefilter_contig_kernel(const T *src, T *dst,
                                                                            const __grid_constant__ AxisPlan<T> p,
-                                                                           int64_t nlines, int nlb, int seglen,
-                                                                           int nseg) {
-  constexpr int B = Tune<T>::B;
-  constexpr int ITEMS = Tune<T>::ITEMS;
-  constexpr int CH = 32;                       // rows per chunk
-  constexpr int K = CH / B;                    // blocks per chunk
-  constexpr int EPV = 16 / (int)sizeof(T);     // elements per 16-byte vector
-  constexpr int VPI = CH / EPV;                // vectors per item per chunk
-  constexpr int PITCH = VPI + 1;               // in vectors
-  constexpr int VPB = B / EPV;                 // vectors per block
-  __shared__ uint4 tin[ITEMS * PITCH];
-  __shared__ uint4 tout[ITEMS * PITCH];
+                                                                           int64_t nitems, int nseg, int seglen) {
+  using Cfg = ContigCfg<T>;
+  constexpr int B = Cfg::B, ITEMS = Cfg::ITEMS, CH = Cfg::CH, K = Cfg::K, EPV = Cfg::EPV, VPI = Cfg::VPI;
+  constexpr int PITCH = Cfg::PITCH, VPB = Cfg::VPB, S = Cfg::STAGES;
+  constexpr int PPI = CH * (int)sizeof(T) / VW;  // pieces per item per chunk
+  constexpr int EPP = VW / (int)sizeof(T);       // elements per piece
+  extern __shared__ uint4 smem_dyn[];
+  uint4 *tin = smem_dyn;                          // S tiles
+  uint4 *tout = smem_dyn + S * ITEMS * PITCH;     // 1 tile
+  long long *s_base = reinterpret_cast<long long *>(tout + ITEMS * PITCH);  // element offset of row 1 of the item's line
+  int *s_ci0 = reinterpret_cast<int *>(s_base + ITEMS);                      // global chunk index of the item's chunk 0
 
   const int tid = threadIdx.x;
-  int64_t bid = blockIdx.x;
-  const int lb = (int)(bid % nlb);
-  const int seg = (int)(bid / nlb);
-  (void)nseg;
-  const int64_t l0 = (int64_t)lb * ITEMS;
-  const int64_t line = l0 + tid;
-  const bool active = line < nlines;
   const int n = p.n;
+  const int cps = seglen / CH;  // chunks per segment
+  const int64_t item = (int64_t)blockIdx.x * ITEMS + tid;
+  const bool active = item < nitems;
+  const int64_t line = active ? item / nseg : 0;
+  const int seg = active ? (int)(item % nseg) : 0;
+  s_base[tid] = active ? line * (int64_t)n : -1;
+  s_ci0[tid] = seg * cps - 1;
+  __syncthreads();
+
   const int s = 1 + seg * seglen;
   const int e = min(n, s + seglen - 1);
-
   T c1 = T(0), cn = T(0);
   if (active && p.nv > 0 && (s <= p.Hz || e > n - p.Hz)) {
     const T *in = src + line * (int64_t)n;
     woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[r - 1]; }, c1, cn);
   }
-
   const int bs = (s - 1) / B, be = (e - 1) / B;
   const int bfirst = bs > 0 ? bs - 1 : bs;
+  const int nlc = cps + 2;  // warm-up chunk, the segment's chunks, look-ahead chunk
+
+  auto issue = [&](int lc) {
+    if (lc < nlc) {
+      unsigned char *tile = reinterpret_cast<unsigned char *>(tin + (lc % S) * ITEMS * PITCH);
+#pragma unroll
+      for (int it = 0; it < PPI; ++it) {
+        const int idx = it * ITEMS + tid;
+        const int im = idx / PPI, pc = idx % PPI;
+        const long long base = s_base[im];
+        const int ci = s_ci0[im] + lc;
+        const int row = 1 + ci * CH + pc * EPP;
+        const bool valid = base >= 0 && ci >= 0 && row <= n;
+        const T *g = valid ? src + base + (row - 1) : src;
+        cp_async_zfill(tile + (size_t)im * PITCH * 16 + (size_t)pc * VW, g, VW, valid);
+      }
+    }
+    cp_async_commit();
+  };
+
   T yprev[B], v[B], xout[B];
   T carry = T(0);
   int cnt_prev = 0;
+#pragma unroll
+  for (int lc = 0; lc < S - 1; ++lc) issue(lc);
 
 #pragma unroll 1
-  for (int ci = bfirst / K; ci <= (be + 1) / K; ++ci) {
-    const int rc0 = 1 + ci * CH;
-    // ---- cooperative load of rows [rc0, rc0+32) of ITEMS lines
-    if (VEC16) {
-#pragma unroll
-      for (int it = 0; it < VPI; ++it) {
-        const int idx = it * ITEMS + tid;
-        const int item = idx / VPI, vj = idx % VPI;
-        const int row = rc0 + vj * EPV;
-        const int64_t ln = l0 + item;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (ln < nlines && row <= n) val = *reinterpret_cast<const uint4 *>(src + ln * (int64_t)n + (row - 1));
-        tin[item * PITCH + vj] = val;
-      }
-    } else {
-      T *tin_s = reinterpret_cast<T *>(tin);
-#pragma unroll 4
-      for (int it = 0; it < CH; ++it) {
-        const int idx = it * ITEMS + tid;
-        const int item = idx / CH, j = idx % CH;
-        const int row = rc0 + j;
-        const int64_t ln = l0 + item;
-        T val = T(0);
-        if (ln < nlines && row <= n) val = src[ln * (int64_t)n + (row - 1)];
-        tin_s[item * (PITCH * EPV) + j] = val;
-      }
-    }
-    __syncthreads();
-    // ---- per-thread block pipeline on this chunk
-    if (active) {
+  for (int lc = 0; lc < nlc; ++lc) {
+    issue(lc + S - 1);
+    cp_async_wait<S - 1>();
+    __syncthreads();  // chunk lc has landed for every thread; tout of the previous iteration is drained
+    const int ci = s_ci0[tid] + lc;
+    if (active && ci >= 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int bi = ci * K + k;
         if (bi < bfirst || bi > be + 1) continue;
         const int r0 = 1 + bi * B;
         const int cnt = max(0, min(B, n - r0 + 1));
-        const uint4 *rowp = tin + tid * PITCH + k * VPB;
+        const uint4 *rowp = tin + (lc % S) * ITEMS * PITCH + tid * PITCH + k * VPB;
 #pragma unroll
         for (int q = 0; q < VPB; ++q) {
           const uint4 u = rowp[q];
@@ -389,32 +443,34 @@ __global__ void __launch_bounds__(Tune<T>::ITEMS) prefilter_contig_kernel(const 
         }
       }
     }
-    __syncthreads();
-    // ---- cooperative store of the rows finished in this chunk: [rc0-B, rc0-B+32) ∩ [s, e]
-    const int ro0 = rc0 - B;
-    if (VEC16) {
+    __syncthreads();  // tout complete; stage lc % S may be refilled by the next iteration's issue()
+    // ---- cooperative store of the rows finished in this chunk: [rc0-B, rc0-B+32) of every item, clipped to
+    //      the item's own segment
+    {
+      const unsigned char *tile = reinterpret_cast<const unsigned char *>(tout);
 #pragma unroll
-      for (int it = 0; it < VPI; ++it) {
+      for (int it = 0; it < PPI; ++it) {
         const int idx = it * ITEMS + tid;
-        const int item = idx / VPI, vj = idx % VPI;
-        const int row = ro0 + vj * EPV;
-        const int64_t ln = l0 + item;
-        if (ln < nlines && row >= s && row <= e)
-          *reinterpret_cast<uint4 *>(dst + ln * (int64_t)n + (row - 1)) = tout[item * PITCH + vj];
-      }
-    } else {
-      const T *tout_s = reinterpret_cast<const T *>(tout);
-#pragma unroll 4
-      for (int it = 0; it < CH; ++it) {
-        const int idx = it * ITEMS + tid;
-        const int item = idx / CH, j = idx % CH;
-        const int row = ro0 + j;
-        const int64_t ln = l0 + item;
-        if (ln < nlines && row >= s && row <= e) dst[ln * (int64_t)n + (row - 1)] = tout_s[item * (PITCH * EPV) + j];
+        const int im = idx / PPI, pc = idx % PPI;
+        const long long base = s_base[im];
+        const int ci0 = s_ci0[im];
+        const int row = 1 + (ci0 + lc) * CH - B + pc * EPP;
+        const int si = 1 + (ci0 + 1) * CH;
+        const int ei = min(n, si + seglen - 1);
+        if (base >= 0 && row >= si && row <= ei) {
+          const unsigned char *sp = tile + (size_t)im * PITCH * 16 + (size_t)pc * VW;
+          T *g = dst + base + (row - 1);
+          if constexpr (VW == 16)
+            *reinterpret_cast<uint4 *>(g) = *reinterpret_cast<const uint4 *>(sp);
+          else if constexpr (VW == 8)
+            *reinterpret_cast<uint2 *>(g) = *reinterpret_cast<const uint2 *>(sp);
+          else
+            *reinterpret_cast<unsigned *>(g) = *reinterpret_cast<const unsigned *>(sp);
+        }
       }
     }
-    // the next iteration's first __syncthreads orders these tile reads before the next tile writes
   }
+  cp_async_wait<0>();
 }
 
 // ================================================================== kernel: any n, any system
@@ -545,15 +601,26 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
     return 0;
   }
   if (axis == 0) {
-    constexpr int ITEMS = Tune<T>::ITEMS;
-    const int64_t nlb = (lines + ITEMS - 1) / ITEMS;
-    const int64_t blocks = nlb * nseg;
-    if (blocks > 0x7fffffff || nlb > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
-    const bool vec = (n % (16 / (int)sizeof(T)) == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    if (vec)
-      prefilter_contig_kernel<T, true><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, job.plan, lines, (int)nlb, seglen, nseg);
+    using Cfg = ContigCfg<T>;
+    const int64_t nitems = lines * nseg;
+    const int64_t blocks = (nitems + Cfg::ITEMS - 1) / Cfg::ITEMS;
+    if (blocks > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
+    const size_t lb = (size_t)n * sizeof(T);
+    const uintptr_t al = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)lb;
+    const int vw = (al % 16 == 0) ? 16 : ((al % 8 == 0) ? 8 : 4);
+    auto go = [&](auto kern) -> int {
+      B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+      kern<<<(unsigned)blocks, Cfg::ITEMS, Cfg::smem_bytes, st>>>(src, dst, job.plan, nitems, nseg, seglen);
+      return 0;
+    };
+    int rc;
+    if (vw == 16)
+      rc = go(prefilter_contig_kernel<T, 16>);
+    else if (vw == 8)
+      rc = go(prefilter_contig_kernel<T, 8>);
     else
-      prefilter_contig_kernel<T, false><<<(unsigned)blocks, ITEMS, 0, st>>>(src, dst, job.plan, lines, (int)nlb, seglen, nseg);
+      rc = go(prefilter_contig_kernel<T, (sizeof(T) == 8 ? 8 : 4)>);
+    if (rc) return rc;
   } else {
     const int64_t nb1 = (R1 + 127) / 128;
     const int64_t blocks = nb1 * nseg * R2;
@@ -567,15 +634,16 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
 
 // segmentation: only when there are too few lines to fill the machine
 template <typename T>
-static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int &nseg, int &seglen) {
+static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int axis, int &nseg, int &seglen) {
   constexpr int B = Tune<T>::B;
+  const int mult = axis == 0 ? 32 : B;  // the contiguous-axis kernel works in 32-row chunks
   nseg = 1;
   const int64_t want = (int64_t)sm_count(dev) * 1024;
   if (fast_ok && lines < want / 2) {
     const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
     nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
   }
-  seglen = (int)(((n + nseg - 1) / nseg + B - 1) / B * B);
+  seglen = (int)(((n + nseg - 1) / nseg + mult - 1) / mult * mult);
   nseg = (int)((n + seglen - 1) / seglen);
 }
 
@@ -593,7 +661,7 @@ static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const A
     if (!jobs[ax]) continue;
     const int64_t n = size[ax];
     int nseg, seglen;
-    choose_segments<T>(dev, total / n, n, jobs[ax]->fast_ok, nseg, seglen);
+    choose_segments<T>(dev, total / n, n, jobs[ax]->fast_ok, ax, nseg, seglen);
     T *dst = cur;
     if (nseg > 1) {
       if (!other) {
@@ -660,28 +728,52 @@ static int prefilter_axis_typed(int dev, void *coefs, int ndims, const int64_t *
   return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st);
 }
 
+// Plans of the reference's own systems depend only on (n, degree, bc, grid): memoised per type, so a
+// repeated `interpolate` costs no host-side factorisation.
+template <typename T>
+static int cached_job(int64_t n, int degree, int bc, int grid, const AxisJob<T> **out) {
+  static std::mutex mu;
+  static std::map<std::tuple<int64_t, int, int, int>, std::unique_ptr<AxisJob<T>>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_tuple(n, degree, bc, grid);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second.get();
+    return 0;
+  }
+  const int64_t ns = n > kSurrogate ? kSurrogate : n;
+  HostSystem<T> S;
+  int rc = assemble_system<T>(ns, degree, bc, grid, S);
+  if (rc) return rc;
+  rc = woodbury_cp<T>(S);
+  if (rc) B200_FAIL(rc, "prefilter: singular Woodbury capacitance matrix");
+  auto job = std::make_unique<AxisJob<T>>();
+  rc = make_job<T>(n, ns, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol, S.Cp, *job);
+  if (rc) return rc;
+  if (cache.size() > 256) cache.clear();
+  *out = job.get();
+  cache[key] = std::move(job);
+  return 0;
+}
+
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
                                const int32_t *bc, const int32_t *grid, cudaStream_t st) {
-  AxisJob<T> store[B200ITP_MAX_DIMS];
   const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int ax = 0; ax < ndims; ++ax) {
     if (degree[ax] == B200ITP_LINEAR) continue;  // prefiltering.jl:30
-    const int64_t n = size[ax];
-    const int64_t ns = n > kSurrogate ? kSurrogate : n;
-    HostSystem<T> S;
-    int rc = assemble_system<T>(ns, degree[ax], bc[ax], grid[ax], S);
+    int rc = cached_job<T>(size[ax], degree[ax], bc[ax], grid[ax], &jobs[ax]);
     if (rc == B200ITP_E_UNSUPPORTED) {
-      if (degree[ax] == B200ITP_CUBIC || degree[ax] == B200ITP_QUADRATIC) continue;  // M === nothing: left unfiltered
+      if (degree[ax] == B200ITP_CUBIC || degree[ax] == B200ITP_QUADRATIC) {
+        jobs[ax] = nullptr;  // M === nothing: the axis is left unfiltered (prefiltering.jl:124)
+        continue;
+      }
       B200_FAIL(rc, "prefilter: unsupported degree %d on axis %d", degree[ax], ax);
     }
-    if (rc) B200_FAIL(rc, "prefilter: axis %d of length %lld is too short for this boundary condition", ax,
-                      (long long)size[ax]);
-    rc = woodbury_cp<T>(S);
-    if (rc) B200_FAIL(rc, "prefilter: singular Woodbury capacitance matrix on axis %d", ax);
-    rc = make_job<T>(n, ns, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol, S.Cp, store[ax]);
+    if (rc == B200ITP_E_SIZE)
+      B200_FAIL(rc, "prefilter: axis %d of length %lld is too short for this boundary condition", ax,
+                (long long)size[ax]);
     if (rc) return rc;
-    jobs[ax] = &store[ax];
   }
   return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st);
 }

@@ -397,7 +397,7 @@ static int etp_inbounds_index(int flo, int fhi, int pair, double l, double u, in
     case B200ITP_BC_LINE: { /* maxp(l, x) */
       int t = tmax(x.t, bt);
       double a = rnd(t, l), b = conv(x, t).v;
-      x = mk(a > b ? a : b, t);
+      x = mk(b < a ? a : b, t); /* max(l, x): NaN x propagates */
       break;
     }
     case B200ITP_BC_PERIODIC: x = etp_periodic(x, l, u, bt); break;
@@ -415,7 +415,7 @@ static int etp_inbounds_index(int flo, int fhi, int pair, double l, double u, in
     case B200ITP_BC_LINE: { /* minp(x, u) */
       int t = tmax(x.t, bt);
       double a = conv(x, t).v, b = rnd(t, u);
-      x = mk(a < b ? a : b, t);
+      x = mk(a > b ? b : a, t); /* min(x, u): NaN x propagates */
       break;
     }
     case B200ITP_BC_PERIODIC: x = etp_periodic(x, l, u, bt); break;
