@@ -731,14 +731,14 @@ static int prefilter_axis_typed(int dev, void *coefs, int ndims, const int64_t *
 // Plans of the reference's own systems depend only on (n, degree, bc, grid): memoised per type, so a
 // repeated `interpolate` costs no host-side factorisation.
 template <typename T>
-static int cached_job(int64_t n, int degree, int bc, int grid, const AxisJob<T> **out) {
+static int cached_job(int64_t n, int degree, int bc, int grid, std::shared_ptr<const AxisJob<T>> *out) {
   static std::mutex mu;
-  static std::map<std::tuple<int64_t, int, int, int>, std::unique_ptr<AxisJob<T>>> cache;
+  static std::map<std::tuple<int64_t, int, int, int>, std::shared_ptr<const AxisJob<T>>> cache;
   std::lock_guard<std::mutex> lk(mu);
   const auto key = std::make_tuple(n, degree, bc, grid);
   auto it = cache.find(key);
   if (it != cache.end()) {
-    *out = it->second.get();
+    *out = it->second;
     return 0;
   }
   const int64_t ns = n > kSurrogate ? kSurrogate : n;
@@ -747,22 +747,24 @@ static int cached_job(int64_t n, int degree, int bc, int grid, const AxisJob<T> 
   if (rc) return rc;
   rc = woodbury_cp<T>(S);
   if (rc) B200_FAIL(rc, "prefilter: singular Woodbury capacitance matrix");
-  auto job = std::make_unique<AxisJob<T>>();
+  auto job = std::make_shared<AxisJob<T>>();
   rc = make_job<T>(n, ns, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow, S.vcol, S.Cp, *job);
   if (rc) return rc;
-  if (cache.size() > 256) cache.clear();
-  *out = job.get();
-  cache[key] = std::move(job);
+  if (cache.size() > 256) cache.clear();  // callers keep their jobs alive through the shared_ptr
+  *out = job;
+  cache[key] = job;
   return 0;
 }
 
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
                                const int32_t *bc, const int32_t *grid, cudaStream_t st) {
+  std::shared_ptr<const AxisJob<T>> keep[B200ITP_MAX_DIMS];
   const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int ax = 0; ax < ndims; ++ax) {
     if (degree[ax] == B200ITP_LINEAR) continue;  // prefiltering.jl:30
-    int rc = cached_job<T>(size[ax], degree[ax], bc[ax], grid[ax], &jobs[ax]);
+    int rc = cached_job<T>(size[ax], degree[ax], bc[ax], grid[ax], &keep[ax]);
+    jobs[ax] = keep[ax].get();
     if (rc == B200ITP_E_UNSUPPORTED) {
       if (degree[ax] == B200ITP_CUBIC || degree[ax] == B200ITP_QUADRATIC) {
         jobs[ax] = nullptr;  // M === nothing: the axis is left unfiltered (prefiltering.jl:124)
