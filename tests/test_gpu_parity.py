@@ -261,7 +261,8 @@ def test_eval_scaled_extrapolated_c4_family(pkg, orc, coef_dtype, coord_dtype, r
         iny = rng.uniform(l2, u2, 4000).astype(coord_dtype).clip(l2, u2)
         inx[:2] = [l1, u1]
         iny[:2] = [l2, u2]
-        ok = (inx >= l1) & (inx <= u1) & (iny >= l2) & (iny <= u2)
+        x64, y64 = inx.astype(np.float64), iny.astype(np.float64)  # compare exactly (NEP 50 would round the bounds)
+        ok = (x64 >= l1) & (x64 <= u1) & (y64 >= l2) & (y64 <= u2)
         check_eval(pkg, orc, sitp, [inx[ok], iny[ok]])
 
 
