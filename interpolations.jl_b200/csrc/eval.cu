@@ -239,17 +239,26 @@ extern "C" int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, c
                      (cudaStream_t)stream);
 }
 
-extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
-  (void)d;
-  return nq > 0 ? (size_t)nq * 4 * 3 + 4096 * 8 : 0;
+namespace b200itp {
+// used by eval_sorted.cu: validated parameters for a values-only evaluation, plus whether the descriptor is
+// a bare Float32 B-spline interpolant (the ordered path's scope) and its uniform degree (0: mixed)
+int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void *const *coords, int64_t nq,
+                            void *out_value, unsigned long long *first_oob_dev, EvalParams &P, int *uniform_degree,
+                            bool *plain_f32) {
+  Chain c;
+  int rc = derive_chain(D, c);
+  if (rc) B200_FAIL(rc, "eval_sorted: invalid descriptor");
+  if (nq < 0) B200_FAIL(B200ITP_E_BADARG, "eval_sorted: negative query count");
+  for (int d = 0; d < D->ndims; ++d)
+    if (!coords[d]) B200_FAIL(B200ITP_E_BADARG, "eval_sorted: null coordinate array %d", d);
+  rc = fill_params(D, c, coefs, coords, nq, out_value, nullptr, nullptr, nullptr, first_oob_dev, P);
+  if (rc) return rc;
+  int deg = D->degree[0];
+  for (int d = 1; d < D->ndims; ++d)
+    if (D->degree[d] != deg) deg = 0;
+  *uniform_degree = deg;
+  *plain_f32 = c.homogeneous && D->etp_kind == B200ITP_ETP_NONE && !D->has_scale && D->coef_dtype == B200ITP_F32 &&
+               D->coord_dtype == B200ITP_F32 && !c.w_wide;
+  return 0;
 }
-
-extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
-                                   int64_t nq, void *out_value, int64_t *first_oob, void *scratch,
-                                   size_t scratch_bytes, void *stream) {
-  // v1: the ordering pass is not wired in yet; results are identical either way
-  (void)scratch;
-  (void)scratch_bytes;
-  return eval_common(dev, d, coefs, coords, nq, out_value, nullptr, first_oob, nullptr, nullptr, nullptr,
-                     (cudaStream_t)stream);
-}
+}  // namespace b200itp

@@ -169,6 +169,7 @@ struct AxisTaps {
   int pos[LMAX];  // 0-based position along the axis of the coefficient array
   TW wv[LMAX], wg[LMAX];
   int L;
+  int first;  // parent index (1-based, before any periodic wrap) of the first tap
   bool edge;
   bool contiguous;  // pos[k] == pos[0] + k
 };
@@ -264,6 +265,7 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       A.wg[2] = A.wg[3] = TW(0);
     }
   }
+  A.first = first;
   A.contiguous = true;
 #pragma unroll
   for (int k = 0; k < AxisTaps<DEG, TW>::LMAX; ++k) {

@@ -118,11 +118,13 @@ if __name__ == "__main__":
                                      m.BSpline(m.Cubic(m.Line(m.OnGrid()))), f64)
     if which in ("all", "eval"):
         R["c3_eval"] = eval_case("C3 eval 2^27 q", (512, 512, 512), m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), f32,
-                                 1 << 27, grad=True)
+                                 1 << 27, grad=True, sorted_q=True)
+        R["c3_eval_1e9"] = eval_case("C3 eval 1e9 q", (512, 512, 512), m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), f32,
+                                     10**9, sorted_q=True)
         R["c3_eval_small"] = eval_case("64^3 eval 2^27 q (L2 resident)", (64, 64, 64),
                                        m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), f32, 1 << 27)
         R["c2_eval"] = eval_case("C2 eval 1e8 q", (4096, 4096), m.BSpline(m.Cubic(m.Flat(m.OnCell()))), f32, 10**8,
-                                 grad=True)
+                                 grad=True, sorted_q=True)
         rng = [m.jrange(np.float32(0), np.float32(1), length=8192, dtype=np.float32)] * 2
         R["c4_eval"] = eval_case("C4 eval 1e8 q", (8192, 8192), m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), f32,
                                  10**8, wrap=lambda i: m.extrapolate(m.scale(i, *rng), m.Line()))
