@@ -4,13 +4,15 @@
 // sectors when the array does not fit the L2, and 64 different L1 lines per warp instruction even when
 // it does: the direct kernel (eval.cuh) is bound by that, not by arithmetic.  This path reorders the
 // queries on the device, inside the call, so that the coefficients are read once:
-//   1. count   : key(q) = (brick of 32 x BY x BZ cells, (y,z) cell inside the brick); histogram in L2
+//   1. count   : key(q) = brick of 32 x BY x BZ cells holding the query's first tap; histogram in L2
 //   2. scan    : exclusive prefix sum of the histogram
-//   3. scatter : records {x, y, z, q} (16 B) are written to their key's slot
+//   3. scatter : records {x, y, z, q} (16 B) are appended to their brick's slot (one open 32-byte tail
+//                per brick: all tails stay L2-resident, so DRAM sees full-sector streaming writes)
 //   4. evaluate: one CTA per (brick, slice of its records): the brick plus its 3-cell halo is staged in
-//                shared memory once (periodic wrap resolved while staging), every warp then serves 32
-//                records of (nearly) one (y,z) cell column, so its shared-memory gathers fall on
-//                consecutive words of one row: conflict-free.  Results go to out[q]: the caller's order.
+//                shared memory once (periodic wrap resolved while staging); the slice is counting-sorted
+//                in shared memory by the (y,z) cell inside the brick, so that every warp serves 32 records
+//                of (nearly) one cell column and its shared-memory gathers fall on consecutive words of
+//                one row: conflict-free.  Results go to out[q]: the caller's order.
 // The per-query arithmetic is the same device code as the direct kernel (axis_setup + the reference's
 // reduction order), so both paths return bit-identical values.
 //
@@ -40,7 +42,7 @@ struct Brick<2> {
 struct SortGeom {
   int nb[3];       // bricks per axis
   int cells[3];    // number of distinct first-tap indices per axis (first in [0, cells))
-  long long nbins; // fine bins
+  long long nbins; // bricks
 };
 
 // first tap index per axis (bit-identical to what the evaluation will compute) and in-bounds test
@@ -62,9 +64,7 @@ __device__ __forceinline__ bool query_key(const EvalParams &P, const SortGeom &G
   }
   using Bk = Brick<N>;
   const int bx = c[0] / Bk::BX, by = c[1] / Bk::BY, bz = N == 3 ? c[2] / Bk::BZ : 0;
-  const int ly = c[1] % Bk::BY, lz = N == 3 ? c[2] % Bk::BZ : 0;
-  const long long brick = ((long long)bz * G.nb[1] + by) * G.nb[0] + bx;
-  key = brick * (Bk::BY * Bk::BZ) + (lz * Bk::BY + ly);
+  key = ((long long)bz * G.nb[1] + by) * G.nb[0] + bx;
   return true;
 }
 
@@ -213,21 +213,27 @@ struct TileCfg {
   static constexpr int FLOATS = PX * TY * TZ;
 };
 
-constexpr int kSplit = 4;        // CTAs per brick (each takes every kSplit-th slice of the brick's records)
-constexpr int kSlice = 4096;     // records per slice
+constexpr int kSplit = 4;      // CTAs per brick (each takes every kSplit-th slice of the brick's records)
+constexpr int kSlice = 1536;   // records per slice (static shared memory: tile + slice < 48 KB)
+constexpr int kEvalThreads = 256;
+constexpr int kRPT = kSlice / kEvalThreads;  // records per thread per slice
 
 template <int N, int DEG>
-__global__ void __launch_bounds__(256) sort_eval_kernel(const __grid_constant__ EvalParams P, const SortGeom G,
-                                                        const unsigned *__restrict__ start,
-                                                        const float4 *__restrict__ rec) {
+__global__ void __launch_bounds__(kEvalThreads) sort_eval_kernel(const __grid_constant__ EvalParams P,
+                                                                 const SortGeom G,
+                                                                 const unsigned *__restrict__ start,
+                                                                 const float4 *__restrict__ rec) {
   using TC = TileCfg<N, DEG>;
   using Bk = Brick<N>;
   constexpr int L = TC::L;
+  constexpr int FPB = Bk::BY * Bk::BZ;  // (y,z) cell columns per brick
   __shared__ float tile[TC::FLOATS];
+  __shared__ float4 srec[kSlice];
+  __shared__ unsigned shist[FPB];
+  __shared__ unsigned sstart[FPB];
   const long long brick = blockIdx.x;
   const int split = blockIdx.y;
-  constexpr int FPB = Bk::BY * Bk::BZ;  // fine bins per brick
-  const unsigned r_begin = start[brick * FPB], r_end = start[(brick + 1) * FPB];
+  const unsigned r_begin = start[brick], r_end = start[brick + 1];
   if (r_begin + (unsigned)split * kSlice >= r_end) return;
 
   // brick origin in first-tap index space
@@ -247,21 +253,70 @@ __global__ void __launch_bounds__(256) sort_eval_kernel(const __grid_constant__ 
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-      int idx = o[d] + l[d];
-      int pos = P.periodic[d] ? modrange1(idx, P.n[d]) - 1 : idx - P.coef_first[d];
+      const int idx = o[d] + l[d];
+      const int pos = P.periodic[d] ? modrange1(idx, P.n[d]) - 1 : idx - P.coef_first[d];
       const int size_d = P.n[d] + (P.coef_first[d] == 0 ? 2 : 0);
       ok = ok && pos >= 0 && pos < size_d;
       off += (long long)pos * P.stride[d];
     }
     tile[(lz * TC::TY + ly) * TC::PX + lx] = ok ? __ldg(coefs + off) : 0.f;
   }
-  __syncthreads();
 
   for (unsigned sbase = r_begin + (unsigned)split * kSlice; sbase < r_end; sbase += (unsigned)kSplit * kSlice) {
-    const unsigned send = min(r_end, sbase + (unsigned)kSlice);
-    for (unsigned i = sbase + threadIdx.x; i < send; i += blockDim.x) {
-      const float4 r = rec[i];
-      const float x[3] = {r.x, r.y, r.z};
+    const unsigned cnt = min(r_end - sbase, (unsigned)kSlice);
+    if (threadIdx.x < FPB) shist[threadIdx.x] = 0;
+    __syncthreads();  // also: tile staged / previous slice fully consumed
+    // ---- counting sort of the slice by (y,z) cell column, in shared memory
+    float4 r[kRPT];
+    unsigned keyrank[kRPT];
+#pragma unroll
+    for (int j = 0; j < kRPT; ++j) {
+      const unsigned i = (unsigned)j * kEvalThreads + threadIdx.x;
+      keyrank[j] = 0xffffffffu;
+      if (i < cnt) {
+        r[j] = rec[sbase + i];
+        int col = 0;
+        {
+          AxisTaps<DEG, float> A;
+          axis_setup<DEG, float, false>(P, 1, r[j].y, A);
+          col = min(max(A.first, 0), G.cells[1] - 1) - o[1];
+        }
+        if (N == 3) {
+          AxisTaps<DEG, float> A;
+          axis_setup<DEG, float, false>(P, N - 1, r[j].z, A);
+          col += (min(max(A.first, 0), G.cells[N - 1] - 1) - o[2]) * Bk::BY;
+        }
+        const unsigned rank = atomicAdd(&shist[col], 1u);
+        keyrank[j] = ((unsigned)col << 16) | rank;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of FPB <= 64 counters by one warp
+      unsigned a = threadIdx.x < FPB ? shist[threadIdx.x] : 0u;
+      unsigned b = threadIdx.x + 32 < FPB ? shist[threadIdx.x + 32] : 0u;
+      unsigned ia = a, ib = b;
+#pragma unroll
+      for (int w = 1; w < 32; w <<= 1) {
+        const unsigned ta = __shfl_up_sync(0xffffffffu, ia, w);
+        const unsigned tb = __shfl_up_sync(0xffffffffu, ib, w);
+        if (threadIdx.x >= w) {
+          ia += ta;
+          ib += tb;
+        }
+      }
+      const unsigned tot_a = __shfl_sync(0xffffffffu, ia, 31);
+      if (threadIdx.x < FPB) sstart[threadIdx.x] = ia - a;
+      if (threadIdx.x + 32 < FPB) sstart[threadIdx.x + 32] = tot_a + ib - b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kRPT; ++j)
+      if (keyrank[j] != 0xffffffffu) srec[sstart[keyrank[j] >> 16] + (keyrank[j] & 0xffffu)] = r[j];
+    __syncthreads();
+    // ---- evaluate in sorted order: a warp's 32 records share (nearly) one cell column
+    for (unsigned i = threadIdx.x; i < cnt; i += kEvalThreads) {
+      const float4 q4 = srec[i];
+      const float x[3] = {q4.x, q4.y, q4.z};
       AxisTaps<DEG, float> ax[N];
       int lpos[3] = {0, 0, 0};
 #pragma unroll
@@ -294,7 +349,7 @@ __global__ void __launch_bounds__(256) sort_eval_kernel(const __grid_constant__ 
         const float t0 = ax[0].wv[k0] * v0;
         val = k0 == 0 ? t0 : t0 + val;
       }
-      reinterpret_cast<float *>(P.out_value)[__float_as_uint(r.w)] = val;
+      reinterpret_cast<float *>(P.out_value)[__float_as_uint(q4.w)] = val;
     }
   }
 }
@@ -318,7 +373,7 @@ static int run_sorted(int dev, EvalParams &P, const b200itp_desc *D, void *scrat
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
     bricks *= G.nb[d];
   }
-  G.nbins = bricks * (Bk::BY * Bk::BZ);
+  G.nbins = bricks;
   if (bricks > 0x7fffffffLL || G.nbins > (1LL << 27) || P.nq > 0xfffffff0LL) return 0;
   const size_t need = (size_t)P.nq * 16 + (size_t)(G.nbins + 1) * 8 + 65536 * 4 + 1024;
   if (!scratch || scratch_bytes < need || ((uintptr_t)scratch % 16) != 0) return 0;
@@ -338,7 +393,7 @@ static int run_sorted(int dev, EvalParams &P, const b200itp_desc *D, void *scrat
   scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nbins, sums, start);
   sort_scatter_kernel<N, DEG><<<blocks, 256, 0, st>>>(P, G, hist, rec);
   dim3 grid((unsigned)bricks, kSplit, 1);
-  sort_eval_kernel<N, DEG><<<grid, 256, 0, st>>>(P, G, start, rec);
+  sort_eval_kernel<N, DEG><<<grid, kEvalThreads, 0, st>>>(P, G, start, rec);
   count_launch(6);
   B200_CUDA_OK(cudaGetLastError());
   *done = true;
