@@ -210,15 +210,22 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
  * promote(coordinate type after all wrappers, eltype(coefs)). <0 on invalid descriptor. */
 B200ITP_API int b200itp_out_dtype(const b200itp_desc *d);
 
-/* Same as b200itp_eval (values only, no debug outputs), but first reorders the
- * queries on the device by coarse coefficient tile so that neighbouring threads
- * touch neighbouring coefficients (L2-friendly ordering); results are written in
- * the original query order.  `scratch` is a device buffer of at least
- * b200itp_eval_sorted_scratch_bytes(d, nq) bytes. */
+/* Same as b200itp_eval (values only, no debug outputs), but the queries are first
+ * ordered on the device by the brick of coefficients they touch (two streaming
+ * multisplit passes), evaluated brick by brick from shared memory, and the results
+ * are streamed back into the caller's query order (two more multisplit passes):
+ * every pass moves whole cache lines, no scattered DRAM access.  Results are
+ * bit-identical to b200itp_eval.  `scratch` is a device buffer of at least
+ * b200itp_eval_sorted_scratch_bytes(d, nq) bytes (about 32 bytes per query).
+ * Calls with fewer than b200itp_eval_sorted_min_queries() queries, or a descriptor
+ * outside the ordered path's scope, are served by the direct kernel. */
 B200ITP_API size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq);
 B200ITP_API int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs,
                         const void *const *coords, int64_t nq, void *out_value,
                         int64_t *first_oob, void *scratch, size_t scratch_bytes, void *stream);
+/* threshold (queries per call) from which the ordered pipeline is used; default 2^20 */
+B200ITP_API int64_t b200itp_eval_sorted_min_queries(void);
+B200ITP_API void b200itp_eval_sorted_set_min_queries(int64_t n);
 
 #ifdef __cplusplus
 }

@@ -1,25 +1,31 @@
-// b200itp_eval_sorted: scattered evaluation with L2/shared-memory friendly query ordering.
+// b200itp_eval_sorted: scattered evaluation with on-device query ordering.
 //
-// A uniformly scattered tricubic query touches 16 (y,z) rows of the coefficient array, i.e. 16-32 DRAM
-// sectors when the array does not fit the L2, and 64 different L1 lines per warp instruction even when
-// it does: the direct kernel (eval.cuh) is bound by that, not by arithmetic.  This path reorders the
-// queries on the device, inside the call, so that the coefficients are read once:
-//   1. count   : key(q) = brick of 32 x BY x BZ cells holding the query's first tap; histogram in L2
-//   2. scan    : exclusive prefix sum of the histogram
-//   3. scatter : records {x, y, z, q} (16 B) are appended to their brick's slot (one open 32-byte tail
-//                per brick: all tails stay L2-resident, so DRAM sees full-sector streaming writes)
-//   4. evaluate: one CTA per (brick, slice of its records): the brick plus its 3-cell halo is staged in
-//                shared memory once (periodic wrap resolved while staging); the slice is counting-sorted
-//                in shared memory by the (y,z) cell inside the brick, so that every warp serves 32 records
-//                of (nearly) one cell column and its shared-memory gathers fall on consecutive words of
-//                one row: conflict-free.  Results go to out[q]: the caller's order.
-// The per-query arithmetic is the same device code as the direct kernel (axis_setup + the reference's
-// reduction order), so both paths return bit-identical values.
+// A uniformly scattered tricubic query touches 16 (y,z) rows of the coefficient array: 16-32 DRAM sectors
+// when the array does not fit the L2, and 32 different L1 lines per warp instruction even when it does,
+// so the direct kernel (eval.cuh) is bound by the L1 tag stage (~9 Gevals/s for 64 taps), not by HBM.
+// Random 4-byte scatters of the results are no better (measured 23 G/s over a 4 GB window).  This path
+// therefore moves the QUERIES instead, with streaming passes only (every pass reads and writes whole
+// 128-byte lines; measured in tools/ubench_scatter.cu):
 //
-// Scope: BSplineInterpolation without wrappers, Float32 coefficients and coordinates, 2-D / 3-D,
-// uniform Quadratic or Cubic degree.  Everything else is forwarded to the direct kernel.
+//   count    key(q) = (brick, bank class) of the query's first tap; histogram with L2 reductions
+//   scan     exclusive prefix sum -> start offset of every (brick, class) stream
+//   split 1  CTA-local multisplit of {x,y,z,q} records by brick GROUP   (<= 512 bins, runs of >= 8 records)
+//   split 2  CTA-local multisplit inside each group by (brick, class)   (<= 512 bins)
+//   evaluate persistent CTAs, one brick tile (+halo, periodic wrap resolved) in shared memory at a time;
+//            lane c of every warp consumes the records of bank class c: the 64 shared-memory gathers of a
+//            warp instruction then fall on 32 different banks by construction (conflict-free without
+//            sorting the records inside the brick).  Results {q, value} leave in stream order.
+//   unsort A multisplit of {q, value} by q >> 23, unsort B by q >> 14 (bins have exact, known sizes)
+//   place    one CTA per window of 2^14 results: permute in shared memory, store coalesced to out[q]
+//
+// The per-query arithmetic is the device code of the direct kernel (axis_setup + the reference's reduction
+// order, -fmad=false), so both paths return bit-identical values.
+//
+// Scope: BSplineInterpolation without wrappers, Float32 coefficients and coordinates, 2-D / 3-D, uniform
+// Quadratic or Cubic degree, at least 2^20 queries.  Everything else is forwarded to the direct kernel.
 #include "eval.cuh"
 
+#include <algorithm>
 #include <climits>
 
 namespace b200itp {
@@ -28,33 +34,56 @@ int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void
                             void *out_value, unsigned long long *first_oob_dev, EvalParams &P, int *uniform_degree,
                             bool *plain_f32);
 
+// ------------------------------------------------------------------------------------------ geometry
 template <int N>
 struct Brick;
 template <>
 struct Brick<3> {
-  static constexpr int BX = 32, BY = 8, BZ = 8;
+  static constexpr int BX = 32, BY = 32, BZ = 16;
 };
 template <>
 struct Brick<2> {
-  static constexpr int BX = 32, BY = 16, BZ = 1;
+  static constexpr int BX = 128, BY = 128, BZ = 1;
 };
 
-struct SortGeom {
-  int nb[3];       // bricks per axis
-  int cells[3];    // number of distinct first-tap indices per axis (first in [0, cells))
-  long long nbins; // bricks
-};
-
-// first tap index per axis (bit-identical to what the evaluation will compute) and in-bounds test
 template <int N, int DEG>
-__device__ __forceinline__ bool query_key(const EvalParams &P, const SortGeom &G, const float (&x)[N], long long &key) {
-  bool inb = true;
-#pragma unroll
-  for (int d = 0; d < N; ++d) {
-    const double xd = (double)x[d];
-    inb = inb && (P.lb[d] <= xd) && (xd <= P.ub[d]);
-  }
-  if (!inb) return false;
+struct TileCfg {
+  using Bk = Brick<N>;
+  static constexpr int L = DEG + 1;
+  static constexpr int TX = Bk::BX + DEG;
+  static constexpr int TY = Bk::BY + DEG;
+  static constexpr int TZ = N == 3 ? Bk::BZ + DEG : 1;
+  static constexpr int PX = TX | 1;  // odd row pitch
+  static constexpr int FLOATS = PX * TY * TZ;
+  static constexpr int MAXT = TX > TY ? (TX > TZ ? TX : TZ) : (TY > TZ ? TY : TZ);
+};
+
+constexpr int kClasses = 32;        // bank classes == lanes
+constexpr int kGroupBricks = 16;    // bricks per split-1 group: split 2 has 16 * 32 = 512 bins
+constexpr int kMaxBins = 512;       // bins per multisplit level (== threads of the split kernels)
+constexpr int kSplitThreads = 512;
+constexpr int kChunk16 = 4096;      // records per multisplit chunk, 16-byte records
+constexpr int kChunk8 = 8192;       // 8-byte records
+constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
+constexpr int kShiftA = 23;         // unsort level A bins of 2^23 results (512 windows each)
+constexpr int kEvalThreads = 768;
+constexpr int kRows = 96;           // records per class per staging round (4 rows per warp)
+constexpr int kRowPitch = kRows + 1;
+constexpr int kItemTarget = 32768;  // records per evaluation work item
+
+struct OrdGeom {
+  int nb[3];     // bricks per axis
+  int cells[3];  // distinct first-tap indices per axis
+  int nbricks;
+  int ngroups;
+  int nfinal;    // nbricks * kClasses
+};
+
+// (brick, class, position inside the brick) of a query: bit-identical to what the evaluation computes
+template <int N, int DEG>
+__device__ __forceinline__ void locate(const EvalParams &P, const OrdGeom &G, const float (&x)[3], int &brick, int &cls) {
+  using Bk = Brick<N>;
+  using TC = TileCfg<N, DEG>;
   int c[3] = {0, 0, 0};
 #pragma unroll
   for (int d = 0; d < N; ++d) {
@@ -62,55 +91,56 @@ __device__ __forceinline__ bool query_key(const EvalParams &P, const SortGeom &G
     axis_setup<DEG, float, false>(P, d, x[d], A);
     c[d] = min(max(A.first, 0), G.cells[d] - 1);
   }
-  using Bk = Brick<N>;
   const int bx = c[0] / Bk::BX, by = c[1] / Bk::BY, bz = N == 3 ? c[2] / Bk::BZ : 0;
-  key = ((long long)bz * G.nb[1] + by) * G.nb[0] + bx;
-  return true;
+  brick = (bz * G.nb[1] + by) * G.nb[0] + bx;
+  const int lx = c[0] - bx * Bk::BX, ly = c[1] - by * Bk::BY, lz = N == 3 ? c[2] - bz * Bk::BZ : 0;
+  cls = ((lz * TC::TY + ly) * TC::PX + lx) & (kClasses - 1);
 }
 
+// A query outside the bounds (or NaN) is a BoundsError (indexing.jl:6): it travels through the pipeline as
+// an all-NaN record (brick 0, class 0, NaN result) so that every q appears exactly once in the unsort.
+template <int N>
+__device__ __forceinline__ void check_query(const EvalParams &P, float (&x)[3], bool &valid) {
+  valid = true;
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    const double xd = (double)x[d];
+    valid = valid && (P.lb[d] <= xd) && (xd <= P.ub[d]);
+  }
+  if (!valid) {
+    const float nn = __int_as_float(0x7fc00000);
+    x[0] = nn;
+    x[1] = nn;
+    if (N == 3) x[2] = nn;
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_query(const EvalParams &P, long long q, float (&x)[3], bool &valid) {
+  x[2] = 0.f;
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = reinterpret_cast<const float *>(P.coords[d])[q];
+  check_query<N>(P, x, valid);
+}
+
+// ------------------------------------------------------------------------------------------ count
 template <int N, int DEG>
-__global__ void __launch_bounds__(256) sort_count_kernel(const __grid_constant__ EvalParams P, const SortGeom G,
-                                                         unsigned *__restrict__ hist) {
+__global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
+                                                        unsigned *__restrict__ hist) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P.nq; q += stride) {
-    float x[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) x[d] = reinterpret_cast<const float *>(P.coords[d])[q];
-    long long key;
-    if (query_key<N, DEG>(P, G, x, key)) {
-      atomicAdd(hist + key, 1u);
-    } else {
-      // BoundsError (indexing.jl:6): NaN result, smallest offending index reported
-      reinterpret_cast<float *>(P.out_value)[q] = nanf("");
-      atomicMin(P.first_oob, (unsigned long long)q);
-    }
+    float x[3];
+    bool valid;
+    load_query<N>(P, q, x, valid);
+    if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
+    int brick, cls;
+    locate<N, DEG>(P, G, x, brick, cls);
+    atomicAdd(hist + (brick * kClasses + cls), 1u);  // result unused: compiles to RED
   }
 }
 
-template <int N, int DEG>
-__global__ void __launch_bounds__(256) sort_scatter_kernel(const __grid_constant__ EvalParams P, const SortGeom G,
-                                                           unsigned *__restrict__ cursor, float4 *__restrict__ rec) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P.nq; q += stride) {
-    float x[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) x[d] = reinterpret_cast<const float *>(P.coords[d])[q];
-    long long key;
-    if (query_key<N, DEG>(P, G, x, key)) {
-      const unsigned pos = atomicAdd(cursor + key, 1u);
-      float4 r;
-      r.x = x[0];
-      r.y = x[1];
-      r.z = N == 3 ? x[2] : 0.f;
-      r.w = __uint_as_float((unsigned)q);
-      rec[pos] = r;
-    }
-  }
-}
-
-// ---- exclusive scan of the histogram (in place), three small kernels
+// ------------------------------------------------------------------------------------------ scan (3 kernels)
 constexpr int kScanBlock = 1024;
-constexpr int kScanPer = 4;  // elements per thread
+constexpr int kScanPer = 4;
 __global__ void __launch_bounds__(kScanBlock) scan_partial_kernel(const unsigned *__restrict__ hist, long long n,
                                                                    unsigned *__restrict__ sums) {
   __shared__ unsigned red[32];
@@ -133,7 +163,6 @@ __global__ void __launch_bounds__(kScanBlock) scan_partial_kernel(const unsigned
   }
 }
 __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned *sums, int nblocks) {
-  // single CTA: sequential chunks of 1024 block sums (nblocks is at most a few 10^4)
   __shared__ unsigned buf[1024];
   __shared__ unsigned carry;
   if (threadIdx.x == 0) carry = 0;
@@ -143,22 +172,22 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned *sums, int nbl
     const unsigned v = i < nblocks ? sums[i] : 0u;
     buf[threadIdx.x] = v;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    for (int o = 1; o < 1024; o <<= 1) {
       const unsigned t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0u;
       __syncthreads();
       buf[threadIdx.x] += t;
       __syncthreads();
     }
-    if (i < nblocks) sums[i] = carry + buf[threadIdx.x] - v;  // exclusive
+    if (i < nblocks) sums[i] = carry + buf[threadIdx.x] - v;
     __syncthreads();
     if (threadIdx.x == 0) carry += buf[1023];
     __syncthreads();
   }
 }
+// start[i] = exclusive prefix (n + 1 entries); hist[i] becomes the split-2 cursor of stream i
 __global__ void __launch_bounds__(kScanBlock) scan_final_kernel(unsigned *hist, long long n,
                                                                  const unsigned *__restrict__ sums,
-                                                                 unsigned *__restrict__ start /* n+1 */) {
-  // exclusive scan inside the block's kScanBlock*kScanPer elements; element order: i = base + t*kScanPer + k
+                                                                 unsigned *__restrict__ start) {
   __shared__ unsigned wsum[32];
   const long long base = (long long)blockIdx.x * kScanBlock * kScanPer;
   unsigned v[kScanPer];
@@ -194,222 +223,626 @@ __global__ void __launch_bounds__(kScanBlock) scan_final_kernel(unsigned *hist, 
     const long long i = base + (long long)threadIdx.x * kScanPer + k;
     if (i < n) {
       start[i] = run;
-      hist[i] = run;  // becomes the scatter cursor
+      hist[i] = run;
     }
     run += v[k];
     if (i == n - 1) start[n] = run;
   }
 }
 
-// ---- evaluation of one brick from shared memory
-template <int N, int DEG>
-struct TileCfg {
-  using Bk = Brick<N>;
-  static constexpr int L = DEG + 1;
-  static constexpr int TX = Bk::BX + DEG;
-  static constexpr int TY = Bk::BY + DEG;
-  static constexpr int TZ = N == 3 ? Bk::BZ + DEG : 1;
-  static constexpr int PX = TX | 1;  // odd row pitch: rows of neighbouring (y,z) start on different banks
-  static constexpr int FLOATS = PX * TY * TZ;
+// ------------------------------------------------------------------------------------------ plan
+// One CTA: cursors of split 1 (per group), chunk table of split 2 (per group), work items of the
+// evaluation (per brick), cursors of the two unsort levels (exact bin sizes).
+struct OrdPlan {
+  unsigned *cursor1;      // ngroups
+  unsigned *chunk_start;  // ngroups + 1 : split-2 chunks
+  unsigned *item_start;   // nbricks + 1 : evaluation work items
+  unsigned *cursorA;      // ceil(nq / 2^kShiftA)
+  unsigned *cursorB;      // ceil(nq / 2^kShiftB)
 };
 
-constexpr int kSplit = 4;      // CTAs per brick (each takes every kSplit-th slice of the brick's records)
-constexpr int kSlice = 1536;   // records per slice (static shared memory: tile + slice < 48 KB)
-constexpr int kEvalThreads = 256;
-constexpr int kRPT = kSlice / kEvalThreads;  // records per thread per slice
-
-template <int N, int DEG>
-__global__ void __launch_bounds__(kEvalThreads) sort_eval_kernel(const __grid_constant__ EvalParams P,
-                                                                 const SortGeom G,
-                                                                 const unsigned *__restrict__ start,
-                                                                 const float4 *__restrict__ rec) {
-  using TC = TileCfg<N, DEG>;
-  using Bk = Brick<N>;
-  constexpr int L = TC::L;
-  constexpr int FPB = Bk::BY * Bk::BZ;  // (y,z) cell columns per brick
-  __shared__ float tile[TC::FLOATS];
-  __shared__ float4 srec[kSlice];
-  __shared__ unsigned shist[FPB];
-  __shared__ unsigned sstart[FPB];
-  const long long brick = blockIdx.x;
-  const int split = blockIdx.y;
-  const unsigned r_begin = start[brick], r_end = start[brick + 1];
-  if (r_begin + (unsigned)split * kSlice >= r_end) return;
-
-  // brick origin in first-tap index space
-  const int bx = (int)(brick % G.nb[0]);
-  const int by = (int)((brick / G.nb[0]) % G.nb[1]);
-  const int bz = (int)(brick / ((long long)G.nb[0] * G.nb[1]));
-  const int o[3] = {bx * Bk::BX, by * Bk::BY, bz * Bk::BZ};
-  const float *coefs = reinterpret_cast<const float *>(P.coefs);
-
-  // ---- stage the brick + halo; tile element (lx,ly,lz) <-> parent index o + l on each axis
-  for (int t = threadIdx.x; t < TC::TX * TC::TY * TC::TZ; t += blockDim.x) {
-    const int lx = t % TC::TX;
-    const int ly = (t / TC::TX) % TC::TY;
-    const int lz = t / (TC::TX * TC::TY);
-    const int l[3] = {lx, ly, lz};
-    long long off = 0;
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-      const int idx = o[d] + l[d];
-      const int pos = P.periodic[d] ? modrange1(idx, P.n[d]) - 1 : idx - P.coef_first[d];
-      const int size_d = P.n[d] + (P.coef_first[d] == 0 ? 2 : 0);
-      ok = ok && pos >= 0 && pos < size_d;
-      off += (long long)pos * P.stride[d];
-    }
-    tile[(lz * TC::TY + ly) * TC::PX + lx] = ok ? __ldg(coefs + off) : 0.f;
-  }
-
-  for (unsigned sbase = r_begin + (unsigned)split * kSlice; sbase < r_end; sbase += (unsigned)kSplit * kSlice) {
-    const unsigned cnt = min(r_end - sbase, (unsigned)kSlice);
-    if (threadIdx.x < FPB) shist[threadIdx.x] = 0;
-    __syncthreads();  // also: tile staged / previous slice fully consumed
-    // ---- counting sort of the slice by (y,z) cell column, in shared memory
-    float4 r[kRPT];
-    unsigned keyrank[kRPT];
-#pragma unroll
-    for (int j = 0; j < kRPT; ++j) {
-      const unsigned i = (unsigned)j * kEvalThreads + threadIdx.x;
-      keyrank[j] = 0xffffffffu;
-      if (i < cnt) {
-        r[j] = rec[sbase + i];
-        int col = 0;
-        {
-          AxisTaps<DEG, float> A;
-          axis_setup<DEG, float, false>(P, 1, r[j].y, A);
-          col = min(max(A.first, 0), G.cells[1] - 1) - o[1];
-        }
-        if (N == 3) {
-          AxisTaps<DEG, float> A;
-          axis_setup<DEG, float, false>(P, N - 1, r[j].z, A);
-          col += (min(max(A.first, 0), G.cells[N - 1] - 1) - o[2]) * Bk::BY;
-        }
-        const unsigned rank = atomicAdd(&shist[col], 1u);
-        keyrank[j] = ((unsigned)col << 16) | rank;
-      }
-    }
+__global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restrict__ start, const OrdGeom G,
+                                                        long long nq, OrdPlan pl) {
+  __shared__ unsigned buf[1024];
+  __shared__ unsigned carry;
+  const int t = threadIdx.x;
+  // unsort cursors
+  const long long na = (nq + (1LL << kShiftA) - 1) >> kShiftA, nbw = (nq + (1LL << kShiftB) - 1) >> kShiftB;
+  for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << kShiftA);
+  for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << kShiftB);
+  // split-1 cursors
+  for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[(long long)g * kGroupBricks * kClasses];
+  // two exclusive scans: chunks per group, items per brick
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? G.ngroups : G.nbricks;
+    unsigned *dst = pass == 0 ? pl.chunk_start : pl.item_start;
+    if (t == 0) carry = 0;
     __syncthreads();
-    if (threadIdx.x < 32) {  // exclusive scan of FPB <= 64 counters by one warp
-      unsigned a = threadIdx.x < FPB ? shist[threadIdx.x] : 0u;
-      unsigned b = threadIdx.x + 32 < FPB ? shist[threadIdx.x + 32] : 0u;
-      unsigned ia = a, ib = b;
-#pragma unroll
-      for (int w = 1; w < 32; w <<= 1) {
-        const unsigned ta = __shfl_up_sync(0xffffffffu, ia, w);
-        const unsigned tb = __shfl_up_sync(0xffffffffu, ib, w);
-        if (threadIdx.x >= w) {
-          ia += ta;
-          ib += tb;
+    for (int base = 0; base < n; base += 1024) {
+      const int i = base + t;
+      unsigned v = 0;
+      if (i < n) {
+        if (pass == 0) {
+          const long long a = (long long)i * kGroupBricks * kClasses;
+          const long long b = min((long long)(i + 1) * kGroupBricks * kClasses, (long long)G.nfinal);
+          const unsigned cnt = start[b] - start[a];
+          v = (cnt + kChunk16 - 1) / kChunk16;
+        } else {
+          const unsigned cnt = start[(long long)(i + 1) * kClasses] - start[(long long)i * kClasses];
+          v = (cnt + kItemTarget - 1) / kItemTarget;
         }
       }
-      const unsigned tot_a = __shfl_sync(0xffffffffu, ia, 31);
-      if (threadIdx.x < FPB) sstart[threadIdx.x] = ia - a;
-      if (threadIdx.x + 32 < FPB) sstart[threadIdx.x + 32] = tot_a + ib - b;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kRPT; ++j)
-      if (keyrank[j] != 0xffffffffu) srec[sstart[keyrank[j] >> 16] + (keyrank[j] & 0xffffu)] = r[j];
-    __syncthreads();
-    // ---- evaluate in sorted order: a warp's 32 records share (nearly) one cell column
-    for (unsigned i = threadIdx.x; i < cnt; i += kEvalThreads) {
-      const float4 q4 = srec[i];
-      const float x[3] = {q4.x, q4.y, q4.z};
-      AxisTaps<DEG, float> ax[N];
-      int lpos[3] = {0, 0, 0};
-#pragma unroll
-      for (int d = 0; d < N; ++d) {
-        axis_setup<DEG, float, false>(P, d, x[d], ax[d]);
-        lpos[d] = min(max(ax[d].first, 0), G.cells[d] - 1) - o[d];
+      buf[t] = v;
+      __syncthreads();
+      for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned u = t >= o ? buf[t - o] : 0u;
+        __syncthreads();
+        buf[t] += u;
+        __syncthreads();
       }
-      // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )   (Interpolations.jl:304-316)
-      const float *tb = tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0];
-      float val = 0.f;
-#pragma unroll
-      for (int k0 = 0; k0 < L; ++k0) {
-        float v0 = 0.f;
-#pragma unroll
-        for (int k1 = 0; k1 < L; ++k1) {
-          float v1;
-          if (N == 2) {
-            v1 = tb[k1 * TC::PX + k0];
-          } else {
-            v1 = 0.f;
-#pragma unroll
-            for (int k2 = 0; k2 < L; ++k2) {
-              const float t2 = ax[N - 1].wv[k2] * tb[(k2 * TC::TY + k1) * TC::PX + k0];
-              v1 = k2 == 0 ? t2 : t2 + v1;
-            }
-          }
-          const float t1 = ax[1].wv[k1] * v1;
-          v0 = k1 == 0 ? t1 : t1 + v0;
-        }
-        const float t0 = ax[0].wv[k0] * v0;
-        val = k0 == 0 ? t0 : t0 + val;
-      }
-      reinterpret_cast<float *>(P.out_value)[__float_as_uint(q4.w)] = val;
+      if (i < n) dst[i] = carry + buf[t] - v;
+      __syncthreads();
+      if (t == 0) carry += buf[1023];
+      __syncthreads();
     }
+    if (t == 0) dst[n] = carry;
+    __syncthreads();
   }
 }
 
+// ------------------------------------------------------------------------------------------ multisplit
+// One chunk of S records, held in registers (RPT per thread), is counting-sorted by key in shared memory
+// and appended bin by bin to the global bins: one global atomic per (chunk, non-empty bin), stores of whole
+// runs.  key == 0xffffffff marks an absent record.
+template <typename Rec, int S>
+struct SplitSmem {
+  Rec rec[S];
+  unsigned short bin[S];
+  unsigned hist[kMaxBins];
+  unsigned start[kMaxBins];
+  unsigned gbase[kMaxBins];
+  unsigned wtot[32];
+};
+
+template <typename Rec, int S>
+__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r)[S / kSplitThreads],
+                                            const unsigned (&key)[S / kSplitThreads], int nbins, unsigned cnt,
+                                            unsigned *__restrict__ cursor, Rec *__restrict__ out) {
+  constexpr int RPT = S / kSplitThreads;
+  const int t = threadIdx.x;
+  sm.hist[t] = 0;  // kMaxBins == kSplitThreads
+  __syncthreads();
+  unsigned rank[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+    if (key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
+  __syncthreads();
+  unsigned gb = 0;
+  {  // exclusive scan of the nbins counters, one per thread
+    const unsigned v = t < nbins ? sm.hist[t] : 0u;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((t & 31) >= o) inc += u;
+    }
+    if ((t & 31) == 31) sm.wtot[t >> 5] = inc;
+    __syncthreads();
+    if (t < 32) {
+      const unsigned w = t < kSplitThreads / 32 ? sm.wtot[t] : 0u;
+      unsigned winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, winc, o);
+        if (t >= o) winc += u;
+      }
+      sm.wtot[t] = winc - w;
+    }
+    __syncthreads();
+    const unsigned st = sm.wtot[t >> 5] + inc - v;
+    sm.start[t] = st;
+    // the reservation's round trip to the L2 overlaps the shared-memory scatter below
+    if (v) gb = atomicAdd(cursor + t, v) - st;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+    if (key[j] != 0xffffffffu) {
+      const unsigned slot = sm.start[key[j]] + rank[j];
+      sm.rec[slot] = r[j];
+      sm.bin[slot] = (unsigned short)key[j];
+    }
+  sm.gbase[t] = gb;
+  __syncthreads();
+  for (unsigned i = t; i < cnt; i += kSplitThreads) out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
+  __syncthreads();
+}
+
+// split 1: coordinates -> {x,y,z,q} records grouped by brick group
 template <int N, int DEG>
-static int run_sorted(int dev, EvalParams &P, const b200itp_desc *D, void *scratch, size_t scratch_bytes,
-                      cudaStream_t st, bool *done) {
+__global__ void __launch_bounds__(kSplitThreads) ord_split1_kernel(const __grid_constant__ EvalParams P,
+                                                                   const OrdGeom G, unsigned *__restrict__ cursor1,
+                                                                   float4 *__restrict__ rec1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
+  constexpr int RPT = kChunk16 / kSplitThreads;
+  const long long nchunks = (P.nq + kChunk16 - 1) / kChunk16;
+  // the coordinates of the next chunk are fetched before the current chunk goes through shared memory
+  float nx[RPT][3];
+  auto fetch = [&](long long ch) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const long long q = ch * kChunk16 + j * kSplitThreads + threadIdx.x;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        nx[j][d] = (d < N && ch < nchunks && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
+    }
+  };
+  fetch(blockIdx.x);
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long base = ch * kChunk16;
+    const unsigned cnt = (unsigned)min((long long)kChunk16, P.nq - base);
+    float4 r[RPT];
+    unsigned key[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const long long q = base + j * kSplitThreads + threadIdx.x;
+      key[j] = 0xffffffffu;
+      if (q < P.nq) {
+        float x[3] = {nx[j][0], nx[j][1], nx[j][2]};
+        bool valid;
+        check_query<N>(P, x, valid);
+        int brick, cls;
+        locate<N, DEG>(P, G, x, brick, cls);
+        key[j] = (unsigned)(brick / kGroupBricks);
+        r[j] = make_float4(x[0], x[1], x[2], __uint_as_float((unsigned)q));
+      }
+    }
+    fetch(ch + gridDim.x);
+    block_split<float4, kChunk16>(sm, r, key, G.ngroups, cnt, cursor1, rec1);
+  }
+}
+
+// split 2: records of one group -> (brick, class) streams
+template <int N, int DEG>
+__global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_constant__ EvalParams P,
+                                                                   const OrdGeom G,
+                                                                   const unsigned *__restrict__ start,
+                                                                   const unsigned *__restrict__ chunk_start,
+                                                                   unsigned *__restrict__ cursor2,
+                                                                   const float4 *__restrict__ rec1,
+                                                                   float4 *__restrict__ rec2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
+  __shared__ unsigned s_chunk[kMaxBins + 1];
+  constexpr int RPT = kChunk16 / kSplitThreads;
+  for (int i = threadIdx.x; i <= G.ngroups; i += kSplitThreads) s_chunk[i] = chunk_start[i];
+  __syncthreads();
+  const unsigned nchunks = s_chunk[G.ngroups];
+  // chunk descriptor: group, first record, count; the records of the next chunk are fetched early
+  auto describe = [&](unsigned ch, int &g, unsigned &base, unsigned &cnt, long long &fa, long long &fb) {
+    int lo = 0, hi = G.ngroups - 1;  // last group with chunk_start <= ch
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_chunk[mid] <= ch) lo = mid; else hi = mid - 1;
+    }
+    g = lo;
+    fa = (long long)g * kGroupBricks * kClasses;
+    fb = min(fa + kGroupBricks * kClasses, (long long)G.nfinal);
+    const unsigned gbeg = start[fa], gend = start[fb];
+    base = gbeg + (ch - s_chunk[g]) * kChunk16;
+    cnt = min((unsigned)kChunk16, gend - base);
+  };
+  float4 nr[RPT];
+  int g = 0, ng = 0;
+  unsigned base = 0, cnt = 0, nbase = 0, ncnt = 0;
+  long long fa = 0, fb = 0, nfa = 0, nfb = 0;
+  auto fetch = [&](unsigned ch) {
+    ncnt = 0;
+    if (ch < nchunks) describe(ch, ng, nbase, ncnt, nfa, nfb);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const unsigned i = j * kSplitThreads + threadIdx.x;
+      if (i < ncnt) nr[j] = rec1[nbase + i];
+    }
+  };
+  fetch(blockIdx.x);
+  for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    g = ng; base = nbase; cnt = ncnt; fa = nfa; fb = nfb;
+    float4 r[RPT];
+    unsigned key[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const unsigned i = j * kSplitThreads + threadIdx.x;
+      key[j] = 0xffffffffu;
+      if (i < cnt) {
+        r[j] = nr[j];
+        const float x[3] = {r[j].x, r[j].y, r[j].z};
+        int brick, cls;
+        locate<N, DEG>(P, G, x, brick, cls);
+        key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
+      }
+    }
+    fetch(ch + gridDim.x);
+    block_split<float4, kChunk16>(sm, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
+  }
+}
+
+// unsort: {q, value} records by (q >> shift) relative to the chunk's parent bin
+template <int LEVEL>
+__global__ void __launch_bounds__(kSplitThreads) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq,
+                                                                   unsigned *__restrict__ cursor,
+                                                                   uint2 *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<SplitSmem<uint2, kChunk8> *>(smem_raw);
+  constexpr int RPT = kChunk8 / kSplitThreads;
+  const long long nchunks = (nq + kChunk8 - 1) / kChunk8;
+  uint2 nr[RPT];
+  auto fetch = [&](long long ch) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const long long i = ch * kChunk8 + j * kSplitThreads + threadIdx.x;
+      if (ch < nchunks && i < nq) nr[j] = in[i];
+    }
+  };
+  fetch(blockIdx.x);
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long base = ch * kChunk8;
+    const unsigned cnt = (unsigned)min((long long)kChunk8, nq - base);
+    // level A: bins over the whole array; level B: the chunk lies inside one level-A bin (2^kShiftA records)
+    const unsigned bin0 = LEVEL == 0 ? 0u : (unsigned)(base >> kShiftA) << (kShiftA - kShiftB);
+    const int nbins = LEVEL == 0 ? (int)((nq + (1LL << kShiftA) - 1) >> kShiftA)
+                                 : (int)min((long long)(1 << (kShiftA - kShiftB)),
+                                            ((nq + (1LL << kShiftB) - 1) >> kShiftB) - (long long)bin0);
+    uint2 r[RPT];
+    unsigned key[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const long long i = base + j * kSplitThreads + threadIdx.x;
+      key[j] = 0xffffffffu;
+      if (i < nq) {
+        r[j] = nr[j];
+        key[j] = LEVEL == 0 ? (r[j].x >> kShiftA) : ((r[j].x >> kShiftB) - bin0);
+      }
+    }
+    fetch(ch + gridDim.x);
+    block_split<uint2, kChunk8>(sm, r, key, nbins, cnt, cursor + bin0, out);
+  }
+}
+
+// place: window w holds exactly the results q in [w * 2^kShiftB, ...): permute in shared memory
+__global__ void __launch_bounds__(1024) ord_place_kernel(const uint2 *__restrict__ in, long long nq,
+                                                         float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *win = reinterpret_cast<float *>(smem_raw);
+  constexpr int W = 1 << kShiftB;
+  const long long base = (long long)blockIdx.x * W;
+  const int cnt = (int)min((long long)W, nq - base);
+  for (int i = threadIdx.x; i < cnt; i += 1024) {
+    const uint2 r = in[base + i];
+    win[r.x & (W - 1)] = __uint_as_float(r.y);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += 1024) out[base + i] = win[i];
+}
+
+// ------------------------------------------------------------------------------------------ evaluate
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int N, int DEG>
+struct EvalSmem {
+  float tile[TileCfg<N, DEG>::FLOATS];
+  float4 stage[2][kClasses][kRowPitch];
+  long long axoff[3][TileCfg<N, DEG>::MAXT];  // element offset of tile coordinate l on each axis, -1: outside
+  unsigned cbeg[kClasses];  // first record of the item's share of each class stream
+  unsigned ccnt[kClasses];
+  int item_brick, item_part, item_parts, max_cnt;
+};
+
+template <int N, int DEG>
+__global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_constant__ EvalParams P,
+                                                                   const OrdGeom G,
+                                                                   const unsigned *__restrict__ start,
+                                                                   const unsigned *__restrict__ item_start,
+                                                                   const float4 *__restrict__ rec,
+                                                                   uint2 *__restrict__ res) {
+  using TC = TileCfg<N, DEG>;
   using Bk = Brick<N>;
-  *done = false;
-  SortGeom G;
+  constexpr int L = TC::L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<EvalSmem<N, DEG> *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kEvalThreads / 32;
+  const float *coefs = reinterpret_cast<const float *>(P.coefs);
+  const unsigned nitems = item_start[G.nbricks];
+  const unsigned it_lo = (unsigned)((unsigned long long)nitems * blockIdx.x / gridDim.x);
+  const unsigned it_hi = (unsigned)((unsigned long long)nitems * (blockIdx.x + 1) / gridDim.x);
+  int cur_brick = -1;
+  int o[3] = {0, 0, 0};
+
+  for (unsigned item = it_lo; item < it_hi; ++item) {
+    __syncthreads();  // previous item fully consumed (stage buffers, cbeg/ccnt)
+    if (tid == 0) {
+      int lo = 0, hi = G.nbricks - 1;  // last brick with item_start <= item (skips empty bricks)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+      }
+      sm.item_brick = lo;
+      sm.item_part = (int)(item - item_start[lo]);
+      sm.item_parts = (int)(item_start[lo + 1] - item_start[lo]);
+      sm.max_cnt = 0;
+    }
+    __syncthreads();
+    const int brick = sm.item_brick;
+    if (tid < kClasses) {
+      const unsigned s = start[(long long)brick * kClasses + tid];
+      const unsigned long long n = start[(long long)brick * kClasses + tid + 1] - s;
+      const unsigned a = (unsigned)(n * (unsigned)sm.item_part / (unsigned)sm.item_parts);
+      const unsigned b = (unsigned)(n * (unsigned)(sm.item_part + 1) / (unsigned)sm.item_parts);
+      sm.cbeg[tid] = s + a;
+      sm.ccnt[tid] = b - a;
+      atomicMax(&sm.max_cnt, (int)(b - a));
+    }
+    if (brick != cur_brick) {  // stage the brick + halo; tile element l <-> parent index o + l on each axis
+      cur_brick = brick;
+      const int bx = brick % G.nb[0];
+      const int by = (brick / G.nb[0]) % G.nb[1];
+      const int bz = brick / (G.nb[0] * G.nb[1]);
+      o[0] = bx * Bk::BX;
+      o[1] = by * Bk::BY;
+      o[2] = bz * Bk::BZ;
+      constexpr int TDIM[3] = {TC::TX, TC::TY, TC::TZ};
+      for (int e = tid; e < 3 * TC::MAXT; e += kEvalThreads) {  // per-axis offset tables, once per brick
+        const int d = e / TC::MAXT, l = e % TC::MAXT;
+        if (d < N && l < TDIM[d]) {
+          int idx = o[d] + l;  // parent index of the tap
+          long long off = -1;
+          if (P.periodic[d]) {
+            const int n = P.n[d];
+            idx = idx - 1;  // modrange1(idx, n) - 1 without a division in the common case
+            if (idx < 0) idx += n;
+            if (idx >= n) idx -= n;
+            if (idx >= n) idx %= n;  // axes shorter than the tile
+            off = (long long)idx * P.stride[d];
+          } else {
+            const int pos = idx - P.coef_first[d];
+            const int size_d = P.n[d] + (P.coef_first[d] == 0 ? 2 : 0);
+            if (pos >= 0 && pos < size_d) off = (long long)pos * P.stride[d];
+          }
+          sm.axoff[d][l] = off;
+        }
+      }
+      __syncthreads();
+      for (int t = tid; t < TC::TX * TC::TY * TC::TZ; t += kEvalThreads) {
+        const int lx = t % TC::TX;
+        const int ly = (t / TC::TX) % TC::TY;
+        const int lz = t / (TC::TX * TC::TY);
+        const long long ox = sm.axoff[0][lx], oy = sm.axoff[1][ly], oz = N == 3 ? sm.axoff[2][lz] : 0;
+        const bool ok = ox >= 0 && oy >= 0 && oz >= 0;
+        sm.tile[(lz * TC::TY + ly) * TC::PX + lx] = ok ? __ldg(coefs + (ox + oy + oz)) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int rounds = (sm.max_cnt + kRows - 1) / kRows;
+
+    // warp w stages and drains classes w, w + NW: no other warp touches those rows of the stage buffers
+    auto issue = [&](int rd) {
+      if (rd < rounds) {
+#pragma unroll
+        for (int c = warp; c < kClasses; c += NW) {
+          const unsigned cnt = sm.ccnt[c];
+          const unsigned r0 = (unsigned)rd * kRows;
+#pragma unroll
+          for (int i = lane; i < kRows; i += 32)
+            if (r0 + i < cnt) cp_async16(&sm.stage[rd & 1][c][i], rec + sm.cbeg[c] + r0 + i);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto drain = [&](int rd) {  // results of round rd: {q, value} in the first 8 bytes of every record slot
+#pragma unroll
+      for (int c = warp; c < kClasses; c += NW) {
+        const unsigned cnt = sm.ccnt[c];
+        const unsigned r0 = (unsigned)rd * kRows;
+#pragma unroll
+        for (int i = lane; i < kRows; i += 32)
+          if (r0 + i < cnt) {
+            const float4 v = sm.stage[rd & 1][c][i];
+            res[sm.cbeg[c] + r0 + i] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+          }
+      }
+    };
+
+    issue(0);
+    for (int rd = 0; rd < rounds; ++rd) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // round rd landed; round rd-1 computed by every warp
+      if (rd > 0) drain(rd - 1);
+      issue(rd + 1);    // refills the buffer just drained (same warp, same rows)
+      const unsigned mycnt = sm.ccnt[lane];
+      for (int i = warp; i < kRows; i += NW) {
+        if ((unsigned)rd * kRows + i < mycnt) {
+          const float4 q4 = sm.stage[rd & 1][lane][i];
+          const float x[3] = {q4.x, q4.y, q4.z};
+          AxisTaps<DEG, float> ax[N];
+          int lpos[3] = {0, 0, 0};
+#pragma unroll
+          for (int d = 0; d < N; ++d) {
+            axis_setup<DEG, float, false>(P, d, x[d], ax[d]);
+            lpos[d] = min(max(ax[d].first, 0), G.cells[d] - 1) - o[d];
+          }
+          // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )  (Interpolations.jl:304-316)
+          const float *tb = sm.tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0];
+          float val = 0.f;
+#pragma unroll
+          for (int k0 = 0; k0 < L; ++k0) {
+            float v0 = 0.f;
+#pragma unroll
+            for (int k1 = 0; k1 < L; ++k1) {
+              float v1;
+              if (N == 2) {
+                v1 = tb[k1 * TC::PX + k0];
+              } else {
+                v1 = 0.f;
+#pragma unroll
+                for (int k2 = 0; k2 < L; ++k2) {
+                  const float t2 = ax[N - 1].wv[k2] * tb[(k2 * TC::TY + k1) * TC::PX + k0];
+                  v1 = k2 == 0 ? t2 : t2 + v1;
+                }
+              }
+              const float t1 = ax[1].wv[k1] * v1;
+              v0 = k1 == 0 ? t1 : t1 + v0;
+            }
+            const float t0 = ax[0].wv[k0] * v0;
+            val = k0 == 0 ? t0 : t0 + val;
+          }
+          sm.stage[rd & 1][lane][i] = make_float4(q4.w, val, 0.f, 0.f);
+        }
+      }
+    }
+    __syncthreads();
+    if (rounds > 0) drain(rounds - 1);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct OrdLayout {
+  size_t rec1, rec2, hist, start, sums, cursor1, chunk_start, item_start, cursorA, cursorB, total;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static OrdLayout ord_layout(long long nq, long long nfinal, long long nbricks, long long ngroups) {
+  OrdLayout Lo;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  Lo.rec1 = take((size_t)nq * 16);
+  Lo.rec2 = take((size_t)nq * 16);
+  Lo.hist = take((size_t)(nfinal + 1) * 4);
+  Lo.start = take((size_t)(nfinal + 1) * 4);
+  Lo.sums = take(65536 * 4);
+  Lo.cursor1 = take((size_t)ngroups * 4);
+  Lo.chunk_start = take((size_t)(ngroups + 1) * 4);
+  Lo.item_start = take((size_t)(nbricks + 1) * 4);
+  Lo.cursorA = take((size_t)(((nq + (1LL << kShiftA) - 1) >> kShiftA) + 1) * 4);
+  Lo.cursorB = take((size_t)(((nq + (1LL << kShiftB) - 1) >> kShiftB) + 1) * 4);
+  Lo.total = off;
+  return Lo;
+}
+
+template <int N, int DEG>
+static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G) {
+  using Bk = Brick<N>;
+  const int bdim[3] = {Bk::BX, Bk::BY, Bk::BZ};
   long long bricks = 1;
   for (int d = 0; d < 3; ++d) {
     G.nb[d] = 1;
     G.cells[d] = 1;
   }
-  const int bdim[3] = {Bk::BX, Bk::BY, Bk::BZ};
   for (int d = 0; d < N; ++d) {
     // first-tap indices: periodic 0..n-1, otherwise 0..size-1-DEG
     G.cells[d] = P.periodic[d] ? P.n[d] : (int)D->size[d] - DEG;
-    if (G.cells[d] < 1) return 0;
+    if (G.cells[d] < 1) return false;
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
     bricks *= G.nb[d];
   }
-  G.nbins = bricks;
-  if (bricks > 0x7fffffffLL || G.nbins > (1LL << 27) || P.nq > 0xfffffff0LL) return 0;
-  const size_t need = (size_t)P.nq * 16 + (size_t)(G.nbins + 1) * 8 + 65536 * 4 + 1024;
-  if (!scratch || scratch_bytes < need || ((uintptr_t)scratch % 16) != 0) return 0;
-  float4 *rec = reinterpret_cast<float4 *>(scratch);
-  unsigned *hist = reinterpret_cast<unsigned *>(rec + P.nq);
-  unsigned *start = hist + (G.nbins + 1);
-  unsigned *sums = start + (G.nbins + 1);
-  const long long per = (long long)kScanBlock * kScanPer;
-  const long long nsb = (G.nbins + per - 1) / per;
-  if (nsb > 65536) return 0;
+  if (bricks > (long long)kGroupBricks * kMaxBins) return false;
+  G.nbricks = (int)bricks;
+  G.ngroups = (int)((bricks + kGroupBricks - 1) / kGroupBricks);
+  G.nfinal = (int)bricks * kClasses;
+  return true;
+}
 
-  B200_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)(G.nbins + 1) * 4, st));
-  const int blocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sm_count(dev) * 16);
-  sort_count_kernel<N, DEG><<<blocks, 256, 0, st>>>(P, G, hist);
-  scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nbins, sums);
+template <int N, int DEG>
+static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scratch, size_t scratch_bytes,
+                       cudaStream_t st, bool *done) {
+  *done = false;
+  OrdGeom G;
+  if (!ord_geometry<N, DEG>(P, D, G)) return 0;
+  if (P.nq > 0xfffffff0LL) return 0;
+  const OrdLayout Lo = ord_layout(P.nq, G.nfinal, G.nbricks, G.ngroups);
+  if (!scratch || scratch_bytes < Lo.total || ((uintptr_t)scratch % 256) != 0) return 0;
+  unsigned char *sb = reinterpret_cast<unsigned char *>(scratch);
+  float4 *rec1 = reinterpret_cast<float4 *>(sb + Lo.rec1);
+  float4 *rec2 = reinterpret_cast<float4 *>(sb + Lo.rec2);
+  unsigned *hist = reinterpret_cast<unsigned *>(sb + Lo.hist);
+  unsigned *start = reinterpret_cast<unsigned *>(sb + Lo.start);
+  unsigned *sums = reinterpret_cast<unsigned *>(sb + Lo.sums);
+  OrdPlan pl;
+  pl.cursor1 = reinterpret_cast<unsigned *>(sb + Lo.cursor1);
+  pl.chunk_start = reinterpret_cast<unsigned *>(sb + Lo.chunk_start);
+  pl.item_start = reinterpret_cast<unsigned *>(sb + Lo.item_start);
+  pl.cursorA = reinterpret_cast<unsigned *>(sb + Lo.cursorA);
+  pl.cursorB = reinterpret_cast<unsigned *>(sb + Lo.cursorB);
+  // results {q, value}: rec1 is dead after split 2 (two 8-byte arrays fit in it), rec2 after the evaluation
+  uint2 *res = reinterpret_cast<uint2 *>(rec1);
+  uint2 *resA = res + P.nq;
+  uint2 *resB = reinterpret_cast<uint2 *>(rec2);
+
+  const int sms = sm_count(dev);
+  const long long per = (long long)kScanBlock * kScanPer;
+  const long long nsb = (G.nfinal + per - 1) / per;
+  constexpr size_t smem16 = sizeof(SplitSmem<float4, kChunk16>), smem8 = sizeof(SplitSmem<uint2, kChunk8>);
+  constexpr size_t smem_eval = sizeof(EvalSmem<N, DEG>);
+  static_assert(smem_eval <= 227 * 1024, "evaluation tile does not fit shared memory");
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 << kShiftB)));
+
+  B200_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)(G.nfinal + 1) * 4, st));
+  const int cblocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sms * 16);
+  ord_count_kernel<N, DEG><<<cblocks, 256, 0, st>>>(P, G, hist);
+  scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums);
   scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)nsb);
-  scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nbins, sums, start);
-  sort_scatter_kernel<N, DEG><<<blocks, 256, 0, st>>>(P, G, hist, rec);
-  dim3 grid((unsigned)bricks, kSplit, 1);
-  sort_eval_kernel<N, DEG><<<grid, kEvalThreads, 0, st>>>(P, G, start, rec);
-  count_launch(6);
+  scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums, start);
+  ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, pl);
+  const int sblocks = sms * 2;
+  ord_split1_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+  ord_split2_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
+  ord_eval_kernel<N, DEG><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
+  const uint2 *last = res;
+  if (P.nq > (1LL << kShiftA)) {
+    ord_unsort_kernel<0><<<sblocks, kSplitThreads, smem8, st>>>(res, P.nq, pl.cursorA, resA);
+    count_launch();
+    last = resA;
+  }
+  ord_unsort_kernel<1><<<sblocks, kSplitThreads, smem8, st>>>(last, P.nq, pl.cursorB, resB);
+  const long long nwin = (P.nq + (1LL << kShiftB) - 1) >> kShiftB;
+  ord_place_kernel<<<(unsigned)nwin, 1024, (4 << kShiftB), st>>>(resB, P.nq, reinterpret_cast<float *>(P.out_value));
+  count_launch(10);
   B200_CUDA_OK(cudaGetLastError());
   *done = true;
   return 0;
 }
 
+// Query count from which the ordered pipeline is used (tests lower it to exercise the pipeline on
+// small inputs; results do not depend on it).
+static int64_t g_sorted_min_queries = 1 << 20;
+
 }  // namespace b200itp
 
 using namespace b200itp;
 
+extern "C" int64_t b200itp_eval_sorted_min_queries(void) { return g_sorted_min_queries; }
+extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) { g_sorted_min_queries = n < 1 ? 1 : n; }
+
 extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
   if (!d || nq <= 0) return 0;
-  long long cells = 1;
-  for (int i = 0; i < d->ndims && i < B200ITP_MAX_DIMS; ++i) cells *= (d->size[i] > 0 ? d->size[i] : 1);
-  // records + histogram/start arrays (one bin per run of 32 cells, generously rounded) + scan sums
-  return (size_t)nq * 16 + (size_t)(cells / 16 + 4096) * 8 + 65536 * 4 + 4096;
+  // upper bound over the supported geometries: kGroupBricks * kMaxBins bricks
+  const long long nbricks = (long long)kGroupBricks * kMaxBins;
+  return ord_layout(nq, nbricks * kClasses, nbricks, kMaxBins).total + 256;
 }
 
 extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
@@ -428,12 +861,23 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
   rc = fill_eval_params_public(d, coefs, coords, nq, out_value, (unsigned long long *)flag, P, &deg, &plain);
   if (rc) return rc;
   bool done = false;
-  if (plain && nq > 0 && (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) && (d->ndims == 2 || d->ndims == 3)) {
+  if (plain && nq >= g_sorted_min_queries && (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) &&
+      (d->ndims == 2 || d->ndims == 3)) {
     B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
-    if (d->ndims == 3 && deg == 3) rc = run_sorted<3, 3>(dev, P, d, scratch, scratch_bytes, st, &done);
-    if (d->ndims == 3 && deg == 2) rc = run_sorted<3, 2>(dev, P, d, scratch, scratch_bytes, st, &done);
-    if (d->ndims == 2 && deg == 3) rc = run_sorted<2, 3>(dev, P, d, scratch, scratch_bytes, st, &done);
-    if (d->ndims == 2 && deg == 2) rc = run_sorted<2, 2>(dev, P, d, scratch, scratch_bytes, st, &done);
+    // the scratch pointer is aligned up to 256 bytes inside the caller's buffer
+    unsigned char *sp = reinterpret_cast<unsigned char *>(scratch);
+    size_t sbytes = scratch_bytes;
+    if (sp) {
+      const size_t mis = (256 - ((uintptr_t)sp % 256)) % 256;
+      if (mis <= sbytes) {
+        sp += mis;
+        sbytes -= mis;
+      }
+    }
+    if (d->ndims == 3 && deg == 3) rc = run_ordered<3, 3>(dev, P, d, sp, sbytes, st, &done);
+    if (d->ndims == 3 && deg == 2) rc = run_ordered<3, 2>(dev, P, d, sp, sbytes, st, &done);
+    if (d->ndims == 2 && deg == 3) rc = run_ordered<2, 3>(dev, P, d, sp, sbytes, st, &done);
+    if (d->ndims == 2 && deg == 2) rc = run_ordered<2, 2>(dev, P, d, sp, sbytes, st, &done);
     if (rc) return rc;
     if (done) {
       if (first_oob) {
