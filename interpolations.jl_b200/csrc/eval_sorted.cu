@@ -308,43 +308,39 @@ template <typename Rec, int S>
 __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r)[S / kSplitThreads],
                                             const unsigned (&key)[S / kSplitThreads], int nbins, unsigned cnt,
                                             unsigned *__restrict__ cursor, Rec *__restrict__ out) {
+  // sm.hist is all zero on entry (zeroed by split_init / by the previous call right after it was read)
   constexpr int RPT = S / kSplitThreads;
-  const int t = threadIdx.x;
-  sm.hist[t] = 0;  // kMaxBins == kSplitThreads
-  __syncthreads();
+  constexpr int NW = kSplitThreads / 32;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   unsigned rank[RPT];
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
     if (key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
-  __syncthreads();
-  unsigned gb = 0;
-  {  // exclusive scan of the nbins counters, one per thread
-    const unsigned v = t < nbins ? sm.hist[t] : 0u;
-    unsigned inc = v;
+  __syncthreads();  // (1) histogram complete; the previous chunk's copy-out has finished in every warp
+  // exclusive scan of the counters, one per thread: warp scan, then every warp scans the NW warp totals itself
+  const unsigned v = t < nbins ? sm.hist[t] : 0u;
+  sm.hist[t] = 0;  // ready for the next chunk (its atomics come after barrier (3))
+  unsigned inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((t & 31) >= o) inc += u;
-    }
-    if ((t & 31) == 31) sm.wtot[t >> 5] = inc;
-    __syncthreads();
-    if (t < 32) {
-      const unsigned w = t < kSplitThreads / 32 ? sm.wtot[t] : 0u;
-      unsigned winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, winc, o);
-        if (t >= o) winc += u;
-      }
-      sm.wtot[t] = winc - w;
-    }
-    __syncthreads();
-    const unsigned st = sm.wtot[t >> 5] + inc - v;
-    sm.start[t] = st;
-    // the reservation's round trip to the L2 overlaps the shared-memory scatter below
-    if (v) gb = atomicAdd(cursor + t, v) - st;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
   }
-  __syncthreads();
+  if (lane == 31) sm.wtot[warp] = inc;
+  __syncthreads();  // (2)
+  unsigned wv = lane < NW ? sm.wtot[lane] : 0u, winc = wv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += u;
+  }
+  const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+  const unsigned st = wbase + inc - v;
+  sm.start[t] = st;
+  // the reservation's round trip to the L2 overlaps the shared-memory scatter below
+  unsigned gb = 0;
+  if (v) gb = atomicAdd(cursor + t, v) - st;
+  __syncthreads();  // (3) start[] visible
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
     if (key[j] != 0xffffffffu) {
@@ -353,8 +349,14 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
       sm.bin[slot] = (unsigned short)key[j];
     }
   sm.gbase[t] = gb;
-  __syncthreads();
+  __syncthreads();  // (4) records in bin order
   for (unsigned i = t; i < cnt; i += kSplitThreads) out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
+  // no barrier here: the next call touches only hist[] before its barrier (1)
+}
+
+template <typename Rec, int S>
+__device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
+  sm.hist[threadIdx.x] = 0;  // kMaxBins == kSplitThreads
   __syncthreads();
 }
 
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split1_kernel(const __grid_
                                                                    float4 *__restrict__ rec1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
+  split_init(sm);
   constexpr int RPT = kChunk16 / kSplitThreads;
   const long long nchunks = (P.nq + kChunk16 - 1) / kChunk16;
   // the coordinates of the next chunk are fetched before the current chunk goes through shared memory
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_
                                                                    float4 *__restrict__ rec2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
+  split_init(sm);
   __shared__ unsigned s_chunk[kMaxBins + 1];
   constexpr int RPT = kChunk16 / kSplitThreads;
   for (int i = threadIdx.x; i <= G.ngroups; i += kSplitThreads) s_chunk[i] = chunk_start[i];
@@ -475,6 +479,7 @@ __global__ void __launch_bounds__(kSplitThreads) ord_unsort_kernel(const uint2 *
                                                                    uint2 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<uint2, kChunk8> *>(smem_raw);
+  split_init(sm);
   constexpr int RPT = kChunk8 / kSplitThreads;
   const long long nchunks = (nq + kChunk8 - 1) / kChunk8;
   uint2 nr[RPT];
@@ -557,11 +562,35 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kEvalThreads / 32;
   const float *coefs = reinterpret_cast<const float *>(P.coefs);
-  const unsigned nitems = item_start[G.nbricks];
-  const unsigned it_lo = (unsigned)((unsigned long long)nitems * blockIdx.x / gridDim.x);
-  const unsigned it_hi = (unsigned)((unsigned long long)nitems * (blockIdx.x + 1) / gridDim.x);
+  // CTA c takes the work items that begin in its share [R*c/G, R*(c+1)/G) of the R ordered records: balanced by
+  // records, whatever the sizes of the items (the items of one brick have equal sizes n_b / P_b)
+  auto first_item = [&](unsigned cta) -> unsigned {
+    const unsigned nitems = item_start[G.nbricks];
+    if (cta >= gridDim.x) return nitems;
+    if (cta == 0) return 0u;
+    const unsigned long long total = start[G.nfinal];
+    const unsigned target = (unsigned)(total * cta / gridDim.x);
+    int lo = 0, hi = G.nbricks - 1;  // last brick whose first record is <= target
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (start[(long long)mid * kClasses] <= target) lo = mid; else hi = mid - 1;
+    }
+    const unsigned s0 = start[(long long)lo * kClasses], nb = start[(long long)(lo + 1) * kClasses] - s0;
+    const unsigned parts = item_start[lo + 1] - item_start[lo];
+    if (nb == 0 || parts == 0) return item_start[lo + 1];
+    // first part whose first record (s0 + nb * p / parts) is >= target
+    const unsigned long long num = (unsigned long long)(target - s0) * parts;
+    const unsigned p = (unsigned)((num + nb - 1) / nb);
+    return item_start[lo] + min(p, parts);
+  };
+  const unsigned it_lo = first_item(blockIdx.x);
+  const unsigned it_hi = first_item(blockIdx.x + 1);
   int cur_brick = -1;
   int o[3] = {0, 0, 0};
+#ifdef B200ITP_EVAL_TRACE
+  const long long t_begin = clock64();
+  unsigned long long n_rec = 0, n_rounds = 0, n_tiles = 0;
+#endif
 
   for (unsigned item = it_lo; item < it_hi; ++item) {
     __syncthreads();  // previous item fully consumed (stage buffers, cbeg/ccnt)
@@ -589,6 +618,9 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     }
     if (brick != cur_brick) {  // stage the brick + halo; tile element l <-> parent index o + l on each axis
       cur_brick = brick;
+#ifdef B200ITP_EVAL_TRACE
+      ++n_tiles;
+#endif
       const int bx = brick % G.nb[0];
       const int by = (brick / G.nb[0]) % G.nb[1];
       const int bz = brick / (G.nb[0] * G.nb[1]);
@@ -628,6 +660,12 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     }
     __syncthreads();
     const int rounds = (sm.max_cnt + kRows - 1) / kRows;
+#ifdef B200ITP_EVAL_TRACE
+    if (tid == 0) {
+      for (int c = 0; c < kClasses; ++c) n_rec += sm.ccnt[c];
+      n_rounds += rounds;
+    }
+#endif
 
     // warp w stages and drains classes w, w + NW: no other warp touches those rows of the stage buffers
     auto issue = [&](int rd) {
@@ -708,6 +746,14 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     if (rounds > 0) drain(rounds - 1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+#ifdef B200ITP_EVAL_TRACE
+  if (tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("evaltrace cta %d sm %u items %u records %llu rounds %llu tiles %llu cycles %lld\n", blockIdx.x, smid,
+           it_hi - it_lo, n_rec, n_rounds, n_tiles, clock64() - t_begin);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ host
