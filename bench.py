@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 
 N_GRID = 512
 DEFAULT_QUERIES = 10**9
+# DRAM bytes per query of one ordered evaluation call, from the ncu launch list in profiles/ (all launches summed)
+NCU_TRAFFIC_PER_QUERY = 142.3
 METRIC = "Gevals/s tricubic + prefilter GB/s (512^3 f32) at 1/2/4/8 B200 vs HBM peak"
 
 
@@ -221,7 +223,8 @@ def main():
             return m.evaluate_sorted(itp, *coords)
         return itp(*coords)
 
-    # ---- device-resident throughput
+    # ---- device-resident throughput; every kernel launch of the timed steps is bracketed by CUDA events on the
+    #      launching stream (b200itp_profile_*), which is where the roofline's per-kernel durations come from
     for _ in range(args.warmup):
         out = step()
     barrier()
@@ -230,12 +233,15 @@ def main():
         sampler.start()
     l0 = L.b200itp_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    L.b200itp_profile_enable(1)
     barrier()
     ev[0].record()
     for _ in range(args.steps):
         out = step()
     ev[1].record()
     barrier()
+    L.b200itp_profile_enable(0)
+    stages = m._lib.profile_stages()
     launches = L.b200itp_launch_count() - l0
     t_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
     if world > 1:
@@ -244,33 +250,50 @@ def main():
     value = nq * world / (ms_per_step * 1e-3) / 1e9
     checksum = float(out.double().sum().item())
 
-    # ---- kernel-level timings on this rank: evaluation kernel (dominant) and the prefilter passes
-    itp = m.interpolate(A, it, device=dev)
-
-    def time_fn(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        return float(np.mean(ts))
-
-    eval_fn = (lambda: m.evaluate_sorted(itp, *coords)) if args.sorted else (lambda: itp(*coords))
-    eval_ms = time_fn(eval_fn, max(2, args.steps))
-    work = itp.coefs.clone()
-    pre_ms = time_fn(lambda: m.prefilter_(work, itp.size, itp.its, local_rank), 10)
+    # ---- roofline (HBM): algorithmic bytes per launch / live CUDA-event duration
     peak, peak_kind = measured_peak()
-    eval_bytes = nq * (12 + 4) + 4 * N_GRID**3          # coordinates in, results out, coefficients once
-    pre_bytes = 2 * 4 * N_GRID**3 * 3                   # one read + one write per axis pass
-    roof = {"bound": "hbm", "kernel": "evaluation (eval_kernel / ordered pipeline)",
+    ncoef = N_GRID**3
+    per_query = {"ord_count": 12, "ord_split1": 12 + 16, "ord_split2": 16 + 16, "ord_eval": 16 + 8,
+                 "ord_unsortA": 8 + 8, "ord_unsortB": 8 + 8, "ord_place": 8 + 4, "eval_direct_value": 12 + 4}
+    stage_rows = []
+    eval_ms = 0.0
+    pre_ms = 0.0
+    for name, ts in stages.items():
+        avg = float(np.mean(ts))
+        per_step = float(np.sum(ts)) / args.steps
+        if name in per_query:
+            b = per_query[name] * nq + (4 * ncoef if name in ("ord_eval", "eval_direct_value") else 0)
+            eval_ms += per_step
+        elif name.startswith("prefilter_axis"):
+            b = 2 * 4 * ncoef
+            pre_ms += per_step
+        elif name == "copy_with_padding":
+            b = 2 * 4 * ncoef
+        else:
+            b = 0
+            if name.startswith("ord_"):
+                eval_ms += per_step
+        stage_rows.append({"kernel": name, "launches": len(ts), "ms": avg, "stream_bytes": b,
+                           "gbs": b / (avg * 1e-3) / 1e9 if avg > 0 else None,
+                           "frac": b / (avg * 1e-3) / 1e9 / peak if avg > 0 else None})
+    eval_bytes = nq * (12 + 4) + 4 * ncoef          # coordinates in, results out, coefficients once
+    pre_bytes = 2 * 4 * ncoef * 3                   # one read + one write per axis pass
+    if rank != 0 or not stages.get("prefilter_axis0_contiguous"):
+        # ranks other than 0 do not prefilter inside the step: time it once here for the report
+        work = torch.empty(ncoef, dtype=torch.float32, device=dev).normal_()
+        L.b200itp_profile_enable(1)
+        for _ in range(5):
+            m.prefilter_(work, (N_GRID,) * 3, (it,) * 3, local_rank)
+        torch.cuda.synchronize()
+        L.b200itp_profile_enable(0)
+        st2 = m._lib.profile_stages()
+        pre_ms = float(sum(np.mean(v) for k, v in st2.items() if k.startswith("prefilter_axis")))
+    roof = {"bound": "hbm", "kernel": "ordered evaluation: all launches of one b200itp_eval_sorted call "
+                                      "(count, scan, split1, split2, eval, unsortA, unsortB, place)",
             "achieved": eval_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-            "frac": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": None,
-            "algorithmic_bytes": eval_bytes, "ms": eval_ms}
+            "frac": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC_PER_QUERY * nq + 4 * ncoef,
+            "traffic_source": "profiles/: ncu dram__bytes_read+write per launch, summed over the call, scaled per query",
+            "algorithmic_bytes": eval_bytes, "ms": eval_ms, "stages": stage_rows}
     roof_pre = {"bound": "hbm", "kernel": "prefilter (3 axis passes, 512^3 f32)",
                 "achieved": pre_bytes / (pre_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": pre_bytes / (pre_ms * 1e-3) / 1e9 / 8000,

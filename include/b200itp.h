@@ -148,6 +148,14 @@ B200ITP_API size_t b200itp_last_error(char *buf, size_t buflen);
 /* number of kernel launches issued by this process so far (bench.py's gpu_launches) */
 B200ITP_API uint64_t b200itp_launch_count(void);
 
+/* Per-stage timing for bench.py's roofline: when enabled, every kernel launch of the library is
+ * bracketed by CUDA events on the caller's stream.  enable(1) clears the record list and starts,
+ * enable(0) stops (records stay readable).  get(i) synchronises on record i and returns its name
+ * (kernel / stage) and duration in milliseconds. */
+B200ITP_API int b200itp_profile_enable(int on);
+B200ITP_API int b200itp_profile_count(void);
+B200ITP_API int b200itp_profile_get(int i, char *name, size_t namelen, double *ms);
+
 /* ---- device memory helpers for hosts without their own CUDA binding ---------- */
 B200ITP_API int b200itp_malloc(int dev, size_t bytes, void **out);
 B200ITP_API int b200itp_free(int dev, void *p);

@@ -10,7 +10,7 @@ from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
                    bounds, evaluate_debug, evaluate_sorted, extrapolate, gradient, interpolate, lbounds, out_dtype,
                    prefilter_, scale, ubounds, value_and_gradient)
-from . import _lib
+from . import _lib, parallel
 
 __all__ = [
     "BSpline", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",

@@ -84,6 +84,9 @@ def lib() -> C.CDLL:
         "b200itp_version": (C.c_int, []),
         "b200itp_last_error": (sz, [C.c_char_p, sz]),
         "b200itp_launch_count": (C.c_uint64, []),
+        "b200itp_profile_enable": (C.c_int, [i32]),
+        "b200itp_profile_count": (C.c_int, []),
+        "b200itp_profile_get": (C.c_int, [i32, C.c_char_p, sz, C.POINTER(C.c_double)]),
         "b200itp_malloc": (C.c_int, [i32, sz, C.POINTER(vp)]),
         "b200itp_free": (C.c_int, [i32, vp]),
         "b200itp_memcpy_h2d": (C.c_int, [i32, vp, vp, sz, vp]),
@@ -109,7 +112,8 @@ def lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "b200itp_version", "b200itp_last_error", "b200itp_launch_count", "b200itp_malloc", "b200itp_free",
+    "b200itp_version", "b200itp_last_error", "b200itp_launch_count", "b200itp_profile_enable",
+    "b200itp_profile_count", "b200itp_profile_get", "b200itp_malloc", "b200itp_free",
     "b200itp_memcpy_h2d", "b200itp_memcpy_d2h", "b200itp_sync", "b200itp_copy_with_padding",
     "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_eval",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted",
@@ -131,3 +135,15 @@ def check(rc: int, what: str):
     if rc > 0:
         raise ValueError(f"{what}: unsupported or invalid argument (code {rc}): {msg}")
     raise B200ItpError(f"{what}: CUDA error (code {rc}): {msg}")
+
+
+def profile_stages():
+    """Per-stage device times recorded since b200itp_profile_enable(1): {name: [ms, ...]} in launch order."""
+    L = lib()
+    out = {}
+    buf = C.create_string_buffer(96)
+    ms = C.c_double(0.0)
+    for i in range(L.b200itp_profile_count()):
+        check(L.b200itp_profile_get(i, buf, 96, C.byref(ms)), "b200itp_profile_get")
+        out.setdefault(buf.value.decode(), []).append(ms.value)
+    return out

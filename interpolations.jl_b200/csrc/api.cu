@@ -4,6 +4,8 @@
 
 #include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace b200itp {
 
@@ -51,9 +53,80 @@ int scratch_get(int dev, int slot, size_t bytes, void **out) {
   return 0;
 }
 
+// ---- per-stage timing
+namespace {
+struct StageRec {
+  std::string name;
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+std::mutex g_prof_mu;
+std::atomic<bool> g_prof_on{false};
+std::vector<StageRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+bool stage_timing_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void stage_begin(const char *name, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  StageRec r;
+  r.name = name;
+  r.a = prof_event();
+  r.b = prof_event();
+  if (r.a) cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+}
+void stage_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_recs.empty() && g_prof_recs.back().b) cudaEventRecord(g_prof_recs.back().b, st);
+}
+
 }  // namespace b200itp
 
 using namespace b200itp;
+
+extern "C" int b200itp_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (on) {  // a new recording starts: recycle the events of the previous one
+    for (auto &r : g_prof_recs) {
+      if (r.a) g_prof_pool.push_back(r.a);
+      if (r.b) g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+  }
+  g_prof_on.store(on != 0);
+  return 0;
+}
+
+extern "C" int b200itp_profile_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return (int)g_prof_recs.size();
+}
+
+extern "C" int b200itp_profile_get(int i, char *name, size_t namelen, double *ms) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (i < 0 || i >= (int)g_prof_recs.size() || !ms) B200_FAIL(B200ITP_E_BADARG, "profile_get: bad index");
+  const StageRec &r = g_prof_recs[i];
+  B200_CUDA_OK(cudaEventSynchronize(r.b));
+  float t = 0.f;
+  B200_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+  *ms = t;
+  if (name && namelen) {
+    const size_t c = r.name.size() < namelen - 1 ? r.name.size() : namelen - 1;
+    memcpy(name, r.name.data(), c);
+    name[c] = 0;
+  }
+  return 0;
+}
 
 extern "C" int b200itp_version(void) { return B200ITP_VERSION; }
 

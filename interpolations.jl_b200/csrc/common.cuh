@@ -55,6 +55,21 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
+// ---- optional per-stage timing (b200itp_profile_*): CUDA events around each launch on the caller's stream
+bool stage_timing_enabled();
+void stage_begin(const char *name, cudaStream_t st);
+void stage_end(cudaStream_t st);
+struct StageScope {
+  cudaStream_t st;
+  bool on;
+  StageScope(const char *name, cudaStream_t s) : st(s), on(stage_timing_enabled()) {
+    if (on) stage_begin(name, st);
+  }
+  ~StageScope() {
+    if (on) stage_end(st);
+  }
+};
+
 // per-device grow-only scratch buffer (guarded by a mutex; see api.cu)
 int scratch_get(int dev, int slot, size_t bytes, void **out);
 

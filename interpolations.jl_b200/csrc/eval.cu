@@ -145,6 +145,7 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
+  StageScope sc(mode == 0 ? "eval_direct_value" : "eval_direct_gradient", st);
   int rc;
   if (cf32 && xf32 && wf32)
     rc = launch_eval_combo<float, float, float>(P, deg, mode, blocks, st);

@@ -849,24 +849,46 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
 
   B200_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)(G.nfinal + 1) * 4, st));
   const int cblocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sms * 16);
-  ord_count_kernel<N, DEG><<<cblocks, 256, 0, st>>>(P, G, hist);
-  scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums);
-  scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)nsb);
-  scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums, start);
-  ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, pl);
+  {
+    StageScope sc("ord_count", st);
+    ord_count_kernel<N, DEG><<<cblocks, 256, 0, st>>>(P, G, hist);
+  }
+  {
+    StageScope sc("ord_scan_plan", st);
+    scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)nsb);
+    scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums, start);
+    ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, pl);
+  }
   const int sblocks = sms * 2;
-  ord_split1_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
-  ord_split2_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
-  ord_eval_kernel<N, DEG><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
+  {
+    StageScope sc("ord_split1", st);
+    ord_split1_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+  }
+  {
+    StageScope sc("ord_split2", st);
+    ord_split2_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
+  }
+  {
+    StageScope sc("ord_eval", st);
+    ord_eval_kernel<N, DEG><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
+  }
   const uint2 *last = res;
   if (P.nq > (1LL << kShiftA)) {
+    StageScope sc("ord_unsortA", st);
     ord_unsort_kernel<0><<<sblocks, kSplitThreads, smem8, st>>>(res, P.nq, pl.cursorA, resA);
     count_launch();
     last = resA;
   }
-  ord_unsort_kernel<1><<<sblocks, kSplitThreads, smem8, st>>>(last, P.nq, pl.cursorB, resB);
+  {
+    StageScope sc("ord_unsortB", st);
+    ord_unsort_kernel<1><<<sblocks, kSplitThreads, smem8, st>>>(last, P.nq, pl.cursorB, resB);
+  }
   const long long nwin = (P.nq + (1LL << kShiftB) - 1) >> kShiftB;
-  ord_place_kernel<<<(unsigned)nwin, 1024, (4 << kShiftB), st>>>(resB, P.nq, reinterpret_cast<float *>(P.out_value));
+  {
+    StageScope sc("ord_place", st);
+    ord_place_kernel<<<(unsigned)nwin, 1024, (4 << kShiftB), st>>>(resB, P.nq, reinterpret_cast<float *>(P.out_value));
+  }
   count_launch(10);
   B200_CUDA_OK(cudaGetLastError());
   *done = true;

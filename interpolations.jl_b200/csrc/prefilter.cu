@@ -600,6 +600,7 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
     B200_CUDA_OK(cudaGetLastError());
     return 0;
   }
+  StageScope sc(axis == 0 ? "prefilter_axis0_contiguous" : (axis == 1 ? "prefilter_axis1_strided" : "prefilter_axis2+_strided"), st);
   if (axis == 0) {
     using Cfg = ContigCfg<T>;
     const int64_t nitems = lines * nseg;
@@ -858,6 +859,7 @@ extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, in
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count(dev) * 16);
+  StageScope sc("copy_with_padding", st);
   if (dtype == B200ITP_F32)
     pad_copy_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)src, (float *)dst, ndims, ds[0], ds[1],
                                                               ds[2], ds[3], ps[0], ps[1], ps[2], ps[3], total);

@@ -1,0 +1,169 @@
+"""Multi-GPU use of the hot path on one 8xB200 box: one process per GPU, `torch.distributed` (NCCL over
+NVLink / NVSwitch) for the plumbing, the CUDA library for every flop (BASELINE.json north_star).
+
+* Evaluation shards: queries are independent, so each rank evaluates a contiguous chunk of the query arrays
+  (`shard_bounds`, `shard_queries`) against its own replica of the coefficient array; the replica comes from
+  one broadcast (`broadcast_interpolant`) or from the all-gather that ends `interpolate_sharded`.  There is no
+  collective on the evaluation data path.
+* Large 3-D prefilters shard: every rank owns a z-slab of the (padded) array.  The passes along x and y are
+  local; one all-to-all re-shards the array along y so that the pass along z is local too
+  (`prefilter_sharded`); `allgather_coefficients` then replicates the result for evaluation.
+* Small arrays (C1, C2, C4 of BASELINE.json): replicas only — run `interpolate` on every rank.
+
+Array convention: a Julia array of size (n1, n2, n3), column-major, is held as a C-contiguous torch tensor of
+shape (n3, n2, n1); a z-slab is a chunk of the leading torch dimension and is contiguous in memory.
+
+The axis solves go through `solve(t, julia_size, its)`, by default the CUDA library (`core.prefilter_`, which
+raises if libb200itp.so is missing).  The CPU tests (gloo, world_size 2) inject a host solver of their own to
+check the data movement; the product never does.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import core
+from .flags import BSpline, Linear, needs_padding
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, order-preserving split of range(n) into `world` chunks whose sizes differ by at most one."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_queries(xs: Sequence, world: int, rank: int):
+    """The rank's chunk of every coordinate array (1-D, equal lengths): `itp.(xs...)` over the full arrays is the
+    concatenation of the per-rank results in rank order."""
+    n = len(xs[0])
+    lo, hi = shard_bounds(n, world, rank)
+    return [x[lo:hi] for x in xs]
+
+
+def _world(group):
+    dist = _dist()
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, device=None, group=None):
+    """Replicate `itp` (held by rank `src`) on every rank: metadata by object broadcast, the coefficient array by one
+    `broadcast` (NCCL: 512 MiB cross NVLink once)."""
+    torch, dist = _torch(), _dist()
+    world, rank = _world(group)
+    meta = [None]
+    if rank == src:
+        meta = [(tuple(itp.size), tuple(itp.parent_len), itp.its, str(itp.coefs.dtype))]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    size, parent_len, its, dtype = meta[0]
+    tdtype = torch.float32 if dtype.endswith("float32") else torch.float64
+    if rank == src:
+        coefs = itp.coefs
+    else:
+        dev = torch.device("cuda", core._device_index(device)) if device is not None else torch.device("cpu")
+        coefs = torch.empty(int(np.prod(size)), dtype=tdtype, device=dev)
+    dist.broadcast(coefs, src=src, group=group)
+    if rank == src:
+        return itp
+    dev_index = coefs.device.index if coefs.device.type == "cuda" else None
+    return core.BSplineInterpolation(coefs, size, parent_len, its, dev_index)
+
+
+def _cuda_solver(device_index: int) -> Callable:
+    def solve(t, julia_size, its):
+        core.prefilter_(t.view(-1), tuple(julia_size), its, device_index)  # raises without the CUDA library
+    return solve
+
+
+def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
+    """Slab-sharded `interpolate(A, it)` for a 3-D array.
+
+    `A_slab`: this rank's z-slab of the samples, torch tensor of shape (nz_local, ny, nx) (z-planes
+    `shard_bounds(nz, world, rank)` of the full array), on the rank's GPU.
+    Returns `(coefs_yshard, meta)`: the rank's y-shard of the padded coefficient array, shape (pz, py_local, px),
+    and the metadata `allgather_coefficients` needs.  Pass order and systems are the reference's
+    (prefiltering.jl:49-59): x, then y, then z.
+    """
+    torch, dist = _torch(), _dist()
+    world, rank = _world(group)
+    if A_slab.dim() != 3:
+        raise ValueError("prefilter_sharded: 3-D arrays only (smaller problems: replicas, SURVEY §8e)")
+    its = core._its_tuple(it, 3)
+    pad = [1 if needs_padding(i) else 0 for i in its]
+    nzl, ny, nx = (int(s) for s in A_slab.shape)
+    counts = [None] * world
+    dist.all_gather_object(counts, nzl, group=group)
+    nz = int(sum(counts))
+    px, py, pz = nx + 2 * pad[0], ny + 2 * pad[1], nz + 2 * pad[2]
+    if solve is None:
+        if A_slab.device.type != "cuda":
+            raise RuntimeError("prefilter_sharded: the product path needs CUDA tensors (there is no CPU fallback)")
+        solve = _cuda_solver(A_slab.device.index)
+    skip = BSpline(Linear())
+
+    # ---- local padded slab: copy_with_padding (prefiltering.jl:17-28); the zero z-planes belong to the end ranks
+    lead = pad[2] if rank == 0 else 0
+    trail = pad[2] if rank == world - 1 else 0
+    pzl = nzl + lead + trail
+    slab = torch.zeros((pzl, py, px), dtype=A_slab.dtype, device=A_slab.device)
+    slab[lead:lead + nzl, pad[1]:pad[1] + ny, pad[0]:pad[0] + nx] = A_slab
+    pz_counts = [c + (pad[2] if r == 0 else 0) + (pad[2] if r == world - 1 else 0) for r, c in enumerate(counts)]
+
+    # ---- passes along x and y: local
+    if pzl > 0:
+        solve(slab, (px, py, pzl), (its[0], skip, skip))
+        solve(slab, (px, py, pzl), (skip, its[1], skip))
+
+    # ---- one all-to-all: z-slabs -> y-slabs
+    ybounds = [shard_bounds(py, world, r) for r in range(world)]
+    send = torch.cat([slab[:, lo:hi, :].reshape(-1) for lo, hi in ybounds]) if pzl > 0 else slab.reshape(-1)
+    in_splits = [pzl * (hi - lo) * px for lo, hi in ybounds]
+    ylo, yhi = ybounds[rank]
+    pyl = yhi - ylo
+    out_splits = [pz_counts[r] * pyl * px for r in range(world)]
+    recv = torch.empty(int(sum(out_splits)), dtype=slab.dtype, device=slab.device)
+    dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+    yshard = recv.view(pz, pyl, px)  # blocks arrive in rank order == z order
+
+    # ---- pass along z: local
+    if pyl > 0:
+        solve(yshard, (px, pyl, pz), (skip, skip, its[2]))
+    meta = {"size": (px, py, pz), "parent_len": (nx, ny, nz), "its": its, "ybounds": ybounds}
+    return yshard, meta
+
+
+def allgather_coefficients(yshard, meta, group=None):
+    """Replicate the y-sharded coefficient array on every rank (one broadcast per shard: uneven shards are fine on
+    both NCCL and gloo).  Returns the flat column-major coefficient tensor."""
+    torch, dist = _torch(), _dist()
+    world, rank = _world(group)
+    px, py, pz = meta["size"]
+    full = torch.empty((pz, py, px), dtype=yshard.dtype, device=yshard.device)
+    for r, (lo, hi) in enumerate(meta["ybounds"]):
+        if hi == lo:
+            continue
+        block = yshard.contiguous() if r == rank else torch.empty((pz, hi - lo, px), dtype=yshard.dtype,
+                                                                   device=yshard.device)
+        dist.broadcast(block, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        full[:, lo:hi, :] = block
+    return full.view(-1)
+
+
+def interpolate_sharded(A_slab, it, group=None, solve: Optional[Callable] = None) -> core.BSplineInterpolation:
+    """`interpolate(A, it)` with the prefilter sharded over the ranks of `group`; every rank returns the same
+    (replicated) interpolant, ready for query-sharded evaluation."""
+    yshard, meta = prefilter_sharded(A_slab, it, group=group, solve=solve)
+    coefs = allgather_coefficients(yshard, meta, group=group)
+    dev_index = coefs.device.index if coefs.device.type == "cuda" else None
+    return core.BSplineInterpolation(coefs, meta["size"], meta["parent_len"], meta["its"], dev_index)

@@ -402,3 +402,30 @@ def test_ordered_evaluation_is_bit_identical(pkg, shape):
     itp = m.interpolate(A.astype(np.float64), m.BSpline(m.Linear()))
     q = [rng.uniform(1, s, 1000) for s in shape]
     assert np.array_equal(itp(*q).cpu().numpy(), m.evaluate_sorted(itp, *q).cpu().numpy())
+
+
+def test_sharded_single_rank(pkg):
+    """parallel.interpolate_sharded with the CUDA library as the axis solver (world_size 1, gloo on CUDA tensors is
+    avoided: NCCL): x/y passes on the slab, all-to-all, z pass, all-gather — equals the single-call interpolate."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from interpolations_jl_b200 import parallel as par
+    m = pkg
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rng = np.random.default_rng(5)
+        for it in (m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Cubic(m.Line(m.OnGrid()))),
+                   m.BSpline(m.Quadratic(m.Reflect(m.OnCell())))):
+            A = rng.standard_normal((150, 140, 136)).astype(np.float32)  # Julia shape (nx, ny, nz)
+            slab = torch.from_numpy(np.ascontiguousarray(A.transpose(2, 1, 0))).cuda()
+            itp_s = par.interpolate_sharded(slab, it)
+            itp_1 = m.interpolate(A, it)
+            assert itp_s.size == itp_1.size
+            assert torch.equal(itp_s.coefs, itp_1.coefs), it
+            q = [rng.uniform(1, s, 1000).astype(np.float32) for s in A.shape]
+            assert torch.equal(itp_s(*q), itp_1(*q))
+    finally:
+        dist.destroy_process_group()
