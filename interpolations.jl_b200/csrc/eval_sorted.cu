@@ -67,8 +67,8 @@ constexpr int kChunk8 = 8192;       // 8-byte records
 constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
 constexpr int kShiftA = 23;         // unsort level A bins of 2^23 results (512 windows each)
 constexpr int kEvalThreads = 768;
-constexpr int kRows = 96;           // records per class per staging round (4 rows per warp)
-constexpr int kRowPitch = kRows + 1;
+constexpr int kRB = 8;              // rows (records per class) a warp stages and evaluates at a time
+constexpr int kRBP = kRB + 1;       // pitch in records: lane c reads slot c * 9 + r -> conflict-free 128-bit accesses
 constexpr int kItemTarget = 32768;  // records per evaluation work item
 
 struct OrdGeom {
@@ -540,7 +540,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 template <int N, int DEG>
 struct EvalSmem {
   float tile[TileCfg<N, DEG>::FLOATS];
-  float4 stage[2][kClasses][kRowPitch];
+  float4 wstage[kEvalThreads / 32][kClasses * kRBP];  // per-warp staging: kRB rows of every class
   long long axoff[3][TileCfg<N, DEG>::MAXT];  // element offset of tile coordinate l on each axis, -1: outside
   unsigned cbeg[kClasses];  // first record of the item's share of each class stream
   unsigned ccnt[kClasses];
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
 #endif
 
   for (unsigned item = it_lo; item < it_hi; ++item) {
-    __syncthreads();  // previous item fully consumed (stage buffers, cbeg/ccnt)
+    __syncthreads();  // previous item fully consumed (cbeg/ccnt, tile)
     if (tid == 0) {
       int lo = 0, hi = G.nbricks - 1;  // last brick with item_start <= item (skips empty bricks)
       while (lo < hi) {
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
       }
     }
     __syncthreads();
-    const int rounds = (sm.max_cnt + kRows - 1) / kRows;
+    const int rounds = (sm.max_cnt + kRB - 1) / kRB;
 #ifdef B200ITP_EVAL_TRACE
     if (tid == 0) {
       for (int c = 0; c < kClasses; ++c) n_rec += sm.ccnt[c];
@@ -667,44 +667,27 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     }
 #endif
 
-    // warp w stages and drains classes w, w + NW: no other warp touches those rows of the stage buffers
-    auto issue = [&](int rd) {
-      if (rd < rounds) {
+    // Every warp streams its own blocks of kRB rows (row r of class c = record cbeg[c] + r): it stages the 32 x kRB
+    // records in its private buffer (lanes cover 4 classes x 8 consecutive records = four 128-byte segments per
+    // instruction), evaluates them with lane c on class c, and stores the {q, value} results with the same mapping.
+    // Only __syncwarp() is needed: no CTA-wide barrier inside an item.
+    float4 *wst = sm.wstage[warp];
+    const unsigned mycnt = sm.ccnt[lane];
+    const int nblk = (sm.max_cnt + kRB - 1) / kRB;
+    for (int blk = warp; blk < nblk; blk += NW) {
+      const unsigned r0 = (unsigned)blk * kRB;
 #pragma unroll
-        for (int c = warp; c < kClasses; c += NW) {
-          const unsigned cnt = sm.ccnt[c];
-          const unsigned r0 = (unsigned)rd * kRows;
-#pragma unroll
-          for (int i = lane; i < kRows; i += 32)
-            if (r0 + i < cnt) cp_async16(&sm.stage[rd & 1][c][i], rec + sm.cbeg[c] + r0 + i);
-        }
+      for (int j = 0; j < kClasses / 4; ++j) {
+        const int c = 4 * j + (lane >> 3), r = lane & 7;
+        if (r0 + r < sm.ccnt[c]) cp_async16(&wst[c * kRBP + r], rec + sm.cbeg[c] + r0 + r);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto drain = [&](int rd) {  // results of round rd: {q, value} in the first 8 bytes of every record slot
-#pragma unroll
-      for (int c = warp; c < kClasses; c += NW) {
-        const unsigned cnt = sm.ccnt[c];
-        const unsigned r0 = (unsigned)rd * kRows;
-#pragma unroll
-        for (int i = lane; i < kRows; i += 32)
-          if (r0 + i < cnt) {
-            const float4 v = sm.stage[rd & 1][c][i];
-            res[sm.cbeg[c] + r0 + i] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
-          }
-      }
-    };
-
-    issue(0);
-    for (int rd = 0; rd < rounds; ++rd) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();  // round rd landed; round rd-1 computed by every warp
-      if (rd > 0) drain(rd - 1);
-      issue(rd + 1);    // refills the buffer just drained (same warp, same rows)
-      const unsigned mycnt = sm.ccnt[lane];
-      for (int i = warp; i < kRows; i += NW) {
-        if ((unsigned)rd * kRows + i < mycnt) {
-          const float4 q4 = sm.stage[rd & 1][lane][i];
+      __syncwarp();
+#pragma unroll 1
+      for (int r = 0; r < kRB; ++r) {
+        if (r0 + r < mycnt) {
+          const float4 q4 = wst[lane * kRBP + r];
           const float x[3] = {q4.x, q4.y, q4.z};
           AxisTaps<DEG, float> ax[N];
           int lpos[3] = {0, 0, 0};
@@ -738,13 +721,20 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
             const float t0 = ax[0].wv[k0] * v0;
             val = k0 == 0 ? t0 : t0 + val;
           }
-          sm.stage[rd & 1][lane][i] = make_float4(q4.w, val, 0.f, 0.f);
+          *reinterpret_cast<float2 *>(&wst[lane * kRBP + r]) = make_float2(q4.w, val);
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kClasses / 4; ++j) {
+        const int c = 4 * j + (lane >> 3), r = lane & 7;
+        if (r0 + r < sm.ccnt[c]) {
+          const float2 v = *reinterpret_cast<const float2 *>(&wst[c * kRBP + r]);
+          res[sm.cbeg[c] + r0 + r] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    if (rounds > 0) drain(rounds - 1);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 #ifdef B200ITP_EVAL_TRACE
   if (tid == 0) {
