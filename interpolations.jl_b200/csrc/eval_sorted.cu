@@ -62,6 +62,15 @@ constexpr int kClasses = 32;        // bank classes == lanes
 constexpr int kGroupBricks = 16;    // bricks per split-1 group: split 2 has 16 * 32 = 512 bins
 constexpr int kMaxBins = 512;       // bins per multisplit level (== threads of the split kernels)
 constexpr int kSplitThreads = 512;
+#ifndef ORD_PREFETCH
+#define ORD_PREFETCH 1  // fetch the next chunk into registers while the current one goes through shared memory
+#endif
+#ifndef ORD_DBUF
+#define ORD_DBUF 0      // double-buffer the sorted chunk: stores of chunk i-1 overlap the reservation of chunk i
+#endif
+constexpr bool kPrefetch = ORD_PREFETCH != 0;
+constexpr int kSplitBufs = ORD_DBUF ? 2 : 1;
+constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_DBUF) ? 1 : 2;
 constexpr int kChunk16 = 4096;      // records per multisplit chunk, 16-byte records
 constexpr int kChunk8 = 8192;       // 8-byte records
 constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
@@ -126,15 +135,29 @@ __device__ __forceinline__ void load_query(const EvalParams &P, long long q, flo
 template <int N, int DEG>
 __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
                                                         unsigned *__restrict__ hist) {
+  constexpr int U = 4;  // queries per thread per iteration: their loads are in flight together
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P.nq; q += stride) {
-    float x[3];
-    bool valid;
-    load_query<N>(P, q, x, valid);
-    if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
-    int brick, cls;
-    locate<N, DEG>(P, G, x, brick, cls);
-    atomicAdd(hist + (brick * kClasses + cls), 1u);  // result unused: compiles to RED
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < P.nq; q0 += U * stride) {
+    float x[U][3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        x[u][d] = (d < N && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < P.nq) {
+        bool valid;
+        check_query<N>(P, x[u], valid);
+        if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
+        int brick, cls;
+        locate<N, DEG>(P, G, x[u], brick, cls);
+        atomicAdd(hist + (brick * kClasses + cls), 1u);  // result unused: compiles to RED
+      }
+    }
   }
 }
 
@@ -296,16 +319,29 @@ __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restri
 // runs.  key == 0xffffffff marks an absent record.
 template <typename Rec, int S>
 struct SplitSmem {
-  Rec rec[S];
-  unsigned short bin[S];
+  Rec rec[kSplitBufs][S];     // records of the current (/ the previous) chunk in bin order
+  unsigned short bin[kSplitBufs][S];
+  unsigned gbase[kSplitBufs][kMaxBins];
   unsigned hist[kMaxBins];
   unsigned start[kMaxBins];
-  unsigned gbase[kMaxBins];
   unsigned wtot[32];
 };
 
+struct SplitState {
+  int p = 0;             // buffer of the next chunk
+  unsigned pending = 0;  // records of the previous chunk still to be stored (buffer p ^ 1)
+};
+
+// stores of the previous chunk: whole runs, consecutive threads on consecutive records
 template <typename Rec, int S>
-__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r)[S / kSplitThreads],
+__device__ __forceinline__ void split_flush(SplitSmem<Rec, S> &sm, SplitState &stt, Rec *__restrict__ out) {
+  const int b = kSplitBufs == 2 ? (stt.p ^ 1) : 0;
+  for (unsigned i = threadIdx.x; i < stt.pending; i += kSplitThreads) out[sm.gbase[b][sm.bin[b][i]] + i] = sm.rec[b][i];
+  stt.pending = 0;
+}
+
+template <typename Rec, int S>
+__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &stt, const Rec (&r)[S / kSplitThreads],
                                             const unsigned (&key)[S / kSplitThreads], int nbins, unsigned cnt,
                                             unsigned *__restrict__ cursor, Rec *__restrict__ out) {
   // sm.hist is all zero on entry (zeroed by split_init / by the previous call right after it was read)
@@ -316,7 +352,7 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
     if (key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
-  __syncthreads();  // (1) histogram complete; the previous chunk's copy-out has finished in every warp
+  __syncthreads();  // (1) histogram complete
   // exclusive scan of the counters, one per thread: warp scan, then every warp scans the NW warp totals itself
   const unsigned v = t < nbins ? sm.hist[t] : 0u;
   sm.hist[t] = 0;  // ready for the next chunk (its atomics come after barrier (3))
@@ -337,21 +373,29 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
   const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
   const unsigned st = wbase + inc - v;
   sm.start[t] = st;
-  // the reservation's round trip to the L2 overlaps the shared-memory scatter below
+  // the bin reservation's round trip to the L2 overlaps the stores of the previous chunk (double-buffered build)
+  // or the shared-memory scatter of this one; the empty asm keeps the compiler from waiting for it earlier
   unsigned gb = 0;
-  if (v) gb = atomicAdd(cursor + t, v) - st;
-  __syncthreads();  // (3) start[] visible
+  if (v) gb = atomicAdd(cursor + t, v);
+  if (kSplitBufs == 2) split_flush(sm, stt, out);
+  __syncthreads();  // (3) start[] visible; the buffer may be overwritten
+  const int p = kSplitBufs == 2 ? stt.p : 0;
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
     if (key[j] != 0xffffffffu) {
       const unsigned slot = sm.start[key[j]] + rank[j];
-      sm.rec[slot] = r[j];
-      sm.bin[slot] = (unsigned short)key[j];
+      sm.rec[p][slot] = r[j];
+      sm.bin[p][slot] = (unsigned short)key[j];
     }
-  sm.gbase[t] = gb;
+  asm volatile("" : "+r"(gb));
+  sm.gbase[p][t] = gb - st;
   __syncthreads();  // (4) records in bin order
-  for (unsigned i = t; i < cnt; i += kSplitThreads) out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
-  // no barrier here: the next call touches only hist[] before its barrier (1)
+  stt.pending = cnt;
+  if (kSplitBufs == 2) {
+    stt.p = p ^ 1;
+  } else {
+    split_flush(sm, stt, out);  // no barrier after it: the next call touches only hist[] before its barrier (1)
+  }
 }
 
 template <typename Rec, int S>
@@ -362,12 +406,13 @@ __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
 
 // split 1: coordinates -> {x,y,z,q} records grouped by brick group
 template <int N, int DEG>
-__global__ void __launch_bounds__(kSplitThreads) ord_split1_kernel(const __grid_constant__ EvalParams P,
+__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G, unsigned *__restrict__ cursor1,
                                                                    float4 *__restrict__ rec1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
+  SplitState stt;
   constexpr int RPT = kChunk16 / kSplitThreads;
   const long long nchunks = (P.nq + kChunk16 - 1) / kChunk16;
   // the coordinates of the next chunk are fetched before the current chunk goes through shared memory
@@ -381,8 +426,9 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split1_kernel(const __grid_
         nx[j][d] = (d < N && ch < nchunks && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
     }
   };
-  fetch(blockIdx.x);
+  if (kPrefetch) fetch(blockIdx.x);
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (!kPrefetch) fetch(ch);
     const long long base = ch * kChunk16;
     const unsigned cnt = (unsigned)min((long long)kChunk16, P.nq - base);
     float4 r[RPT];
@@ -401,14 +447,15 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split1_kernel(const __grid_
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float((unsigned)q));
       }
     }
-    fetch(ch + gridDim.x);
-    block_split<float4, kChunk16>(sm, r, key, G.ngroups, cnt, cursor1, rec1);
+    if (kPrefetch) fetch(ch + gridDim.x);
+    block_split<float4, kChunk16>(sm, stt, r, key, G.ngroups, cnt, cursor1, rec1);
   }
+  split_flush(sm, stt, rec1);
 }
 
 // split 2: records of one group -> (brick, class) streams
 template <int N, int DEG>
-__global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_constant__ EvalParams P,
+__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split2_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G,
                                                                    const unsigned *__restrict__ start,
                                                                    const unsigned *__restrict__ chunk_start,
@@ -418,6 +465,7 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
+  SplitState stt;
   __shared__ unsigned s_chunk[kMaxBins + 1];
   constexpr int RPT = kChunk16 / kSplitThreads;
   for (int i = threadIdx.x; i <= G.ngroups; i += kSplitThreads) s_chunk[i] = chunk_start[i];
@@ -450,8 +498,9 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_
       if (i < ncnt) nr[j] = rec1[nbase + i];
     }
   };
-  fetch(blockIdx.x);
+  if (kPrefetch) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (!kPrefetch) fetch(ch);
     g = ng; base = nbase; cnt = ncnt; fa = nfa; fb = nfb;
     float4 r[RPT];
     unsigned key[RPT];
@@ -467,19 +516,21 @@ __global__ void __launch_bounds__(kSplitThreads) ord_split2_kernel(const __grid_
         key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
       }
     }
-    fetch(ch + gridDim.x);
-    block_split<float4, kChunk16>(sm, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
+    if (kPrefetch) fetch(ch + gridDim.x);
+    block_split<float4, kChunk16>(sm, stt, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
   }
+  split_flush(sm, stt, rec2);
 }
 
 // unsort: {q, value} records by (q >> shift) relative to the chunk's parent bin
 template <int LEVEL>
-__global__ void __launch_bounds__(kSplitThreads) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq,
+__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq,
                                                                    unsigned *__restrict__ cursor,
                                                                    uint2 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<uint2, kChunk8> *>(smem_raw);
   split_init(sm);
+  SplitState stt;
   constexpr int RPT = kChunk8 / kSplitThreads;
   const long long nchunks = (nq + kChunk8 - 1) / kChunk8;
   uint2 nr[RPT];
@@ -490,8 +541,9 @@ __global__ void __launch_bounds__(kSplitThreads) ord_unsort_kernel(const uint2 *
       if (ch < nchunks && i < nq) nr[j] = in[i];
     }
   };
-  fetch(blockIdx.x);
+  if (kPrefetch) fetch(blockIdx.x);
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (!kPrefetch) fetch(ch);
     const long long base = ch * kChunk8;
     const unsigned cnt = (unsigned)min((long long)kChunk8, nq - base);
     // level A: bins over the whole array; level B: the chunk lies inside one level-A bin (2^kShiftA records)
@@ -510,9 +562,10 @@ __global__ void __launch_bounds__(kSplitThreads) ord_unsort_kernel(const uint2 *
         key[j] = LEVEL == 0 ? (r[j].x >> kShiftA) : ((r[j].x >> kShiftB) - bin0);
       }
     }
-    fetch(ch + gridDim.x);
-    block_split<uint2, kChunk8>(sm, r, key, nbins, cnt, cursor + bin0, out);
+    if (kPrefetch) fetch(ch + gridDim.x);
+    block_split<uint2, kChunk8>(sm, stt, r, key, nbins, cnt, cursor + bin0, out);
   }
+  split_flush(sm, stt, out);
 }
 
 // place: window w holds exactly the results q in [w * 2^kShiftB, ...): permute in shared memory
