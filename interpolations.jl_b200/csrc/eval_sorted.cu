@@ -941,13 +941,17 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
 // Query count from which the ordered pipeline is used (tests lower it to exercise the pipeline on
 // small inputs; results do not depend on it).
 static int64_t g_sorted_min_queries = 1 << 20;
+static long long g_sorted_min_coef_bytes = 128LL << 20;
 
 }  // namespace b200itp
 
 using namespace b200itp;
 
 extern "C" int64_t b200itp_eval_sorted_min_queries(void) { return g_sorted_min_queries; }
-extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) { g_sorted_min_queries = n < 1 ? 1 : n; }
+extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
+  g_sorted_min_queries = n < 1 ? 1 : n;
+  g_sorted_min_coef_bytes = n <= 1 ? 0 : (128LL << 20);  // n == 1 (tests): every supported call takes the ordered path
+}
 
 extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
   if (!d || nq <= 0) return 0;
@@ -972,8 +976,12 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
   rc = fill_eval_params_public(d, coefs, coords, nq, out_value, (unsigned long long *)flag, P, &deg, &plain);
   if (rc) return rc;
   bool done = false;
-  if (plain && nq >= g_sorted_min_queries && (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) &&
-      (d->ndims == 2 || d->ndims == 3)) {
+  // The ordered pipeline pays off when the coefficient array does not fit the L2 (measured: 4096^2 Float32, 64 MiB:
+  // direct 36 vs ordered 20 Gevals/s; 8192^2, 256 MiB: 20 vs 21; 512^3, 512 MiB: 2.1 vs 20).
+  long long coef_bytes = 4;
+  for (int i = 0; i < d->ndims && i < B200ITP_MAX_DIMS; ++i) coef_bytes *= d->size[i];
+  if (plain && nq >= g_sorted_min_queries && coef_bytes >= g_sorted_min_coef_bytes &&
+      (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) && (d->ndims == 2 || d->ndims == 3)) {
     B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
     // the scratch pointer is aligned up to 256 bytes inside the caller's buffer
     unsigned char *sp = reinterpret_cast<unsigned char *>(scratch);

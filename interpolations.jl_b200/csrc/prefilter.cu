@@ -209,8 +209,11 @@ __device__ __forceinline__ void pipeline_step(const AxisPlan<T> &p, int r0, int 
 // addresses in every row.  Rows [s, e] of the segment, s = 1 + seg*seglen (seglen multiple of B).
 // The loads of block b+1 are issued before block b is processed (register double buffering), so
 // every thread keeps B independent loads in flight while it runs the two recurrences.
+#ifndef PF_STRIDED_MINB
+#define PF_STRIDED_MINB 7  // 7 CTAs of 128 threads per SM: 2048 CTAs of the 512^3 passes fit in two full waves (measured best of 4..8)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(128) prefilter_strided_kernel(const T *src, T *dst,
+__global__ void __launch_bounds__(128, sizeof(T) == 4 ? PF_STRIDED_MINB : 1) prefilter_strided_kernel(const T *src, T *dst,
                                                                 const __grid_constant__ AxisPlan<T> p, int64_t R1,
                                                                 int nb1, int seglen, int nseg) {
   constexpr int B = Tune<T>::B;
@@ -322,7 +325,10 @@ struct ContigCfg {
   static constexpr int VPI = CH / EPV;
   static constexpr int PITCH = VPI + 1;
   static constexpr int VPB = B / EPV;
-  static constexpr int STAGES = 3;
+#ifndef PF_CONTIG_STAGES
+#define PF_CONTIG_STAGES 2  // 2 input stages: 55 KB per CTA, 4 CTAs per SM (measured best of 2..4)
+#endif
+  static constexpr int STAGES = PF_CONTIG_STAGES;
   static constexpr size_t smem_bytes = (size_t)(STAGES + 1) * ITEMS * PITCH * 16 + (size_t)ITEMS * 16;
 };
 
