@@ -312,6 +312,8 @@ def main():
     torch.cuda.synchronize()
 
     def step_e2e():
+        # host buffers in, host buffer out: H2D of the samples + prefilter on rank 0, broadcast, then the public
+        # host-buffer call (chunked: H2D / evaluation / D2H overlap on three streams)
         if rank == 0:
             Ad = host_A.to(dev, non_blocking=True)
             coefs = m.interpolate(Ad, it, device=dev).coefs
@@ -320,9 +322,7 @@ def main():
         if world > 1:
             dist.broadcast(coefs, src=0)
         itp2 = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
-        dc = [h.to(dev, non_blocking=True) for h in host_coords]  # nq_e queries per rank
-        r = m.evaluate_sorted(itp2, *dc) if args.sorted else itp2(*dc)
-        host_out.copy_(r, non_blocking=True)
+        m.evaluate_from_host(itp2, *host_coords, out=host_out, ordered=bool(args.sorted))
         torch.cuda.synchronize()
 
     for _ in range(2):

@@ -543,6 +543,77 @@ def evaluate_sorted(itp, *xs):
     return _broadcast_eval(itp, xs, want_value=True, want_grad=False, sorted_queries=True)[0]
 
 
+def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
+    """`itp.(xs...)` for coordinate arrays that live in (pinned) HOST memory: the queries are cut into chunks and the
+    host->device copy of chunk i+1, the evaluation of chunk i and the device->host copy of chunk i-1 run on three
+    CUDA streams, so the call is bound by the PCIe transfer of the coordinates instead of the sum of the three.
+    `host_xs`: N 1-D CPU torch tensors of one float dtype (pinned for asynchronous copies); `out`: optional pinned CPU
+    tensor for the results.  Returns the result tensor on the host (values identical to `itp(*xs)`)."""
+    torch = _torch()
+    N = itp.ndims
+    if len(host_xs) != N:
+        raise ValueError(f"expected {N} coordinate arguments, got {len(host_xs)}")
+    nq = int(host_xs[0].numel())
+    dt = host_xs[0].dtype
+    if any(x.dtype != dt or x.numel() != nq or x.device.type != "cpu" for x in host_xs):
+        raise ValueError("evaluate_from_host: N CPU tensors of equal length and dtype are required")
+    dev_index = itp.device_index
+    dev = torch.device("cuda", dev_index)
+    odt = torch.float32 if out_dtype(itp, np.float32 if dt == torch.float32 else np.float64) == np.float32 else torch.float64
+    if out is None:
+        out = torch.empty(nq, dtype=odt, pin_memory=True)
+    if out.numel() != nq or out.dtype != odt:
+        raise ValueError("evaluate_from_host: `out` has the wrong length or dtype")
+    if nq == 0:
+        return out
+    chunk = max(1, int(chunk))
+    nchunks = (nq + chunk - 1) // chunk
+    with torch.cuda.device(dev_index):
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in.wait_stream(main)
+        nbuf = min(3, nchunks)
+        bufs = [[torch.empty(min(chunk, nq), dtype=dt, device=dev) for _ in range(N)] for _ in range(nbuf)]
+        free_ev = [None] * nbuf   # buffer may be refilled once its evaluation has finished
+        results = [None] * nbuf
+        done_ev = [None] * nbuf   # result buffer may be reused once its D2H copy has finished
+        ready = [None] * nbuf
+
+        def upload(c):
+            lo, hi = c * chunk, min(nq, (c + 1) * chunk)
+            b = c % nbuf
+            with torch.cuda.stream(s_in):
+                if free_ev[b] is not None:
+                    s_in.wait_event(free_ev[b])
+                for d in range(N):
+                    bufs[b][d][: hi - lo].copy_(host_xs[d][lo:hi], non_blocking=True)
+                ready[b] = torch.cuda.Event()
+                ready[b].record(s_in)
+
+        upload(0)
+        for c in range(nchunks):
+            lo, hi = c * chunk, min(nq, (c + 1) * chunk)
+            b = c % nbuf
+            if c + 1 < nchunks:
+                upload(c + 1)  # queued before the (host-blocking) evaluation of chunk c: the copy engine never idles
+            main.wait_event(ready[b])
+            if done_ev[b] is not None:
+                main.wait_event(done_ev[b])
+            xs = [bufs[b][d][: hi - lo] for d in range(N)]
+            results[b] = evaluate_sorted(itp, *xs) if ordered else itp(*xs)
+            free_ev[b] = torch.cuda.Event()
+            free_ev[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(free_ev[b])
+                out[lo:hi].copy_(results[b], non_blocking=True)
+                results[b].record_stream(s_out)
+                done_ev[b] = torch.cuda.Event()
+                done_ev[b].record(s_out)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+    return out
+
+
 def bounds(itp):
     return itp.bounds()
 

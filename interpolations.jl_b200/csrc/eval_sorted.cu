@@ -61,7 +61,10 @@ struct TileCfg {
 constexpr int kClasses = 32;        // bank classes == lanes
 constexpr int kGroupBricks = 16;    // bricks per split-1 group: split 2 has 16 * 32 = 512 bins
 constexpr int kMaxBins = 512;       // bins per multisplit level (== threads of the split kernels)
-constexpr int kSplitThreads = 512;
+#ifndef ORD_SPLIT_THREADS
+#define ORD_SPLIT_THREADS 512
+#endif
+constexpr int kSplitThreads = ORD_SPLIT_THREADS;  // >= kMaxBins (threads 0..kMaxBins-1 own one bin each)
 #ifndef ORD_PREFETCH
 #define ORD_PREFETCH 1  // fetch the next chunk into registers while the current one goes through shared memory
 #endif
@@ -70,7 +73,7 @@ constexpr int kSplitThreads = 512;
 #endif
 constexpr bool kPrefetch = ORD_PREFETCH != 0;
 constexpr int kSplitBufs = ORD_DBUF ? 2 : 1;
-constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_DBUF) ? 1 : 2;
+constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_DBUF || ORD_SPLIT_THREADS > 512) ? 1 : 2;
 constexpr int kChunk16 = 4096;      // records per multisplit chunk, 16-byte records
 constexpr int kChunk8 = 8192;       // 8-byte records
 constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
@@ -354,8 +357,9 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
     if (key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
   __syncthreads();  // (1) histogram complete
   // exclusive scan of the counters, one per thread: warp scan, then every warp scans the NW warp totals itself
-  const unsigned v = t < nbins ? sm.hist[t] : 0u;
-  sm.hist[t] = 0;  // ready for the next chunk (its atomics come after barrier (3))
+  const bool owner = t < kMaxBins;
+  const unsigned v = (owner && t < nbins) ? sm.hist[t] : 0u;
+  if (owner) sm.hist[t] = 0;  // ready for the next chunk (its atomics come after barrier (3))
   unsigned inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -372,7 +376,7 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
   }
   const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
   const unsigned st = wbase + inc - v;
-  sm.start[t] = st;
+  if (owner) sm.start[t] = st;
   // the bin reservation's round trip to the L2 overlaps the stores of the previous chunk (double-buffered build)
   // or the shared-memory scatter of this one; the empty asm keeps the compiler from waiting for it earlier
   unsigned gb = 0;
@@ -388,7 +392,7 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
       sm.bin[p][slot] = (unsigned short)key[j];
     }
   asm volatile("" : "+r"(gb));
-  sm.gbase[p][t] = gb - st;
+  if (owner) sm.gbase[p][t] = gb - st;
   __syncthreads();  // (4) records in bin order
   stt.pending = cnt;
   if (kSplitBufs == 2) {
@@ -400,7 +404,7 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
 
 template <typename Rec, int S>
 __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
-  sm.hist[threadIdx.x] = 0;  // kMaxBins == kSplitThreads
+  if (threadIdx.x < kMaxBins) sm.hist[threadIdx.x] = 0;
   __syncthreads();
 }
 

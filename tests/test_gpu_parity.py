@@ -429,3 +429,21 @@ def test_sharded_single_rank(pkg):
             assert torch.equal(itp_s(*q), itp_1(*q))
     finally:
         dist.destroy_process_group()
+
+
+def test_evaluate_from_host_matches_device_call(pkg):
+    """The chunked host-buffer call (three streams) returns exactly what the device call returns, for chunk sizes that
+    do and do not divide the query count, ordered and direct paths."""
+    import torch
+    m = pkg
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((40, 36, 33)).astype(np.float32)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
+    nq = 1_000_003
+    hx = [torch.from_numpy(rng.uniform(1, s, nq).astype(np.float32)).pin_memory() for s in A.shape]
+    ref = itp(*[h.cuda() for h in hx]).cpu()
+    for chunk, ordered in ((1 << 18, True), (333_333, False), (1 << 21, True)):
+        out = m.evaluate_from_host(itp, *hx, chunk=chunk, ordered=ordered)
+        assert torch.equal(out, ref)
+    out = torch.empty(nq, dtype=torch.float32, pin_memory=True)
+    assert m.evaluate_from_host(itp, *hx, out=out, chunk=1 << 19) is out and torch.equal(out, ref)
