@@ -250,6 +250,7 @@ def main():
     value = nq * world / (ms_per_step * 1e-3) / 1e9
     checksum = float(out.double().sum().item())
 
+    itp_check = m.interpolate(A, it, device=dev) if (world > 1 and rank == 0) else None
     # ---- roofline (HBM): algorithmic bytes per launch / live CUDA-event duration
     peak, peak_kind = measured_peak()
     ncoef = N_GRID**3
@@ -298,6 +299,34 @@ def main():
                 "achieved": pre_bytes / (pre_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": pre_bytes / (pre_ms * 1e-3) / 1e9 / 8000,
                 "traffic": None, "algorithmic_bytes": pre_bytes, "ms": pre_ms}
+
+    # ---- N > 1: the slab-sharded prefilter (x/y passes on z-slabs, one all-to-all, z pass, all-gather), timed on the
+    #      device as the max over ranks; GB/s uses the single-GPU algorithmic bytes
+    sharded = None
+    if world > 1:
+        from interpolations_jl_b200 import parallel as par
+        lo, hi = par.shard_bounds(N_GRID, world, rank)
+        slab = A.permute(2, 1, 0)[lo:hi].contiguous()   # torch layout (nz_local, ny, nx) of the Julia array (nx, ny, nz)
+        ts_solve, ts_all = [], []
+        for i in range(4):
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            ysh, meta = par.prefilter_sharded(slab, it)
+            e1.record()
+            full = par.allgather_coefficients(ysh, meta)
+            e2.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                ts_solve.append(e0.elapsed_time(e1))
+                ts_all.append(e0.elapsed_time(e2))
+        t2 = torch.tensor([float(np.mean(ts_solve)), float(np.mean(ts_all))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(full, itp_check.coefs)) if rank == 0 else True
+        sharded = {"prefilter_ms": t2[0].item(), "prefilter_plus_allgather_ms": t2[1].item(),
+                   "prefilter_gbs": pre_bytes / (t2[0].item() * 1e-3) / 1e9, "matches_single_gpu": ok,
+                   "note": "includes the torch-side slab packing; one all-to-all between the y and z passes"}
+        del full, ysh, slab
 
     # ---- end to end through the public API with host buffers (pinned): H2D coords + D2H result per step
     del out
@@ -353,7 +382,7 @@ def main():
                        "l2": "inputs larger than L2 (coefficients 512 MiB, coordinates 12 B/query)",
                        "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
             "prefilter_gbs": roof_pre["achieved"], "prefilter_ms": pre_ms, "eval_gevals_kernel": nq / (eval_ms * 1e-3) / 1e9,
-            "roofline": roof, "roofline_prefilter": roof_pre,
+            "roofline": roof, "roofline_prefilter": roof_pre, "prefilter_sharded": sharded,
             "e2e": {"value": e2e_val, "unit": "Gevals/s", "h2d_bytes_per_step": (12 * nq_e) * world + 4 * N_GRID**3,
                     "d2h_bytes_per_step": 4 * nq_e * world, "queries_per_gpu_per_step": nq_e},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "checksum": checksum,
