@@ -69,6 +69,9 @@ constexpr int kSplitThreads = ORD_SPLIT_THREADS;  // >= kMaxBins (threads 0..kMa
 #ifndef ORD_PREFETCH
 #define ORD_PREFETCH 1  // fetch the next chunk into registers while the current one goes through shared memory
 #endif
+#ifndef ORD_FETCH_EARLY
+#define ORD_FETCH_EARLY 0  // issue the next chunk's loads before (1) or after (0) the key computation of this one
+#endif
 #ifndef ORD_DBUF
 #define ORD_DBUF 0      // double-buffer the sorted chunk: stores of chunk i-1 overlap the reservation of chunk i
 #endif
@@ -431,11 +434,16 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
     float4 r[RPT];
     unsigned key[RPT];
 #pragma unroll
+    for (int j = 0; j < RPT; ++j) r[j] = make_float4(nx[j][0], nx[j][1], nx[j][2], 0.f);
+#if ORD_FETCH_EARLY
+    if (kPrefetch) fetch(ch + gridDim.x);
+#endif
+#pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const long long q = base + j * kSplitThreads + threadIdx.x;
       key[j] = 0xffffffffu;
       if (q < P.nq) {
-        float x[3] = {nx[j][0], nx[j][1], nx[j][2]};
+        float x[3] = {r[j].x, r[j].y, r[j].z};
         bool valid;
         check_query<N>(G, x, valid);
         int brick, cls;
@@ -444,7 +452,9 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float((unsigned)q));
       }
     }
+#if !ORD_FETCH_EARLY
     if (kPrefetch) fetch(ch + gridDim.x);
+#endif
     block_split<float4, kChunk16>(sm, stt, r, key, G.ngroups, cnt, cursor1, rec1);
   }
   split_flush(sm, stt, rec1);
