@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <type_traits>
 
 namespace b200itp {
 
@@ -69,15 +70,8 @@ constexpr int kSplitThreads = ORD_SPLIT_THREADS;  // >= kMaxBins (threads 0..kMa
 #ifndef ORD_PREFETCH
 #define ORD_PREFETCH 1  // fetch the next chunk into registers while the current one goes through shared memory
 #endif
-#ifndef ORD_FETCH_EARLY
-#define ORD_FETCH_EARLY 0  // issue the next chunk's loads before (1) or after (0) the key computation of this one
-#endif
-#ifndef ORD_DBUF
-#define ORD_DBUF 0      // double-buffer the sorted chunk: stores of chunk i-1 overlap the reservation of chunk i
-#endif
 constexpr bool kPrefetch = ORD_PREFETCH != 0;
-constexpr int kSplitBufs = ORD_DBUF ? 2 : 1;
-constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_DBUF || ORD_SPLIT_THREADS > 512) ? 1 : 2;
+constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_SPLIT_THREADS > 512) ? 1 : 2;
 constexpr int kChunk16 = 4096;      // records per multisplit chunk, 16-byte records
 constexpr int kChunk8 = 8192;       // 8-byte records
 constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
@@ -96,20 +90,36 @@ struct OrdGeom {
   int nfinal;    // nbricks * kClasses
 };
 
-// (brick, class) of a query: bit-identical to what the evaluation computes (same axis_setup).  A hand-trimmed
-// first-tap function (no weights) was measured 8 % SLOWER in the split kernels (instruction scheduling around the
-// register prefetch), so the shared device function stays.
+// First tap index of one axis: the `first` of axis_setup (eval.cuh; cubic.jl:40-57, quadratic.jl:39-43,
+// indexing.jl:172-187) computed with ONE float->int conversion (F2I.FLOOR / F2I.CEIL run on the quarter-rate
+// conversion pipe; floorf + (int) would take two trips).  For every x inside the bounds the integer results equal
+// (int)floorf(.) / (int)ceilf(.) of the same float expression, so the index is identical to the evaluation's.
+template <int DEG>
+__device__ __forceinline__ int first_tap(const EvalParams &P, int d, float x) {
+  const int n = P.n[d];
+  int f;
+  if (DEG == B200ITP_CUBIC) {
+    if (P.periodic[d]) {   // uniform branch
+      f = __float2int_rd(x);
+    } else {
+      f = __float2int_rd(x + (x < 1.f ? 0.5f : 0.f));
+      f = f > n - 1 ? f - 1 : f;
+    }
+  } else {  // quadratic: n + 0.5 is exact in Float32 (n < 2^22), so the Float64 comparison of axis_setup is this one
+    const float xh = x + 0.5f;
+    f = x < (float)n + 0.5f ? __float2int_rd(xh) : __float2int_ru(xh) - 1;
+  }
+  return (x == x) ? f - 1 : 0;  // NaN record -> 0
+}
+
+// (brick, class) of a query
 template <int N, int DEG>
 __device__ __forceinline__ void locate(const EvalParams &P, const OrdGeom &G, const float (&x)[3], int &brick, int &cls) {
   using Bk = Brick<N>;
   using TC = TileCfg<N, DEG>;
   int c[3] = {0, 0, 0};
 #pragma unroll
-  for (int d = 0; d < N; ++d) {
-    AxisTaps<DEG, float> A;
-    axis_setup<DEG, float, false>(P, d, x[d], A);
-    c[d] = min(max(A.first, 0), G.cells[d] - 1);
-  }
+  for (int d = 0; d < N; ++d) c[d] = min(max(first_tap<DEG>(P, d, x[d]), 0), G.cells[d] - 1);
   const int bx = c[0] / Bk::BX, by = c[1] / Bk::BY, bz = N == 3 ? c[2] / Bk::BZ : 0;
   brick = (bz * G.nb[1] + by) * G.nb[0] + bx;
   const int lx = c[0] - bx * Bk::BX, ly = c[1] - by * Bk::BY, lz = N == 3 ? c[2] - bz * Bk::BZ : 0;
@@ -318,29 +328,18 @@ __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restri
 // runs.  key == 0xffffffff marks an absent record.
 template <typename Rec, int S>
 struct SplitSmem {
-  Rec rec[kSplitBufs][S];     // records of the current (/ the previous) chunk in bin order
-  unsigned short bin[kSplitBufs][S];
-  unsigned gbase[kSplitBufs][kMaxBins];
+  Rec rec[S];  // records of the chunk in bin order
+  unsigned short bin[S];
+  unsigned gbase[kMaxBins];
   unsigned hist[kMaxBins];
   unsigned start[kMaxBins];
   unsigned wtot[32];
 };
 
-struct SplitState {
-  int p = 0;             // buffer of the next chunk
-  unsigned pending = 0;  // records of the previous chunk still to be stored (buffer p ^ 1)
-};
-
-// stores of the previous chunk: whole runs, consecutive threads on consecutive records
-template <typename Rec, int S>
-__device__ __forceinline__ void split_flush(SplitSmem<Rec, S> &sm, SplitState &stt, Rec *__restrict__ out) {
-  const int b = kSplitBufs == 2 ? (stt.p ^ 1) : 0;
-  for (unsigned i = threadIdx.x; i < stt.pending; i += kSplitThreads) out[sm.gbase[b][sm.bin[b][i]] + i] = sm.rec[b][i];
-  stt.pending = 0;
-}
-
-template <typename Rec, int S>
-__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &stt, const Rec (&r)[S / kSplitThreads],
+// FULL: the chunk holds exactly S records (every chunk but the last of a bin/array): no per-record predicates, and the
+// copy-out loop has a constant trip count, so its shared-memory look-ups are issued back to back.
+template <bool FULL, typename Rec, int S>
+__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r)[S / kSplitThreads],
                                             const unsigned (&key)[S / kSplitThreads], int nbins, unsigned cnt,
                                             unsigned *__restrict__ cursor, Rec *__restrict__ out) {
   // sm.hist is all zero on entry (zeroed by split_init / by the previous call right after it was read)
@@ -350,8 +349,8 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
   unsigned rank[RPT];
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
-    if (key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
-  __syncthreads();  // (1) histogram complete
+    if (FULL || key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
+  __syncthreads();  // (1) histogram complete; the previous chunk's copy-out has finished in every warp
   // exclusive scan of the counters, one per thread: warp scan, then every warp scans the NW warp totals itself
   const bool owner = t < kMaxBins;
   const unsigned v = (owner && t < nbins) ? sm.hist[t] : 0u;
@@ -373,28 +372,31 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, SplitState &s
   const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
   const unsigned st = wbase + inc - v;
   if (owner) sm.start[t] = st;
-  // the bin reservation's round trip to the L2 overlaps the stores of the previous chunk (double-buffered build)
-  // or the shared-memory scatter of this one; the empty asm keeps the compiler from waiting for it earlier
+  // the bin reservation's round trip to the L2 overlaps the shared-memory scatter below; the empty asm keeps the
+  // compiler from waiting for it earlier
   unsigned gb = 0;
   if (v) gb = atomicAdd(cursor + t, v);
-  if (kSplitBufs == 2) split_flush(sm, stt, out);
-  __syncthreads();  // (3) start[] visible; the buffer may be overwritten
-  const int p = kSplitBufs == 2 ? stt.p : 0;
+  __syncthreads();  // (3) start[] visible
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
-    if (key[j] != 0xffffffffu) {
+    if (FULL || key[j] != 0xffffffffu) {
       const unsigned slot = sm.start[key[j]] + rank[j];
-      sm.rec[p][slot] = r[j];
-      sm.bin[p][slot] = (unsigned short)key[j];
+      sm.rec[slot] = r[j];
+      sm.bin[slot] = (unsigned short)key[j];
     }
   asm volatile("" : "+r"(gb));
-  if (owner) sm.gbase[p][t] = gb - st;
+  if (owner) sm.gbase[t] = gb - st;
   __syncthreads();  // (4) records in bin order
-  stt.pending = cnt;
-  if (kSplitBufs == 2) {
-    stt.p = p ^ 1;
+  // stores of whole runs, consecutive threads on consecutive records; no barrier after them: the next call touches
+  // only hist[] before its barrier (1)
+  if (FULL) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const unsigned i = (unsigned)j * kSplitThreads + t;
+      out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
+    }
   } else {
-    split_flush(sm, stt, out);  // no barrier after it: the next call touches only hist[] before its barrier (1)
+    for (unsigned i = t; i < cnt; i += kSplitThreads) out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
   }
 }
 
@@ -412,52 +414,65 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
-  SplitState stt;
   constexpr int RPT = kChunk16 / kSplitThreads;
-  const long long nchunks = (P.nq + kChunk16 - 1) / kChunk16;
+  const unsigned nq = (unsigned)P.nq;  // < 2^32 (checked by the host)
+  const unsigned nchunks = (nq + kChunk16 - 1) / kChunk16;
+  const float *cx = reinterpret_cast<const float *>(P.coords[0]);
+  const float *cy = reinterpret_cast<const float *>(P.coords[1]);
+  const float *cz = N == 3 ? reinterpret_cast<const float *>(P.coords[2]) : cx;
   // the coordinates of the next chunk are fetched before the current chunk goes through shared memory
   float nx[RPT][3];
-  auto fetch = [&](long long ch) {
+  auto fetch = [&](unsigned ch) {
+    if (ch >= nchunks) return;
+    const unsigned q0 = ch * kChunk16 + threadIdx.x;
+    if (q0 - threadIdx.x + kChunk16 <= nq) {
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const long long q = ch * kChunk16 + j * kSplitThreads + threadIdx.x;
+      for (int j = 0; j < RPT; ++j) {
+        nx[j][0] = cx[q0 + j * kSplitThreads];
+        nx[j][1] = cy[q0 + j * kSplitThreads];
+        nx[j][2] = N == 3 ? cz[q0 + j * kSplitThreads] : 0.f;
+      }
+    } else {
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-        nx[j][d] = (d < N && ch < nchunks && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
+      for (int j = 0; j < RPT; ++j) {
+        const unsigned q = q0 + j * kSplitThreads;
+        nx[j][0] = q < nq ? cx[q] : 0.f;
+        nx[j][1] = q < nq ? cy[q] : 0.f;
+        nx[j][2] = (N == 3 && q < nq) ? cz[q] : 0.f;
+      }
     }
   };
-  if (kPrefetch) fetch(blockIdx.x);
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    if (!kPrefetch) fetch(ch);
-    const long long base = ch * kChunk16;
-    const unsigned cnt = (unsigned)min((long long)kChunk16, P.nq - base);
+  auto body = [&](auto full_tag, unsigned ch) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    const unsigned base = ch * kChunk16;
+    const unsigned cnt = FULL ? (unsigned)kChunk16 : nq - base;
     float4 r[RPT];
     unsigned key[RPT];
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) r[j] = make_float4(nx[j][0], nx[j][1], nx[j][2], 0.f);
-#if ORD_FETCH_EARLY
-    if (kPrefetch) fetch(ch + gridDim.x);
-#endif
-#pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      const long long q = base + j * kSplitThreads + threadIdx.x;
+      const unsigned q = base + j * kSplitThreads + threadIdx.x;
       key[j] = 0xffffffffu;
-      if (q < P.nq) {
-        float x[3] = {r[j].x, r[j].y, r[j].z};
+      if (FULL || q < nq) {
+        float x[3] = {nx[j][0], nx[j][1], nx[j][2]};
         bool valid;
         check_query<N>(G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
         key[j] = (unsigned)(brick / kGroupBricks);
-        r[j] = make_float4(x[0], x[1], x[2], __uint_as_float((unsigned)q));
+        r[j] = make_float4(x[0], x[1], x[2], __uint_as_float(q));
       }
     }
-#if !ORD_FETCH_EARLY
     if (kPrefetch) fetch(ch + gridDim.x);
-#endif
-    block_split<float4, kChunk16>(sm, stt, r, key, G.ngroups, cnt, cursor1, rec1);
+    block_split<FULL, float4, kChunk16>(sm, r, key, G.ngroups, cnt, cursor1, rec1);
+  };
+  if (kPrefetch) fetch(blockIdx.x);
+  for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (!kPrefetch) fetch(ch);
+    if (ch * kChunk16 + kChunk16 <= nq)
+      body(std::true_type{}, ch);
+    else
+      body(std::false_type{}, ch);
   }
-  split_flush(sm, stt, rec1);
 }
 
 // split 2: records of one group -> (brick, class) streams
@@ -472,107 +487,127 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split2_kerne
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
-  SplitState stt;
   __shared__ unsigned s_chunk[kMaxBins + 1];
   constexpr int RPT = kChunk16 / kSplitThreads;
   for (int i = threadIdx.x; i <= G.ngroups; i += kSplitThreads) s_chunk[i] = chunk_start[i];
   __syncthreads();
   const unsigned nchunks = s_chunk[G.ngroups];
   // chunk descriptor: group, first record, count; the records of the next chunk are fetched early
-  auto describe = [&](unsigned ch, int &g, unsigned &base, unsigned &cnt, long long &fa, long long &fb) {
+  auto describe = [&](unsigned ch, int &g, unsigned &base, unsigned &cnt, unsigned &fa, unsigned &fb) {
     int lo = 0, hi = G.ngroups - 1;  // last group with chunk_start <= ch
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_chunk[mid] <= ch) lo = mid; else hi = mid - 1;
     }
     g = lo;
-    fa = (long long)g * kGroupBricks * kClasses;
-    fb = min(fa + kGroupBricks * kClasses, (long long)G.nfinal);
+    fa = (unsigned)g * kGroupBricks * kClasses;
+    fb = min(fa + kGroupBricks * kClasses, (unsigned)G.nfinal);
     const unsigned gbeg = start[fa], gend = start[fb];
     base = gbeg + (ch - s_chunk[g]) * kChunk16;
     cnt = min((unsigned)kChunk16, gend - base);
   };
   float4 nr[RPT];
   int g = 0, ng = 0;
-  unsigned base = 0, cnt = 0, nbase = 0, ncnt = 0;
-  long long fa = 0, fb = 0, nfa = 0, nfb = 0;
+  unsigned base = 0, cnt = 0, nbase = 0, ncnt = 0, fa = 0, fb = 0, nfa = 0, nfb = 0;
   auto fetch = [&](unsigned ch) {
     ncnt = 0;
-    if (ch < nchunks) describe(ch, ng, nbase, ncnt, nfa, nfb);
+    if (ch >= nchunks) return;
+    describe(ch, ng, nbase, ncnt, nfa, nfb);
+    const float4 *src = rec1 + nbase + threadIdx.x;
+    if (ncnt == kChunk16) {
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const unsigned i = j * kSplitThreads + threadIdx.x;
-      if (i < ncnt) nr[j] = rec1[nbase + i];
+      for (int j = 0; j < RPT; ++j) nr[j] = src[j * kSplitThreads];
+    } else {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (j * kSplitThreads + threadIdx.x < ncnt) nr[j] = src[j * kSplitThreads];
     }
   };
   if (kPrefetch) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     if (!kPrefetch) fetch(ch);
     g = ng; base = nbase; cnt = ncnt; fa = nfa; fb = nfb;
-    float4 r[RPT];
-    unsigned key[RPT];
+    auto run = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      float4 r[RPT];
+      unsigned key[RPT];
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const unsigned i = j * kSplitThreads + threadIdx.x;
-      key[j] = 0xffffffffu;
-      if (i < cnt) {
-        r[j] = nr[j];
-        const float x[3] = {r[j].x, r[j].y, r[j].z};
-        int brick, cls;
-        locate<N, DEG>(P, G, x, brick, cls);
-        key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
+      for (int j = 0; j < RPT; ++j) {
+        const unsigned i = j * kSplitThreads + threadIdx.x;
+        key[j] = 0xffffffffu;
+        if (FULL || i < cnt) {
+          r[j] = nr[j];
+          const float x[3] = {r[j].x, r[j].y, r[j].z};
+          int brick, cls;
+          locate<N, DEG>(P, G, x, brick, cls);
+          key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
+        }
       }
-    }
-    if (kPrefetch) fetch(ch + gridDim.x);
-    block_split<float4, kChunk16>(sm, stt, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
+      if (kPrefetch) fetch(ch + gridDim.x);
+      block_split<FULL, float4, kChunk16>(sm, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
+    };
+    if (cnt == kChunk16)
+      run(std::true_type{});
+    else
+      run(std::false_type{});
   }
-  split_flush(sm, stt, rec2);
 }
 
 // unsort: {q, value} records by (q >> shift) relative to the chunk's parent bin
 template <int LEVEL>
-__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq,
+__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq_,
                                                                    unsigned *__restrict__ cursor,
                                                                    uint2 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<uint2, kChunk8> *>(smem_raw);
   split_init(sm);
-  SplitState stt;
   constexpr int RPT = kChunk8 / kSplitThreads;
-  const long long nchunks = (nq + kChunk8 - 1) / kChunk8;
+  const unsigned nq = (unsigned)nq_;
+  const unsigned nchunks = (nq + kChunk8 - 1) / kChunk8;
+  const unsigned nwin = (nq + (1u << kShiftB) - 1) >> kShiftB;
   uint2 nr[RPT];
-  auto fetch = [&](long long ch) {
+  auto fetch = [&](unsigned ch) {
+    if (ch >= nchunks) return;
+    const uint2 *src = in + ch * kChunk8 + threadIdx.x;
+    if (ch * kChunk8 + kChunk8 <= nq) {
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const long long i = ch * kChunk8 + j * kSplitThreads + threadIdx.x;
-      if (ch < nchunks && i < nq) nr[j] = in[i];
+      for (int j = 0; j < RPT; ++j) nr[j] = src[j * kSplitThreads];
+    } else {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (ch * kChunk8 + j * kSplitThreads + threadIdx.x < nq) nr[j] = src[j * kSplitThreads];
     }
   };
   if (kPrefetch) fetch(blockIdx.x);
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+  for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     if (!kPrefetch) fetch(ch);
-    const long long base = ch * kChunk8;
-    const unsigned cnt = (unsigned)min((long long)kChunk8, nq - base);
+    const unsigned base = ch * kChunk8;
     // level A: bins over the whole array; level B: the chunk lies inside one level-A bin (2^kShiftA records)
-    const unsigned bin0 = LEVEL == 0 ? 0u : (unsigned)(base >> kShiftA) << (kShiftA - kShiftB);
-    const int nbins = LEVEL == 0 ? (int)((nq + (1LL << kShiftA) - 1) >> kShiftA)
-                                 : (int)min((long long)(1 << (kShiftA - kShiftB)),
-                                            ((nq + (1LL << kShiftB) - 1) >> kShiftB) - (long long)bin0);
-    uint2 r[RPT];
-    unsigned key[RPT];
+    const unsigned bin0 = LEVEL == 0 ? 0u : (base >> kShiftA) << (kShiftA - kShiftB);
+    const int nbins = LEVEL == 0 ? (int)((nq + (1u << kShiftA) - 1) >> kShiftA)
+                                 : (int)min(1u << (kShiftA - kShiftB), nwin - bin0);
+    auto run = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const unsigned cnt = FULL ? (unsigned)kChunk8 : nq - base;
+      uint2 r[RPT];
+      unsigned key[RPT];
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const long long i = base + j * kSplitThreads + threadIdx.x;
-      key[j] = 0xffffffffu;
-      if (i < nq) {
-        r[j] = nr[j];
-        key[j] = LEVEL == 0 ? (r[j].x >> kShiftA) : ((r[j].x >> kShiftB) - bin0);
+      for (int j = 0; j < RPT; ++j) {
+        const unsigned i = base + j * kSplitThreads + threadIdx.x;
+        key[j] = 0xffffffffu;
+        if (FULL || i < nq) {
+          r[j] = nr[j];
+          key[j] = LEVEL == 0 ? (r[j].x >> kShiftA) : ((r[j].x >> kShiftB) - bin0);
+        }
       }
-    }
-    if (kPrefetch) fetch(ch + gridDim.x);
-    block_split<uint2, kChunk8>(sm, stt, r, key, nbins, cnt, cursor + bin0, out);
+      if (kPrefetch) fetch(ch + gridDim.x);
+      block_split<FULL, uint2, kChunk8>(sm, r, key, nbins, cnt, cursor + bin0, out);
+    };
+    if (base + kChunk8 <= nq)
+      run(std::true_type{});
+    else
+      run(std::false_type{});
   }
-  split_flush(sm, stt, out);
 }
 
 // place: window w holds exactly the results q in [w * 2^kShiftB, ...): permute in shared memory
