@@ -346,10 +346,23 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
   constexpr int RPT = S / kSplitThreads;
   constexpr int NW = kSplitThreads / 32;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  unsigned rank[RPT];
+  // 16-byte records: key | rank << 16 in one register across the barriers (ranks < S <= 2^16, keys < 2^16); 8-byte
+  // records (16 per thread) were measured faster with the two values in separate registers
+  constexpr bool PACK = sizeof(Rec) == 16;
+  unsigned kr[RPT], rk[PACK ? 1 : RPT];
 #pragma unroll
-  for (int j = 0; j < RPT; ++j)
-    if (FULL || key[j] != 0xffffffffu) rank[j] = atomicAdd(&sm.hist[key[j]], 1u);
+  for (int j = 0; j < RPT; ++j) {
+    kr[j] = 0xffffffffu;
+    if (FULL || key[j] != 0xffffffffu) {
+      const unsigned rank = atomicAdd(&sm.hist[key[j]], 1u);
+      if (PACK) {
+        kr[j] = key[j] | (rank << 16);
+      } else {
+        kr[j] = key[j];
+        rk[j] = rank;
+      }
+    }
+  }
   __syncthreads();  // (1) histogram complete; the previous chunk's copy-out has finished in every warp
   // exclusive scan of the counters, one per thread: warp scan, then every warp scans the NW warp totals itself
   const bool owner = t < kMaxBins;
@@ -379,10 +392,11 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
   __syncthreads();  // (3) start[] visible
 #pragma unroll
   for (int j = 0; j < RPT; ++j)
-    if (FULL || key[j] != 0xffffffffu) {
-      const unsigned slot = sm.start[key[j]] + rank[j];
+    if (FULL || kr[j] != 0xffffffffu) {
+      const unsigned k = PACK ? (kr[j] & 0xffffu) : kr[j];
+      const unsigned slot = sm.start[k] + (PACK ? (kr[j] >> 16) : rk[PACK ? 0 : j]);
       sm.rec[slot] = r[j];
-      sm.bin[slot] = (unsigned short)key[j];
+      sm.bin[slot] = (unsigned short)k;
     }
   asm volatile("" : "+r"(gb));
   if (owner) sm.gbase[t] = gb - st;
@@ -390,7 +404,7 @@ __device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r
   // stores of whole runs, consecutive threads on consecutive records; no barrier after them: the next call touches
   // only hist[] before its barrier (1)
   if (FULL) {
-#pragma unroll
+#pragma unroll 8
     for (int j = 0; j < RPT; ++j) {
       const unsigned i = (unsigned)j * kSplitThreads + t;
       out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
