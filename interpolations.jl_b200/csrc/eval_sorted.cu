@@ -91,6 +91,7 @@ struct OrdGeom {
   float lbf[3], ubf[3];  // bounds as Float32 thresholds: (double)x >= lb <=> x >= lbf, (double)x <= ub <=> x <= ubf
   int nb[3];     // bricks per axis
   int cells[3];  // distinct first-tap indices per axis
+  int fmin[3];   // smallest first-tap index (parent index space): -1 for periodic cubic axes (OnCell, x < 1), else 0
   int nbricks;
   int ngroups;
   int nfinal;    // nbricks * kClasses
@@ -125,7 +126,7 @@ __device__ __forceinline__ void locate(const EvalParams &P, const OrdGeom &G, co
   using TC = TileCfg<N, DEG>;
   int c[3] = {0, 0, 0};
 #pragma unroll
-  for (int d = 0; d < N; ++d) c[d] = min(max(first_tap<DEG>(P, d, x[d]), 0), G.cells[d] - 1);
+  for (int d = 0; d < N; ++d) c[d] = min(max(first_tap<DEG>(P, d, x[d]) - G.fmin[d], 0), G.cells[d] - 1);
   const int bx = c[0] / Bk::BX, by = c[1] / Bk::BY, bz = N == 3 ? c[2] / Bk::BZ : 0;
   brick = (bz * G.nb[1] + by) * G.nb[0] + bx;
   const int lx = c[0] - bx * Bk::BX, ly = c[1] - by * Bk::BY, lz = N == 3 ? c[2] - bz * Bk::BZ : 0;
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
       for (int e = tid; e < 3 * TC::MAXT; e += kEvalThreads) {  // per-axis offset tables, once per brick
         const int d = e / TC::MAXT, l = e % TC::MAXT;
         if (d < N && l < TDIM[d]) {
-          int idx = o[d] + l;  // parent index of the tap
+          int idx = o[d] + l + G.fmin[d];  // parent index of the tap
           long long off = -1;
           if (P.periodic[d]) {
             const int n = P.n[d];
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
 #pragma unroll
           for (int d = 0; d < N; ++d) {
             axis_setup<DEG, float, false>(P, d, x[d], ax[d]);
-            lpos[d] = min(max(ax[d].first, 0), G.cells[d] - 1) - o[d];
+            lpos[d] = min(max(ax[d].first - G.fmin[d], 0), G.cells[d] - 1) - o[d];
           }
           // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )  (Interpolations.jl:304-316)
           const float *tb = sm.tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0];
@@ -908,6 +909,7 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
     G.cells[d] = 1;
     G.lbf[d] = 0.f;
     G.ubf[d] = 0.f;
+    G.fmin[d] = 0;
   }
   for (int d = 0; d < N; ++d) {
     // smallest Float32 >= lb and largest Float32 <= ub: the Float64 comparisons of the direct kernel, in Float32
@@ -918,8 +920,10 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
     G.ubf[d] = hi;
   }
   for (int d = 0; d < N; ++d) {
-    // first-tap indices: periodic 0..n-1, otherwise 0..size-1-DEG
-    G.cells[d] = P.periodic[d] ? P.n[d] : (int)D->size[d] - DEG;
+    // first-tap indices: periodic cubic -1..n-1 (floor(x) - 1 with x in [0.5, n + 0.5] on OnCell grids), periodic
+    // quadratic 0..n-1, otherwise 0..size-1-DEG
+    G.fmin[d] = (P.periodic[d] && DEG == B200ITP_CUBIC) ? -1 : 0;
+    G.cells[d] = P.periodic[d] ? P.n[d] - G.fmin[d] : (int)D->size[d] - DEG;
     if (G.cells[d] < 1) return false;
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
     bricks *= G.nb[d];

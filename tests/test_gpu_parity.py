@@ -8,6 +8,7 @@ Bars (BASELINE.json north_star):
     (the streaming solve uses a different operation order than the reference's LU + Woodbury sweeps).
 """
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -447,3 +448,48 @@ def test_evaluate_from_host_matches_device_call(pkg):
         assert torch.equal(out, ref)
     out = torch.empty(nq, dtype=torch.float32, pin_memory=True)
     assert m.evaluate_from_host(itp, *hx, out=out, chunk=1 << 19) is out and torch.equal(out, ref)
+
+
+def test_ordered_evaluation_fuzz(pkg):
+    """Random shapes (axes shorter and longer than a brick, odd sizes), degrees, boundary conditions and query
+    distributions (uniform, one hot cell, one hot brick, axis-aligned lines, exact nodes): ordered == direct, bit for bit."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    L.b200itp_eval_sorted_set_min_queries(1)
+    rng = np.random.default_rng(2024)
+    bcs = [m.Flat, m.Line, m.Free, m.Periodic]
+    for case in range(int(os.environ.get("B200ITP_FUZZ_CASES", "24"))):
+        nd = int(rng.integers(2, 4))
+        shape = tuple(int(rng.choice([7, 13, 31, 33, 64, 97, 130])) for _ in range(nd))
+        if nd == 3 and np.prod(shape) > 2_000_000:
+            shape = (shape[0], shape[1], 13)
+        deg = m.Cubic if rng.random() < 0.6 else m.Quadratic
+        bc = bcs[int(rng.integers(0, 4))]
+        gt = m.OnGrid if rng.random() < 0.5 else m.OnCell
+        it = m.BSpline(deg(bc(gt())))
+        A = rng.standard_normal(shape).astype(np.float32)
+        itp = m.interpolate(A, it)
+        nq = int(rng.choice([1, 33, 5000, 70001, 400_000]))
+        kind = case % 5
+        coords = []
+        for d, (lb, ub) in enumerate(itp.bounds()):
+            lb, ub = float(lb), float(ub)
+            if kind == 0:
+                x = rng.uniform(lb, ub, nq)
+            elif kind == 1:   # one hot cell
+                c0 = rng.uniform(lb, ub - 1)
+                x = rng.uniform(c0, min(ub, c0 + 1), nq)
+            elif kind == 2:   # one hot brick-sized region
+                c0 = rng.uniform(lb, max(lb, ub - 20))
+                x = rng.uniform(c0, min(ub, c0 + 20), nq)
+            elif kind == 3:   # line along axis 0
+                x = rng.uniform(lb, ub, nq) if d == 0 else np.full(nq, rng.uniform(lb, ub))
+            else:             # exact nodes and half nodes
+                x = rng.integers(int(np.ceil(lb)), int(np.floor(ub)) + 1, nq) + rng.choice([0.0, 0.5], nq)
+            coords.append(np.clip(x.astype(np.float32), np.float32(lb), np.float32(ub)))
+            coords[-1] = np.where((coords[-1] < lb) | (coords[-1] > ub), np.float32((lb + ub) / 2), coords[-1])
+        a = itp(*coords).cpu().numpy()
+        b = m.evaluate_sorted(itp, *coords).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True), (case, shape, it, nq, kind)
+    L.b200itp_eval_sorted_set_min_queries(1 << 20)
