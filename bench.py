@@ -243,6 +243,8 @@ def main():
     L.b200itp_profile_enable(0)
     stages = m._lib.profile_stages()
     launches = L.b200itp_launch_count() - l0
+    if args.sorted and L.b200itp_eval_sorted_ordered_calls() == 0:
+        raise RuntimeError("bench: the ordered evaluation pipeline did not run (fell back to the direct kernel)")
     t_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)

@@ -236,6 +236,9 @@ B200ITP_API int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *
  * threshold to 1 (tests) also lifts the array-size condition. */
 B200ITP_API int64_t b200itp_eval_sorted_min_queries(void);
 B200ITP_API void b200itp_eval_sorted_set_min_queries(int64_t n);
+/* number of b200itp_eval_sorted calls of this process that were served by the ordered pipeline (the others were
+ * forwarded to the direct kernel): lets tests and bench.py assert which path ran */
+B200ITP_API uint64_t b200itp_eval_sorted_ordered_calls(void);
 
 #ifdef __cplusplus
 }

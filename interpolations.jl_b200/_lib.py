@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         "b200itp_eval_sorted": (C.c_int, [i32, C.POINTER(Desc), vp, C.POINTER(vp), i64, vp, pi64, vp, sz, vp]),
         "b200itp_eval_sorted_min_queries": (i64, []),
         "b200itp_eval_sorted_set_min_queries": (None, [i64]),
+        "b200itp_eval_sorted_ordered_calls": (C.c_uint64, []),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export the symbol
@@ -118,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_eval",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted",
     "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries",
+    "b200itp_eval_sorted_ordered_calls",
 ]
 
 

@@ -920,9 +920,9 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
     G.ubf[d] = hi;
   }
   for (int d = 0; d < N; ++d) {
-    // first-tap indices: periodic cubic -1..n-1 (floor(x) - 1 with x in [0.5, n + 0.5] on OnCell grids), periodic
-    // quadratic 0..n-1, otherwise 0..size-1-DEG
-    G.fmin[d] = (P.periodic[d] && DEG == B200ITP_CUBIC) ? -1 : 0;
+    // first-tap indices: periodic cubic on OnCell grids -1..n-1 (floor(x) - 1 with x in [0.5, n + 0.5]), other periodic
+    // axes 0..n-1, otherwise 0..size-1-DEG
+    G.fmin[d] = (P.periodic[d] && DEG == B200ITP_CUBIC && P.lb[d] < 1.0) ? -1 : 0;  // OnGrid: x >= 1, first >= 0
     G.cells[d] = P.periodic[d] ? P.n[d] - G.fmin[d] : (int)D->size[d] - DEG;
     if (G.cells[d] < 1) return false;
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
@@ -1026,12 +1026,14 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
 // small inputs; results do not depend on it).
 static int64_t g_sorted_min_queries = 1 << 20;
 static long long g_sorted_min_coef_bytes = 128LL << 20;
+static std::atomic<uint64_t> g_ordered_calls{0};  // calls served by the ordered pipeline (not the direct kernel)
 
 }  // namespace b200itp
 
 using namespace b200itp;
 
 extern "C" int64_t b200itp_eval_sorted_min_queries(void) { return g_sorted_min_queries; }
+extern "C" uint64_t b200itp_eval_sorted_ordered_calls(void) { return g_ordered_calls.load(); }
 extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
   g_sorted_min_queries = n < 1 ? 1 : n;
   g_sorted_min_coef_bytes = n <= 1 ? 0 : (128LL << 20);  // n == 1 (tests): every supported call takes the ordered path
@@ -1083,6 +1085,7 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
     if (d->ndims == 2 && deg == 2) rc = run_ordered<2, 2>(dev, P, d, sp, sbytes, st, &done);
     if (rc) return rc;
     if (done) {
+      g_ordered_calls.fetch_add(1, std::memory_order_relaxed);
       if (first_oob) {
         unsigned long long h = ~0ULL;
         B200_CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st));

@@ -89,7 +89,10 @@ def test_c3_tricubic_periodic_512_f32(pkg, orc):
     A = torch.randn((n, n, n), device="cuda", dtype=torch.float32, generator=g)
     itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
     coords = [(torch.rand(nq, device="cuda", dtype=torch.float32, generator=g) * (n - 1) + 1).clamp_(1, n) for _ in range(3)]
+    L = m._lib.lib()
+    n0 = L.b200itp_eval_sorted_ordered_calls()
     v = m.evaluate_sorted(itp, *coords)
+    assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "C3 must be served by the ordered pipeline"
     k = 20_000_000
     assert torch.equal(v[:k], itp(*[c[:k] for c in coords]))          # ordered pipeline == direct kernel
     assert torch.equal(v[-k:], itp(*[c[-k:] for c in coords]))

@@ -393,7 +393,9 @@ def test_ordered_evaluation_is_bit_identical(pkg, shape):
             x[-4:] = [float(lb), float(ub), 1.0, shape[d]]
             coords.append(np.clip(x.astype(np.float32), np.float32(lb), np.float32(ub)))
         a = itp(*coords).cpu().numpy()
+        n0 = L.b200itp_eval_sorted_ordered_calls()
         b = m.evaluate_sorted(itp, *coords).cpu().numpy()
+        assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "the ordered pipeline must serve this call"
         assert np.array_equal(a, b), it
         bad = [c.copy() for c in coords]
         bad[0][12345] = np.float32(float(itp.bounds()[0][1]) + 1.0)
@@ -490,6 +492,8 @@ def test_ordered_evaluation_fuzz(pkg):
             coords.append(np.clip(x.astype(np.float32), np.float32(lb), np.float32(ub)))
             coords[-1] = np.where((coords[-1] < lb) | (coords[-1] > ub), np.float32((lb + ub) / 2), coords[-1])
         a = itp(*coords).cpu().numpy()
+        n0 = L.b200itp_eval_sorted_ordered_calls()
         b = m.evaluate_sorted(itp, *coords).cpu().numpy()
+        assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, (case, shape, it)
         assert np.array_equal(a, b, equal_nan=True), (case, shape, it, nq, kind)
     L.b200itp_eval_sorted_set_min_queries(1 << 20)
