@@ -498,8 +498,11 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
 }
 
 // split 2: records of one group -> (brick, class) streams
+// Measured per kernel (1e9 queries): split 2 is fastest WITHOUT the register prefetch at two CTAs per SM (7.5 vs 8.6 ms);
+// split 1 and the unsort levels are fastest with it at one CTA per SM (7.6 vs 8.3 ms, 3.8 vs 4.2 ms).
+constexpr bool kPrefetchSplit2 = false;
 template <int N, int DEG>
-__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split2_kernel(const __grid_constant__ EvalParams P,
+__global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_THREADS > 512) ? 1 : 2) ord_split2_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G,
                                                                    const unsigned *__restrict__ start,
                                                                    const unsigned *__restrict__ chunk_start,
@@ -545,9 +548,9 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split2_kerne
         if (j * kSplitThreads + threadIdx.x < ncnt) nr[j] = src[j * kSplitThreads];
     }
   };
-  if (kPrefetch) fetch(blockIdx.x);
+  if (kPrefetchSplit2) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    if (!kPrefetch) fetch(ch);
+    if (!kPrefetchSplit2) fetch(ch);
     g = ng; base = nbase; cnt = ncnt; fa = nfa; fb = nfb;
     auto run = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split2_kerne
           key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
         }
       }
-      if (kPrefetch) fetch(ch + gridDim.x);
+      if (kPrefetchSplit2) fetch(ch + gridDim.x);
       block_split<FULL, float4, kChunk16>(sm, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
     };
     if (cnt == kChunk16)
