@@ -231,6 +231,12 @@ B200ITP_API size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int6
 B200ITP_API int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs,
                         const void *const *coords, int64_t nq, void *out_value,
                         int64_t *first_oob, void *scratch, size_t scratch_bytes, void *stream);
+/* `Interpolations.gradient.(Ref(itp), xs...)` through the same ordered pipeline: `out_grad` receives nq*ndims elements,
+ * ndims contiguous per query (SVector layout), bit-identical to b200itp_eval's gradients.  Same scope, scratch size and
+ * fallback rule as b200itp_eval_sorted. */
+B200ITP_API int b200itp_gradient_sorted(int dev, const b200itp_desc *d, const void *coefs,
+                            const void *const *coords, int64_t nq, void *out_grad, int64_t *first_oob,
+                            void *scratch, size_t scratch_bytes, void *stream);
 /* threshold (queries per call) from which the ordered pipeline is used; default 2^20, and only for coefficient
  * arrays of at least 128 MiB (smaller ones stay L2-resident, where the direct kernel is faster).  Setting the
  * threshold to 1 (tests) also lifts the array-size condition. */

@@ -497,12 +497,17 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
             return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(None)
 
         if nq > 0:
-            if sorted_queries and want_value and not want_grad and not debug:
+            if sorted_queries and (want_value != want_grad) and not debug:
                 nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq)
                 scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=tdev)
-                rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), C.byref(foob), p(scratch),
-                                           nbytes, _stream_ptr(dev))
-                _lib.check(rc, "b200itp_eval_sorted")
+                if want_value:
+                    rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), C.byref(foob), p(scratch),
+                                               nbytes, _stream_ptr(dev))
+                    _lib.check(rc, "b200itp_eval_sorted")
+                else:
+                    rc = L.b200itp_gradient_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(grad), C.byref(foob),
+                                                   p(scratch), nbytes, _stream_ptr(dev))
+                    _lib.check(rc, "b200itp_gradient_sorted")
             else:
                 rc = L.b200itp_eval(dev, C.byref(D), p(coefs), ptrs, nq, p(val), p(grad), C.byref(foob), p(dbg_i),
                                     p(dbg_b), _stream_ptr(dev))
@@ -612,6 +617,12 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
         main.wait_stream(s_out)
         main.wait_stream(s_in)
     return out
+
+
+def gradient_sorted(itp, *xs):
+    """`Interpolations.gradient.(Ref(itp), xs...)` through the ordered pipeline (results in the caller's order, identical
+    to `gradient`)."""
+    return _broadcast_eval(itp, xs, want_value=False, want_grad=True, sorted_queries=True)[1]
 
 
 def bounds(itp):

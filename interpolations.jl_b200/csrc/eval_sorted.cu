@@ -74,8 +74,16 @@ constexpr bool kPrefetch = ORD_PREFETCH != 0;
 constexpr int kSplitMinCtas = (ORD_PREFETCH || ORD_SPLIT_THREADS > 512) ? 1 : 2;
 constexpr int kChunk16 = 4096;      // records per multisplit chunk, 16-byte records
 constexpr int kChunk8 = 8192;       // 8-byte records
-constexpr int kShiftB = 14;         // final windows of 2^14 results (64 KB of shared memory)
-constexpr int kShiftA = 23;         // unsort level A bins of 2^23 results (512 windows each)
+// Unsort of the results: values travel as {q, value} (8 bytes), gradients as {q, g1, g2, g3} (16 bytes).  Final windows
+// of 2^SB results are permuted in shared memory (values: 2^14 x 4 B = 64 KB; gradients: 2^13 x N x 4 B <= 96 KB); level A
+// bins hold 512 windows each.
+template <bool GRAD>
+struct Uns {
+  using Rec = typename std::conditional<GRAD, uint4, uint2>::type;
+  static constexpr int S = GRAD ? kChunk16 : kChunk8;
+  static constexpr int SB = GRAD ? 13 : 14;
+  static constexpr int SA = SB + 9;
+};
 #ifndef ORD_EVAL_THREADS
 #define ORD_EVAL_THREADS 768
 #endif
@@ -276,19 +284,19 @@ struct OrdPlan {
   unsigned *cursor1;      // ngroups
   unsigned *chunk_start;  // ngroups + 1 : split-2 chunks
   unsigned *item_start;   // nbricks + 1 : evaluation work items
-  unsigned *cursorA;      // ceil(nq / 2^kShiftA)
-  unsigned *cursorB;      // ceil(nq / 2^kShiftB)
+  unsigned *cursorA;      // ceil(nq / 2^SA)
+  unsigned *cursorB;      // ceil(nq / 2^SB)
 };
 
 __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restrict__ start, const OrdGeom G,
-                                                        long long nq, int ctas, OrdPlan pl) {
+                                                        long long nq, int ctas, int shiftA, int shiftB, OrdPlan pl) {
   __shared__ unsigned buf[1024];
   __shared__ unsigned carry;
   const int t = threadIdx.x;
   // unsort cursors
-  const long long na = (nq + (1LL << kShiftA) - 1) >> kShiftA, nbw = (nq + (1LL << kShiftB) - 1) >> kShiftB;
-  for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << kShiftA);
-  for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << kShiftB);
+  const long long na = (nq + (1LL << shiftA) - 1) >> shiftA, nbw = (nq + (1LL << shiftB) - 1) >> shiftB;
+  for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << shiftA);
+  for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << shiftB);
   // split-1 cursors
   for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[(long long)g * kGroupBricks * kClasses];
   // two exclusive scans: chunks per group, items per brick
@@ -578,43 +586,45 @@ __global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_T
   }
 }
 
-// unsort: {q, value} records by (q >> shift) relative to the chunk's parent bin
-template <int LEVEL>
-__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kernel(const uint2 *__restrict__ in, long long nq_,
-                                                                   unsigned *__restrict__ cursor,
-                                                                   uint2 *__restrict__ out) {
+// unsort: result records by (q >> shift) relative to the chunk's parent bin; q is the first word of the record
+template <int LEVEL, bool GRAD>
+__global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kernel(const typename Uns<GRAD>::Rec *__restrict__ in,
+                                                                   long long nq_, unsigned *__restrict__ cursor,
+                                                                   typename Uns<GRAD>::Rec *__restrict__ out) {
+  using U = Uns<GRAD>;
+  using Rec = typename U::Rec;
+  constexpr int S = U::S, SA = U::SA, SB = U::SB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto &sm = *reinterpret_cast<SplitSmem<uint2, kChunk8> *>(smem_raw);
+  auto &sm = *reinterpret_cast<SplitSmem<Rec, S> *>(smem_raw);
   split_init(sm);
-  constexpr int RPT = kChunk8 / kSplitThreads;
+  constexpr int RPT = S / kSplitThreads;
   const unsigned nq = (unsigned)nq_;
-  const unsigned nchunks = (nq + kChunk8 - 1) / kChunk8;
-  const unsigned nwin = (nq + (1u << kShiftB) - 1) >> kShiftB;
-  uint2 nr[RPT];
+  const unsigned nchunks = (nq + S - 1) / S;
+  const unsigned nwin = (nq + (1u << SB) - 1) >> SB;
+  Rec nr[RPT];
   auto fetch = [&](unsigned ch) {
     if (ch >= nchunks) return;
-    const uint2 *src = in + ch * kChunk8 + threadIdx.x;
-    if (ch * kChunk8 + kChunk8 <= nq) {
+    const Rec *src = in + ch * S + threadIdx.x;
+    if (ch * S + S <= nq) {
 #pragma unroll
       for (int j = 0; j < RPT; ++j) nr[j] = src[j * kSplitThreads];
     } else {
 #pragma unroll
       for (int j = 0; j < RPT; ++j)
-        if (ch * kChunk8 + j * kSplitThreads + threadIdx.x < nq) nr[j] = src[j * kSplitThreads];
+        if (ch * S + j * kSplitThreads + threadIdx.x < nq) nr[j] = src[j * kSplitThreads];
     }
   };
   if (kPrefetch) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     if (!kPrefetch) fetch(ch);
-    const unsigned base = ch * kChunk8;
-    // level A: bins over the whole array; level B: the chunk lies inside one level-A bin (2^kShiftA records)
-    const unsigned bin0 = LEVEL == 0 ? 0u : (base >> kShiftA) << (kShiftA - kShiftB);
-    const int nbins = LEVEL == 0 ? (int)((nq + (1u << kShiftA) - 1) >> kShiftA)
-                                 : (int)min(1u << (kShiftA - kShiftB), nwin - bin0);
+    const unsigned base = ch * S;
+    // level A: bins over the whole array; level B: the chunk lies inside one level-A bin (2^SA records)
+    const unsigned bin0 = LEVEL == 0 ? 0u : (base >> SA) << (SA - SB);
+    const int nbins = LEVEL == 0 ? (int)((nq + (1u << SA) - 1) >> SA) : (int)min(1u << (SA - SB), nwin - bin0);
     auto run = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
-      const unsigned cnt = FULL ? (unsigned)kChunk8 : nq - base;
-      uint2 r[RPT];
+      const unsigned cnt = FULL ? (unsigned)S : nq - base;
+      Rec r[RPT];
       unsigned key[RPT];
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
@@ -622,33 +632,42 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_unsort_kerne
         key[j] = 0xffffffffu;
         if (FULL || i < nq) {
           r[j] = nr[j];
-          key[j] = LEVEL == 0 ? (r[j].x >> kShiftA) : ((r[j].x >> kShiftB) - bin0);
+          key[j] = LEVEL == 0 ? (r[j].x >> SA) : ((r[j].x >> SB) - bin0);
         }
       }
       if (kPrefetch) fetch(ch + gridDim.x);
-      block_split<FULL, uint2, kChunk8>(sm, r, key, nbins, cnt, cursor + bin0, out);
+      block_split<FULL, Rec, S>(sm, r, key, nbins, cnt, cursor + bin0, out);
     };
-    if (base + kChunk8 <= nq)
+    if (base + S <= nq)
       run(std::true_type{});
     else
       run(std::false_type{});
   }
 }
 
-// place: window w holds exactly the results q in [w * 2^kShiftB, ...): permute in shared memory
-__global__ void __launch_bounds__(1024) ord_place_kernel(const uint2 *__restrict__ in, long long nq,
+// place: window w holds exactly the results q in [w * 2^SB, ...): permute in shared memory, store coalesced.
+// Gradients: NG = N components per query, contiguous in the output (SVector layout).
+template <bool GRAD, int NG>
+__global__ void __launch_bounds__(1024) ord_place_kernel(const typename Uns<GRAD>::Rec *__restrict__ in, long long nq,
                                                          float *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *win = reinterpret_cast<float *>(smem_raw);
-  constexpr int W = 1 << kShiftB;
+  constexpr int W = 1 << Uns<GRAD>::SB;
   const long long base = (long long)blockIdx.x * W;
   const int cnt = (int)min((long long)W, nq - base);
   for (int i = threadIdx.x; i < cnt; i += 1024) {
-    const uint2 r = in[base + i];
-    win[r.x & (W - 1)] = __uint_as_float(r.y);
+    const auto r = in[base + i];
+    const unsigned slot = r.x & (W - 1);
+    if constexpr (GRAD) {
+      win[slot * NG + 0] = __uint_as_float(r.y);
+      win[slot * NG + 1] = __uint_as_float(r.z);
+      if (NG == 3) win[slot * NG + 2] = __uint_as_float(r.w);
+    } else {
+      win[slot] = __uint_as_float(r.y);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < cnt; i += 1024) out[base + i] = win[i];
+  for (int i = threadIdx.x; i < cnt * NG; i += 1024) out[base * NG + i] = win[i];
 }
 
 // ------------------------------------------------------------------------------------------ evaluate
@@ -656,6 +675,40 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+
+// Nested reduction with gradients from the shared-memory tile: the same operations in the same order as Reduce<...,true,0>
+// of eval.cuh (Interpolations.jl:304-316 with one axis' weights swapped for the gradient weights, partial sums shared).
+template <int N, int DEG, int D>
+struct TileReduce {
+  using TC = TileCfg<N, DEG>;
+  __device__ __forceinline__ static void run(const AxisTaps<DEG, float> (&ax)[N], const float *base, float &val,
+                                             float (&g)[N]) {
+    constexpr int L = DEG + 1;
+    constexpr int stride = D == 0 ? 1 : (D == 1 ? TC::PX : TC::PX * TC::TY);
+    const AxisTaps<DEG, float> &A = ax[D];
+    float gv = 0.f;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      float vk;
+      float gk[N];
+      const float *b = base + k * stride;
+      if constexpr (D == N - 1) {
+        vk = *b;
+      } else {
+        TileReduce<N, DEG, D + 1>::run(ax, b, vk, gk);
+      }
+      const float w = A.wv[k];
+      val = k == 0 ? w * vk : w * vk + val;
+      const float wgk = A.wg[k];
+      gv = k == 0 ? wgk * vk : wgk * vk + gv;
+      if constexpr (D < N - 1) {
+#pragma unroll
+        for (int j = D + 1; j < N; ++j) g[j] = k == 0 ? w * gk[j] : w * gk[j] + g[j];
+      }
+    }
+    g[D] = gv;
+  }
+};
 
 template <int N, int DEG>
 struct EvalSmem {
@@ -667,13 +720,13 @@ struct EvalSmem {
   int item_brick, item_part, item_parts, max_cnt, next_blk;
 };
 
-template <int N, int DEG>
+template <int N, int DEG, bool GRAD>
 __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G,
                                                                    const unsigned *__restrict__ start,
                                                                    const unsigned *__restrict__ item_start,
                                                                    const float4 *__restrict__ rec,
-                                                                   uint2 *__restrict__ res) {
+                                                                   typename Uns<GRAD>::Rec *__restrict__ res) {
   using TC = TileCfg<N, DEG>;
   using Bk = Brick<N>;
   constexpr int L = TC::L;
@@ -820,35 +873,41 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
           int lpos[3] = {0, 0, 0};
 #pragma unroll
           for (int d = 0; d < N; ++d) {
-            axis_setup<DEG, float, false>(P, d, x[d], ax[d]);
+            axis_setup<DEG, float, GRAD>(P, d, x[d], ax[d]);
             lpos[d] = min(max(ax[d].first - G.fmin[d], 0), G.cells[d] - 1) - o[d];
           }
-          // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )  (Interpolations.jl:304-316)
           const float *tb = sm.tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0];
-          float val = 0.f;
+          if constexpr (GRAD) {
+            float val = 0.f, g[N];
+            TileReduce<N, DEG, 0>::run(ax, tb, val, g);
+            wst[lane * kRBP + r] = make_float4(q4.w, g[0], g[1], N == 3 ? g[N - 1] : 0.f);
+          } else {
+            // value = sum_k0 w0[k0] * ( sum_k1 w1[k1] * ( sum_k2 w2[k2] * c[k2][k1][k0] ) )  (Interpolations.jl:304-316)
+            float val = 0.f;
 #pragma unroll
-          for (int k0 = 0; k0 < L; ++k0) {
-            float v0 = 0.f;
+            for (int k0 = 0; k0 < L; ++k0) {
+              float v0 = 0.f;
 #pragma unroll
-            for (int k1 = 0; k1 < L; ++k1) {
-              float v1;
-              if (N == 2) {
-                v1 = tb[k1 * TC::PX + k0];
-              } else {
-                v1 = 0.f;
+              for (int k1 = 0; k1 < L; ++k1) {
+                float v1;
+                if (N == 2) {
+                  v1 = tb[k1 * TC::PX + k0];
+                } else {
+                  v1 = 0.f;
 #pragma unroll
-                for (int k2 = 0; k2 < L; ++k2) {
-                  const float t2 = ax[N - 1].wv[k2] * tb[(k2 * TC::TY + k1) * TC::PX + k0];
-                  v1 = k2 == 0 ? t2 : t2 + v1;
+                  for (int k2 = 0; k2 < L; ++k2) {
+                    const float t2 = ax[N - 1].wv[k2] * tb[(k2 * TC::TY + k1) * TC::PX + k0];
+                    v1 = k2 == 0 ? t2 : t2 + v1;
+                  }
                 }
+                const float t1 = ax[1].wv[k1] * v1;
+                v0 = k1 == 0 ? t1 : t1 + v0;
               }
-              const float t1 = ax[1].wv[k1] * v1;
-              v0 = k1 == 0 ? t1 : t1 + v0;
+              const float t0 = ax[0].wv[k0] * v0;
+              val = k0 == 0 ? t0 : t0 + val;
             }
-            const float t0 = ax[0].wv[k0] * v0;
-            val = k0 == 0 ? t0 : t0 + val;
+            *reinterpret_cast<float2 *>(&wst[lane * kRBP + r]) = make_float2(q4.w, val);
           }
-          *reinterpret_cast<float2 *>(&wst[lane * kRBP + r]) = make_float2(q4.w, val);
         }
       }
       __syncwarp();
@@ -856,8 +915,14 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
       for (int j = 0; j < kClasses / 4; ++j) {
         const int c = 4 * j + (lane >> 3), r = lane & 7;
         if (r0 + r < sm.ccnt[c]) {
-          const float2 v = *reinterpret_cast<const float2 *>(&wst[c * kRBP + r]);
-          res[sm.cbeg[c] + r0 + r] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+          if constexpr (GRAD) {
+            const float4 v = wst[c * kRBP + r];
+            res[sm.cbeg[c] + r0 + r] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                                                  __float_as_uint(v.w));
+          } else {
+            const float2 v = *reinterpret_cast<const float2 *>(&wst[c * kRBP + r]);
+            res[sm.cbeg[c] + r0 + r] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+          }
         }
       }
       __syncwarp();
@@ -896,8 +961,9 @@ static OrdLayout ord_layout(long long nq, long long nfinal, long long nbricks, l
   Lo.cursor1 = take((size_t)ngroups * 4);
   Lo.chunk_start = take((size_t)(ngroups + 1) * 4);
   Lo.item_start = take((size_t)(nbricks + 1) * 4);
-  Lo.cursorA = take((size_t)(((nq + (1LL << kShiftA) - 1) >> kShiftA) + 1) * 4);
-  Lo.cursorB = take((size_t)(((nq + (1LL << kShiftB) - 1) >> kShiftB) + 1) * 4);
+  Lo.cursorA = take((size_t)(((nq + (1LL << Uns<true>::SA) - 1) >> Uns<true>::SA) + 1) * 4);  // gradient mode: the
+  Lo.cursorB = take((size_t)(((nq + (1LL << Uns<true>::SB) - 1) >> Uns<true>::SB) + 1) * 4);  // smaller shifts
+
   Lo.total = off;
   return Lo;
 }
@@ -938,13 +1004,15 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
   return true;
 }
 
-template <int N, int DEG>
-static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scratch, size_t scratch_bytes,
+template <int N, int DEG, bool GRAD>
+static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out, void *scratch, size_t scratch_bytes,
                        cudaStream_t st, bool *done) {
+  using U = Uns<GRAD>;
+  using Rec = typename U::Rec;
   *done = false;
   OrdGeom G;
   if (!ord_geometry<N, DEG>(P, D, G)) return 0;
-  if (P.nq > 0xfffffff0LL) return 0;
+  if (P.nq > (GRAD ? 0x7ffffff0LL : 0xfffffff0LL)) return 0;  // level A has at most 512 bins of 2^SA results
   const OrdLayout Lo = ord_layout(P.nq, G.nfinal, G.nbricks, G.ngroups);
   if (!scratch || scratch_bytes < Lo.total || ((uintptr_t)scratch % 256) != 0) return 0;
   unsigned char *sb = reinterpret_cast<unsigned char *>(scratch);
@@ -959,23 +1027,26 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
   pl.item_start = reinterpret_cast<unsigned *>(sb + Lo.item_start);
   pl.cursorA = reinterpret_cast<unsigned *>(sb + Lo.cursorA);
   pl.cursorB = reinterpret_cast<unsigned *>(sb + Lo.cursorB);
-  // results {q, value}: rec1 is dead after split 2 (two 8-byte arrays fit in it), rec2 after the evaluation
-  uint2 *res = reinterpret_cast<uint2 *>(rec1);
-  uint2 *resA = res + P.nq;
-  uint2 *resB = reinterpret_cast<uint2 *>(rec2);
+  // result records: rec1 is dead after split 2, rec2 after the evaluation.  Values (8 bytes): res and resA share rec1,
+  // resB is rec2.  Gradients (16 bytes): res = rec1, resA = rec2, resB = rec1 again.
+  Rec *res = reinterpret_cast<Rec *>(rec1);
+  Rec *resA = GRAD ? reinterpret_cast<Rec *>(rec2) : res + P.nq;
+  Rec *resB = GRAD ? reinterpret_cast<Rec *>(rec1) : reinterpret_cast<Rec *>(rec2);
 
   const int sms = sm_count(dev);
   const long long per = (long long)kScanBlock * kScanPer;
   const long long nsb = (G.nfinal + per - 1) / per;
-  constexpr size_t smem16 = sizeof(SplitSmem<float4, kChunk16>), smem8 = sizeof(SplitSmem<uint2, kChunk8>);
+  constexpr size_t smem16 = sizeof(SplitSmem<float4, kChunk16>), smemU = sizeof(SplitSmem<Rec, U::S>);
   constexpr size_t smem_eval = sizeof(EvalSmem<N, DEG>);
+  constexpr int smem_place = (4 << U::SB) * (GRAD ? N : 1);
   static_assert(smem_eval <= 227 * 1024, "evaluation tile does not fit shared memory");
+  static_assert(smem_place <= 227 * 1024, "placement window does not fit shared memory");
   B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 << kShiftB)));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_place_kernel<GRAD, GRAD ? N : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_place));
 
   B200_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)(G.nfinal + 1) * 4, st));
   const int cblocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sms * 16);
@@ -988,7 +1059,7 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
     scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)nsb);
     scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums, start);
-    ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, pl);
+    ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, U::SA, U::SB, pl);
   }
   const int sblocks = sms * 2;
   {
@@ -1000,24 +1071,26 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *scra
     ord_split2_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
   }
   {
-    StageScope sc("ord_eval", st);
-    ord_eval_kernel<N, DEG><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
+    StageScope sc(GRAD ? "ord_eval_gradient" : "ord_eval", st);
+    ord_eval_kernel<N, DEG, GRAD><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
   }
-  const uint2 *last = res;
-  if (P.nq > (1LL << kShiftA)) {
+  const Rec *last = res;
+  if (P.nq > (1LL << U::SA)) {
     StageScope sc("ord_unsortA", st);
-    ord_unsort_kernel<0><<<sblocks, kSplitThreads, smem8, st>>>(res, P.nq, pl.cursorA, resA);
+    ord_unsort_kernel<0, GRAD><<<sblocks, kSplitThreads, smemU, st>>>(res, P.nq, pl.cursorA, resA);
     count_launch();
     last = resA;
+  } else if (GRAD) {
+    resB = reinterpret_cast<Rec *>(rec2);  // level A skipped: res (rec1) is the input of level B
   }
   {
     StageScope sc("ord_unsortB", st);
-    ord_unsort_kernel<1><<<sblocks, kSplitThreads, smem8, st>>>(last, P.nq, pl.cursorB, resB);
+    ord_unsort_kernel<1, GRAD><<<sblocks, kSplitThreads, smemU, st>>>(last, P.nq, pl.cursorB, resB);
   }
-  const long long nwin = (P.nq + (1LL << kShiftB) - 1) >> kShiftB;
+  const long long nwin = (P.nq + (1LL << U::SB) - 1) >> U::SB;
   {
     StageScope sc("ord_place", st);
-    ord_place_kernel<<<(unsigned)nwin, 1024, (4 << kShiftB), st>>>(resB, P.nq, reinterpret_cast<float *>(P.out_value));
+    ord_place_kernel<GRAD, GRAD ? N : 1><<<(unsigned)nwin, 1024, smem_place, st>>>(resB, P.nq, reinterpret_cast<float *>(out));
   }
   count_launch(10);
   B200_CUDA_OK(cudaGetLastError());
@@ -1049,10 +1122,12 @@ extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64
   return ord_layout(nq, nbricks * kClasses, nbricks, kMaxBins).total + 256;
 }
 
-extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
-                                   int64_t nq, void *out_value, int64_t *first_oob, void *scratch,
-                                   size_t scratch_bytes, void *stream) {
-  if (!d || !coefs || !coords || !out_value) B200_FAIL(B200ITP_E_BADARG, "eval_sorted: null pointer");
+static int eval_sorted_common(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords, int64_t nq,
+                              void *out_value, void *out_grad, int64_t *first_oob, void *scratch, size_t scratch_bytes,
+                              void *stream) {
+  void *out = out_value ? out_value : out_grad;
+  const bool grad = out_value == nullptr;
+  if (!d || !coefs || !coords || !out) B200_FAIL(B200ITP_E_BADARG, "eval_sorted: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   int deg = 0;
   bool plain = false;
@@ -1062,11 +1137,11 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
   void *flag = nullptr;
   int rc = scratch_get(dev, 2, 256, &flag);
   if (rc) return rc;
-  rc = fill_eval_params_public(d, coefs, coords, nq, out_value, (unsigned long long *)flag, P, &deg, &plain);
+  rc = fill_eval_params_public(d, coefs, coords, nq, out, (unsigned long long *)flag, P, &deg, &plain);
   if (rc) return rc;
   bool done = false;
   // The ordered pipeline pays off when the coefficient array does not fit the L2 (measured: 4096^2 Float32, 64 MiB:
-  // direct 36 vs ordered 20 Gevals/s; 8192^2, 256 MiB: 20 vs 21; 512^3, 512 MiB: 2.1 vs 20).
+  // direct 36 vs ordered 20 Gevals/s; 8192^2, 256 MiB: 20 vs 21; 512^3, 512 MiB: 2.1 vs 23).
   long long coef_bytes = 4;
   for (int i = 0; i < d->ndims && i < B200ITP_MAX_DIMS; ++i) coef_bytes *= d->size[i];
   if (plain && nq >= g_sorted_min_queries && coef_bytes >= g_sorted_min_coef_bytes &&
@@ -1082,10 +1157,18 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
         sbytes -= mis;
       }
     }
-    if (d->ndims == 3 && deg == 3) rc = run_ordered<3, 3>(dev, P, d, sp, sbytes, st, &done);
-    if (d->ndims == 3 && deg == 2) rc = run_ordered<3, 2>(dev, P, d, sp, sbytes, st, &done);
-    if (d->ndims == 2 && deg == 3) rc = run_ordered<2, 3>(dev, P, d, sp, sbytes, st, &done);
-    if (d->ndims == 2 && deg == 2) rc = run_ordered<2, 2>(dev, P, d, sp, sbytes, st, &done);
+    const int key = d->ndims * 100 + deg * 10 + (grad ? 1 : 0);
+    switch (key) {
+      case 330: rc = run_ordered<3, 3, false>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 320: rc = run_ordered<3, 2, false>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 230: rc = run_ordered<2, 3, false>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 220: rc = run_ordered<2, 2, false>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 331: rc = run_ordered<3, 3, true>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 321: rc = run_ordered<3, 2, true>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 231: rc = run_ordered<2, 3, true>(dev, P, d, out, sp, sbytes, st, &done); break;
+      case 221: rc = run_ordered<2, 2, true>(dev, P, d, out, sp, sbytes, st, &done); break;
+      default: break;
+    }
     if (rc) return rc;
     if (done) {
       g_ordered_calls.fetch_add(1, std::memory_order_relaxed);
@@ -1099,5 +1182,19 @@ extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *c
     }
   }
   // outside the ordered path's scope: same results from the direct kernel
-  return b200itp_eval(dev, d, coefs, coords, nq, out_value, nullptr, first_oob, nullptr, nullptr, stream);
+  return b200itp_eval(dev, d, coefs, coords, nq, out_value, out_grad, first_oob, nullptr, nullptr, stream);
+}
+
+extern "C" int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+                                   int64_t nq, void *out_value, int64_t *first_oob, void *scratch,
+                                   size_t scratch_bytes, void *stream) {
+  if (!out_value) B200_FAIL(B200ITP_E_BADARG, "eval_sorted: null output pointer");
+  return eval_sorted_common(dev, d, coefs, coords, nq, out_value, nullptr, first_oob, scratch, scratch_bytes, stream);
+}
+
+extern "C" int b200itp_gradient_sorted(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+                                       int64_t nq, void *out_grad, int64_t *first_oob, void *scratch,
+                                       size_t scratch_bytes, void *stream) {
+  if (!out_grad) B200_FAIL(B200ITP_E_BADARG, "gradient_sorted: null output pointer");
+  return eval_sorted_common(dev, d, coefs, coords, nq, nullptr, out_grad, first_oob, scratch, scratch_bytes, stream);
 }

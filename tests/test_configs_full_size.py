@@ -97,6 +97,15 @@ def test_c3_tricubic_periodic_512_f32(pkg, orc):
     assert torch.equal(v[:k], itp(*[c[:k] for c in coords]))          # ordered pipeline == direct kernel
     assert torch.equal(v[-k:], itp(*[c[-k:] for c in coords]))
     _sample_check(m, orc, itp, itp, coords, grad=True)
+    # gradients of 5*10^7 queries through the ordered pipeline == the direct kernel's
+    kg = 50_000_000
+    n1 = L.b200itp_eval_sorted_ordered_calls()
+    gs = m.gradient_sorted(itp, *[c[:kg] for c in coords])
+    assert L.b200itp_eval_sorted_ordered_calls() == n1 + 1
+    kd = 4_000_000
+    assert torch.equal(gs[:kd], m.gradient(itp, *[c[:kd] for c in coords]))
+    assert torch.equal(gs[-kd:], m.gradient(itp, *[c[kg - kd:kg] for c in coords]))
+    del gs
     # checksum of checksums: a permutation of the queries permutes the results
     perm = torch.randperm(1 << 22, device="cuda", generator=g)
     a = m.evaluate_sorted(itp, *[c[: 1 << 22] for c in coords])

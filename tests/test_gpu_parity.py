@@ -397,6 +397,10 @@ def test_ordered_evaluation_is_bit_identical(pkg, shape):
         b = m.evaluate_sorted(itp, *coords).cpu().numpy()
         assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "the ordered pipeline must serve this call"
         assert np.array_equal(a, b), it
+        ga = m.gradient(itp, *coords).cpu().numpy()
+        gb = m.gradient_sorted(itp, *coords).cpu().numpy()
+        assert L.b200itp_eval_sorted_ordered_calls() == n0 + 2, "the ordered pipeline must serve the gradient call"
+        assert ga.shape == gb.shape == (nq, len(shape)) and np.array_equal(ga, gb), it
         bad = [c.copy() for c in coords]
         bad[0][12345] = np.float32(float(itp.bounds()[0][1]) + 1.0)
         with pytest.raises(m.BoundsError):
@@ -496,4 +500,8 @@ def test_ordered_evaluation_fuzz(pkg):
         b = m.evaluate_sorted(itp, *coords).cpu().numpy()
         assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, (case, shape, it)
         assert np.array_equal(a, b, equal_nan=True), (case, shape, it, nq, kind)
+        if case % 2 == 0:
+            ga = m.gradient(itp, *coords).cpu().numpy()
+            gb = m.gradient_sorted(itp, *coords).cpu().numpy()
+            assert np.array_equal(ga, gb, equal_nan=True), (case, shape, it, nq, kind)
     L.b200itp_eval_sorted_set_min_queries(1 << 20)
