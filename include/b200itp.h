@@ -214,6 +214,14 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
                  int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
                  int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
 
+/* Replaces `Base.copy(::Broadcasted)` of `Interpolations.hessian.(Ref(itp), xs...)` (src/b-splines/indexing.jl:37-41,
+ * 114-144,201-229; src/scaling/scaling.jl:150-160; src/extrapolation/extrapolation.jl:84-90): `out_hess` receives
+ * nq*ndims*ndims elements of b200itp_out_dtype(d), the full symmetric matrix per query (SMatrix layout).  Extrapolation
+ * wrappers evaluate in bounds only: a query outside is reported through `first_oob` like a BoundsError (the reference
+ * raises "extrapolation of hessian not yet implemented"); FilledExtrapolation has no hessian method (E_UNSUPPORTED). */
+B200ITP_API int b200itp_hessian(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords,
+                    int64_t nq, void *out_hess, int64_t *first_oob, void *stream);
+
 /* Element type of the outputs of b200itp_eval for this descriptor:
  * promote(coordinate type after all wrappers, eltype(coefs)). <0 on invalid descriptor. */
 B200ITP_API int b200itp_out_dtype(const b200itp_desc *d);

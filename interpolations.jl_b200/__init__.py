@@ -8,7 +8,7 @@ from .flags import (BSpline, Cubic, Flat, Free, Line, Linear, Natural, OnCell, O
                     Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
-                   bounds, evaluate_debug, evaluate_from_host, evaluate_sorted, extrapolate, gradient, gradient_sorted, interpolate, lbounds, out_dtype,
+                   bounds, evaluate_debug, evaluate_from_host, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, lbounds, out_dtype,
                    prefilter_, scale, ubounds, value_and_gradient)
 from . import _lib, parallel
 
@@ -17,6 +17,6 @@ __all__ = [
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
     "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host",
     "evaluate_sorted",
-    "extrapolate", "gradient", "gradient_sorted", "interpolate", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
+    "extrapolate", "gradient", "gradient_sorted", "hessian", "interpolate", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
     "value_and_gradient",
 ]

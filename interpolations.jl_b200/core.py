@@ -619,6 +619,40 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
     return out
 
 
+def hessian(itp, *xs):
+    """`Interpolations.hessian.(Ref(itp), xs...)`: trailing axes (N, N) hold the symmetric matrix of every query
+    (indexing.jl:37-41, scaling.jl:150-160; extrapolated interpolants: in bounds only, extrapolation.jl:84-90)."""
+    torch = _torch()
+    L = _lib.lib()
+    coords, shape, dt = _prepare_coords(itp, xs)
+    nq = coords[0].numel() if coords else 0
+    N = itp.ndims
+    npdt = np.float32 if dt == torch.float32 else np.float64
+    D = itp.descriptor(npdt)
+    # output type: the in-bounds path never meets the extrapolation bounds, so they do not widen Float32 coordinates
+    Dn = itp.descriptor(npdt)
+    Dn.etp_kind = 0
+    ocode = L.b200itp_out_dtype(C.byref(Dn))
+    if ocode < 0:
+        raise ValueError("invalid descriptor")
+    odt = torch.float32 if ocode == F32 else torch.float64
+    dev = itp.device_index
+    coefs = itp.coefficients()
+    foob = C.c_int64(-1)
+    with torch.cuda.device(dev):
+        out = torch.empty(nq * N * N, dtype=odt, device=coefs.device)
+        if nq > 0:
+            ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in coords])
+            rc = L.b200itp_hessian(dev, C.byref(D), C.c_void_p(coefs.data_ptr()), ptrs, nq, C.c_void_p(out.data_ptr()),
+                                   C.byref(foob), _stream_ptr(dev))
+            _lib.check(rc, "b200itp_hessian")
+    if foob.value >= 0:
+        q = foob.value
+        xq = tuple(float(c[q].item()) for c in coords)
+        raise BoundsError(f"attempt to access the hessian of {itp!r} at index {xq}")
+    return out.reshape(shape + (N, N))
+
+
 def gradient_sorted(itp, *xs):
     """`Interpolations.gradient.(Ref(itp), xs...)` through the ordered pipeline (results in the caller's order, identical
     to `gradient`)."""

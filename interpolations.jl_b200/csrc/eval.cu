@@ -104,6 +104,7 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
       if (!(D->range_step[d] > 0)) B200_FAIL(B200ITP_E_BADARG, "eval: ranges must have positive steps (scaling.jl:48)");
       P.rfirst[d] = D->range_first[d];
       P.rstep[d] = D->range_step[d];
+      P.range_f32[d] = D->range_tag[d] == B200ITP_TAG_F32;
     }
     P.etp_lo[d] = D->etp_lo[d];
     P.etp_hi[d] = D->etp_hi[d];
@@ -145,7 +146,7 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
-  StageScope sc(mode == 0 ? "eval_direct_value" : "eval_direct_gradient", st);
+  StageScope sc(mode == 0 ? "eval_direct_value" : (mode == 1 ? "eval_direct_gradient" : "eval_direct_hessian"), st);
   int rc;
   if (cf32 && xf32 && wf32)
     rc = launch_eval_combo<float, float, float>(P, deg, mode, blocks, st);
@@ -238,6 +239,51 @@ extern "C" int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, c
                             uint32_t *dbg_branch, void *stream) {
   return eval_common(dev, d, coefs, coords, nq, out_value, out_grad, first_oob, dbg_index, dbg_branch, nullptr,
                      (cudaStream_t)stream);
+}
+
+extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coefs, const void *const *coords, int64_t nq,
+                               void *out_hess, int64_t *first_oob, void *stream) {
+  if (!Din || !coefs || !coords || !out_hess) B200_FAIL(B200ITP_E_BADARG, "hessian: null pointer");
+  if (nq < 0) B200_FAIL(B200ITP_E_BADARG, "hessian: negative query count");
+  if (Din->etp_kind == B200ITP_ETP_FILL)
+    B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: FilledExtrapolation has no hessian method in the reference (filled.jl:75)");
+  if (Din->etp_kind != B200ITP_ETP_NONE && Din->etp_kind != B200ITP_ETP_FLAGS) B200_FAIL(B200ITP_E_BADARG, "hessian: bad etp_kind");
+  // hessian(etp, x) is hessian(parent(etp), x) in bounds and an error outside (extrapolation.jl:84-90): exactly the
+  // unwrapped interpolant, including its types (the extrapolation bounds never meet the coordinates)
+  b200itp_desc Dcopy = *Din;
+  Dcopy.etp_kind = B200ITP_ETP_NONE;
+  const b200itp_desc *D = &Dcopy;
+  Chain c;
+  int rc = derive_chain(D, c);
+  if (rc) B200_FAIL(rc, "hessian: invalid descriptor");
+  if (!c.homogeneous) B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: mixed per-axis promotion is not on the hot path");
+  for (int d = 0; d < D->ndims; ++d)
+    if (!coords[d]) B200_FAIL(B200ITP_E_BADARG, "hessian: null coordinate array %d", d);
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "hessian: cannot select device %d", dev);
+  if (first_oob) *first_oob = -1;
+  if (nq == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  void *flag = nullptr;
+  rc = scratch_get(dev, 2, 256, &flag);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
+  // the hessian of an Extrapolation is the parent's, in bounds only: the chain of the in-bounds gradient path
+  // (no extrapolation-stage promotion) decides the output type
+  EvalParams P;
+  const int blocks = (int)std::min<int64_t>((nq + 255) / 256, (int64_t)sm_count(dev) * 32);
+  rc = fill_params(D, c, coefs, coords, nq, nullptr, nullptr, nullptr, nullptr, (unsigned long long *)flag, P);
+  if (rc) return rc;
+  P.out_hess = out_hess;
+  rc = dispatch(D, c, P, 2, blocks, st);
+  if (rc) return rc;
+  if (first_oob) {
+    unsigned long long h = ~0ULL;
+    B200_CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    *first_oob = h == ~0ULL ? -1 : (int64_t)h;
+  }
+  return 0;
 }
 
 namespace b200itp {

@@ -51,6 +51,8 @@ struct EvalParams {
   const void *coefs;
   void *out_value;
   void *out_grad;
+  void *out_hess;     // nq * N * N, the full symmetric matrix per query
+  int range_f32[4];   // eltype(ranges[d]) == Float32: steps[i] * steps[j] is rounded to Float32 (scaling.jl:157-160)
   int *dbg_index;
   unsigned *dbg_branch;
   unsigned long long *first_oob;
@@ -167,7 +169,7 @@ template <int DEG, typename TW>
 struct AxisTaps {
   static constexpr int LMAX = DEG == 0 ? 4 : DEG + 1;
   int pos[LMAX];  // 0-based position along the axis of the coefficient array
-  TW wv[LMAX], wg[LMAX];
+  TW wv[LMAX], wg[LMAX], wh[LMAX];  // value / gradient / hessian weights
   int L;
   int first;  // parent index (1-based, before any periodic wrap) of the first tap
   bool edge;
@@ -218,6 +220,11 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       A.wg[1] = TW(-2) * dx + TW(1.5) * x2;
       A.wg[2] = TW(2) * omd - TW(1.5) * xc2;
       A.wg[3] = TW(0.5) * x2;
+      // hessian_weights cubic.jl:79
+      A.wh[0] = omd;
+      A.wh[1] = TW(3) * dx - TW(2);
+      A.wh[2] = TW(3) * omd - TW(2);
+      A.wh[3] = dx;
     }
   } else if (deg == B200ITP_QUADRATIC) {
     // quadratic.jl:39-43, roundbounds indexing.jl:172-177
@@ -240,10 +247,14 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
       A.wg[0] = a;
       A.wg[1] = TW(-2) * dx;
       A.wg[2] = b;
+      A.wh[0] = TW(1);  // quadratic.jl:55
+      A.wh[1] = TW(-2);
+      A.wh[2] = TW(1);
     }
     if (DEG == 0) {
       A.wv[3] = TW(0);
       A.wg[3] = TW(0);
+      A.wh[3] = TW(0);
     }
   } else {  // linear.jl:43-58
     TW f = s_floor<TW>(x);
@@ -259,10 +270,13 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
     if (GRAD) {
       A.wg[0] = TW(-1);
       A.wg[1] = TW(1);
+      A.wh[0] = TW(0);  // linear.jl:58
+      A.wh[1] = TW(0);
     }
     if (DEG == 0) {
       A.wv[2] = A.wv[3] = TW(0);
       A.wg[2] = A.wg[3] = TW(0);
+      A.wh[2] = A.wh[3] = TW(0);
     }
   }
   A.first = first;
@@ -330,6 +344,34 @@ struct Reduce {
   }
 };
 
+// One hessian component: the reference's nested reduction (Interpolations.jl:304-316) with, per axis, value (0),
+// gradient (1) or hessian (2) weights (indexing.jl:114-144).
+template <int N, int DEG, typename TC, typename TW, int D>
+struct ReduceSel {
+  using TA = typename Promote<TW, TC>::type;
+  static constexpr int LMAX = AxisTaps<DEG, TW>::LMAX;
+  __device__ __forceinline__ static TA run(const EvalParams &P, const AxisTaps<DEG, TW> (&ax)[N], const int (&sel)[N],
+                                           const TC *base) {
+    const AxisTaps<DEG, TW> &A = ax[D];
+    TA val = TA(0);
+#pragma unroll
+    for (int k = 0; k < LMAX; ++k) {
+      if (DEG != 0 || k < A.L) {
+        const TC *b = base + (long long)A.pos[k] * P.stride[D];
+        TA vk;
+        if constexpr (D == N - 1) {
+          vk = (TA)__ldg(b);
+        } else {
+          vk = ReduceSel<N, DEG, TC, TW, D + 1>::run(P, ax, sel, b);
+        }
+        const TA w = (TA)(sel[D] == 0 ? A.wv[k] : (sel[D] == 1 ? A.wg[k] : A.wh[k]));
+        val = k == 0 ? w * vk : w * vk + val;
+      }
+    }
+    return val;
+  }
+};
+
 // Value-only fast path for Float32 coefficients whose axis-1 taps are adjacent in memory: every
 // (axis 2..N) row is fetched with two aligned 128-bit loads instead of 3-4 scalar loads, then the
 // reduction runs in the reference order from registers.
@@ -369,6 +411,30 @@ __device__ __forceinline__ void store_out(void *p, long long i, TO v, int out_f6
 
 // B-spline stage of one query: positions, weights (type TWW) and the nested reduction; results are
 // widened (exactly) to TAO.
+// hessian of the bare B-spline at xl: N*N entries (symmetric), components evaluated in the reference's order
+template <int N, int DEG, typename TC, typename TWW, typename TAO>
+__device__ __forceinline__ void bspline_hessian(const EvalParams &P, const TC *coefs, const TWW (&xl)[N],
+                                                TAO (&h)[N * N], int (&first_idx)[N], unsigned &br) {
+  AxisTaps<DEG, TWW> ax[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    axis_setup<DEG, TWW, true>(P, d, xl[d], ax[d]);
+    first_idx[d] = ax[d].pos[0] + P.coef_first[d];
+    if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) {
+      int sel[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) sel[d] = (d == i && d == j) ? 2 : ((d == i || d == j) ? 1 : 0);
+      const TAO v = (TAO)ReduceSel<N, DEG, TC, TWW, 0>::run(P, ax, sel, coefs);
+      h[i * N + j] = v;
+      h[j * N + i] = v;
+    }
+}
+
 template <int N, int DEG, typename TC, typename TWW, typename TAO>
 __device__ __forceinline__ void bspline_stage(const EvalParams &P, const TC *coefs, const TWW (&xl)[N], bool need_grad,
                                               TAO &val_out, TAO (&grad_out)[N], int (&first_idx)[N], unsigned &br) {
@@ -440,7 +506,8 @@ __device__ __forceinline__ void bspline_stage(const EvalParams &P, const TC *coe
   val_out = (TAO)val;
 }
 
-// MODE 0: values; MODE 1: gradients
+// MODE 0: values; MODE 1: gradients; MODE 2: hessians (in bounds only: indexing.jl:37-41, scaling.jl:150-155,
+// extrapolation.jl:84-90)
 template <int N, int DEG, typename TC, typename TX, typename TW, int MODE>
 __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalParams P) {
   using TA = typename Promote<TW, TC>::type;
@@ -491,7 +558,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalP
         }
         threw = threw || th;
       }
-      if (MODE == 1 && inb) use_x = true;
+      if (MODE >= 1 && inb) use_x = true;
+      if (MODE == 2) threw = !inb;  // "extrapolation of hessian not yet implemented": reported like a BoundsError
     } else {
 #pragma unroll
       for (int d = 0; d < N; ++d) xs[d] = (TW)x[d];
@@ -533,8 +601,31 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalP
       //      only widening came from the extrapolation bounds is computed in TX, as the reference does)
       const bool need_grad = MODE == 1 || (moved && P.any_line);
       bool narrow = false;
-      if constexpr (MODE == 1 && sizeof(TX) != sizeof(TW)) narrow = use_x && !P.w_wide_x;
-      if (narrow) {
+      if constexpr (MODE >= 1 && sizeof(TX) != sizeof(TW)) narrow = use_x && !P.w_wide_x;
+      if constexpr (MODE == 2) {
+        TA h[N * N];
+        if (narrow) {
+          if constexpr (sizeof(TX) != sizeof(TW)) {
+            TX xn[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) xn[d] = (TX)xl[d];
+            bspline_hessian<N, DEG, TC, TX, TA>(P, coefs, xn, h, first_idx, br);
+          }
+        } else {
+          bspline_hessian<N, DEG, TC, TW, TA>(P, coefs, xl, h, first_idx, br);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            TA v = h[i * N + j];
+            if (P.has_scale) {  // rescale_hessian_components scaling.jl:157-160: h ./ (steps .* steps')
+              const double prod = P.range_f32[i] ? (double)((float)P.rstep[i] * (float)P.rstep[j]) : P.rstep[i] * P.rstep[j];
+              v = v / (TA)prod;
+            }
+            store_out<TA>(P.out_hess, (q * N + i) * N + j, v, P.out_f64);
+          }
+      } else if (narrow) {
         if constexpr (MODE == 1 && sizeof(TX) != sizeof(TW)) {
           TX xn[N];
 #pragma unroll
@@ -587,7 +678,12 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ EvalP
       atomicMin(P.first_oob, (unsigned long long)q);
     }
     // ---- outputs
-    if (MODE == 0) {
+    if (MODE == 2) {
+      if (threw) {
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) store_out<double>(P.out_hess, q * N * N + k, nan(""), P.out_f64);
+      }
+    } else if (MODE == 0) {
       if (threw) {
         store_out<double>(P.out_value, q, nan(""), P.out_f64);
       } else if (filled) {

@@ -14,7 +14,8 @@ int launch_eval_combo(const EvalParams &P, int deg, int mode, int blocks, cudaSt
   }
 #define B200_CASES_N(NN) \
   B200_CASE(NN, 0, 0) B200_CASE(NN, 1, 0) B200_CASE(NN, 2, 0) B200_CASE(NN, 3, 0) \
-  B200_CASE(NN, 0, 1) B200_CASE(NN, 1, 1) B200_CASE(NN, 2, 1) B200_CASE(NN, 3, 1)
+  B200_CASE(NN, 0, 1) B200_CASE(NN, 1, 1) B200_CASE(NN, 2, 1) B200_CASE(NN, 3, 1) \
+  B200_CASE(NN, 0, 2) B200_CASE(NN, 1, 2) B200_CASE(NN, 2, 2) B200_CASE(NN, 3, 2)
   B200_CASES_N(1)
   B200_CASES_N(2)
   B200_CASES_N(3)

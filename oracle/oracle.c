@@ -157,7 +157,7 @@ typedef struct {
   int64_t pos[4]; /* 0-based position of each tap along this axis of the coefficient array */
   int base;       /* first tap in the reference's (1-based parent) index space */
   int edge;       /* the degree's edge rule fired */
-  tv wv[4], wg[4];
+  tv wv[4], wg[4], wh[4]; /* value / gradient / hessian weights */
 } axis_taps;
 
 /* modrange(x, 1:n) = mod(x - 1, n) + 1   (utils.jl:7) */
@@ -220,6 +220,11 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
     A->wg[1] = tv_add(tv_mul(mk(-2.0, t), dx), tv_mul(r32, x2));
     A->wg[2] = tv_sub(tv_mul(mk(2.0, t), omd), tv_mul(r32, xc2));
     A->wg[3] = tv_mul(r12, x2);
+    /* hessian_weights cubic.jl:79: (1-dx, 3*dx-2, 3*(1-dx)-2, dx) */
+    A->wh[0] = omd;
+    A->wh[1] = tv_sub(tv_mul(mk(3.0, t), dx), mk(2.0, t));
+    A->wh[2] = tv_sub(tv_mul(mk(3.0, t), omd), mk(2.0, t));
+    A->wh[3] = dx;
   } else if (deg == B200ITP_QUADRATIC) {
     /* quadratic.jl:39-43 ; roundbounds indexing.jl:172-177: ifelse(x < u + half(u), floor(x+h), ceil(x+h)-1) */
     double xh = rnd(t, x.v + 0.5), xm;
@@ -247,6 +252,10 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
     A->wg[0] = a;
     A->wg[1] = tv_mul(mk(-2.0, t), dx);
     A->wg[2] = b;
+    /* hessian_weights quadratic.jl:55: (1, -2, 1) of dx's type */
+    A->wh[0] = mk(1.0, t);
+    A->wh[1] = mk(-2.0, t);
+    A->wh[2] = mk(1.0, t);
   } else { /* linear.jl:43-58 */
     double f = floor(x.v);
     if (x.v == (double)n) {
@@ -266,6 +275,8 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
     A->wv[1] = dx;
     A->wg[0] = mk(-1.0, t);
     A->wg[1] = mk(1.0, t);
+    A->wh[0] = mk(0.0, t); /* linear.jl:58 */
+    A->wh[1] = mk(0.0, t);
   }
 }
 
@@ -563,6 +574,87 @@ int orc_eval(const b200itp_desc *D, const void *coefs, const void *const *coords
       for (int d = 0; d < N; d++) dbg_index[q * N + d] = base[d];
     if (dbg_branch) dbg_branch[q] = br;
     if (threw) {
+#pragma omp critical
+      if (foob < 0 || q < foob) foob = q;
+    }
+  }
+  if (first_oob) *first_oob = foob;
+  return 0;
+}
+
+/* hessian(itp, x...) (indexing.jl:37-41): components in the order of `weightedindexes` (indexing.jl:114-144):
+ * (1,1), (1,2), ..., (1,N), (2,2), ..., (N,N); axis i and j carry gradient weights (hessian weights when i == j),
+ * the others value weights; each component is its own interp_getindex reduction.  Scaled: scaling.jl:150-159,
+ * h ./ (steps .* steps').  Output: the full symmetric N x N matrix (symmatrix, indexing.jl:201-229). */
+static void inner_hess(const b200itp_desc *D, const void *coefs, const tv *x, tv *h /* N*N */) {
+  const int N = D->ndims;
+  tv xl[4];
+  for (int d = 0; d < N; d++) {
+    if (D->has_scale) {
+      tv f = mk(D->range_first[d], D->range_tag[d]), st = mk(D->range_step[d], D->range_tag[d]);
+      tv one = mk(1.0, D->range_tag[d]);
+      tv q = tv_add(tv_div(tv_sub(x[d], f), st), one);
+      int t = tmax(q.t, D->inner_tag[d]);
+      double lo = D->inner_lb[d], hi = D->inner_ub[d];
+      double c = q.v > hi ? rnd(t, hi) : (q.v < lo ? rnd(t, lo) : q.v);
+      xl[d] = mk(c, t);
+    } else {
+      xl[d] = x[d];
+    }
+  }
+  axis_taps ax[4];
+  reduce_ctx C;
+  C.D = D;
+  C.coefs = coefs;
+  C.ax = ax;
+  int64_t s = 1;
+  for (int d = 0; d < N; d++) {
+    axis_setup(D, d, xl[d], &ax[d]);
+    C.stride[d] = s;
+    s *= D->size[d];
+  }
+  C.lt[N] = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
+  for (int d = N - 1; d >= 0; d--) C.lt[d] = tmax(xl[d].t, C.lt[d + 1]);
+  for (int i = 0; i < N; i++)
+    for (int j = i; j < N; j++) {
+      for (int d = 0; d < N; d++)
+        C.w[d] = (d == i && d == j) ? ax[d].wh : ((d == i || d == j) ? ax[d].wg : ax[d].wv);
+      tv v = mk(reduce_level(&C, 0, 0), C.lt[0]);
+      if (D->has_scale) {
+        tv si = mk(D->range_step[i], D->range_tag[i]), sj = mk(D->range_step[j], D->range_tag[j]);
+        v = tv_div(v, tv_mul(si, sj));
+      }
+      h[i * N + j] = v;
+      h[j * N + i] = v;
+    }
+}
+
+/* hessian.(Ref(itp), xs...): out_hess[nq * N * N] doubles already rounded to their Julia type.  Extrapolation
+ * wrappers only evaluate in bounds (extrapolation.jl:84-90: "extrapolation of hessian not yet implemented" is
+ * reported like a BoundsError); FilledExtrapolation has no hessian method. */
+int orc_hessian(const b200itp_desc *D, const void *coefs, const void *const *coords, int64_t nq, double *out_hess,
+                int64_t *first_oob, int nthreads) {
+  const int N = D->ndims;
+  int64_t foob = -1;
+  if (N < 1 || N > 4) return B200ITP_E_BADARG;
+  if (D->etp_kind == B200ITP_ETP_FILL) return B200ITP_E_UNSUPPORTED;
+  const int xt = D->coord_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
+  const double *lb = D->has_scale ? D->outer_lb : D->inner_lb;
+  const double *ub = D->has_scale ? D->outer_ub : D->inner_ub;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t q = 0; q < nq; q++) {
+    tv x[4], h[16];
+    int inb = 1;
+    for (int d = 0; d < N; d++) {
+      const double xv = D->coord_dtype == B200ITP_F32 ? (double)((const float *)coords[d])[q] : ((const double *)coords[d])[q];
+      x[d] = mk(xv, xt);
+      if (!(lb[d] <= xv) || !(xv <= ub[d])) inb = 0;
+    }
+    if (inb) {
+      inner_hess(D, coefs, x, h);
+      for (int k = 0; k < N * N; k++) out_hess[q * N * N + k] = h[k].v;
+    } else {
+      for (int k = 0; k < N * N; k++) out_hess[q * N * N + k] = NAN;
 #pragma omp critical
       if (foob < 0 || q < foob) foob = q;
     }

@@ -183,6 +183,36 @@ def evaluate(itp, *xs, want_value=True, want_grad=False, debug=False, nthreads=1
             bi.reshape(shape + (N,)) if debug else None, br.reshape(shape) if debug else None, foob.value)
 
 
+def hessian(itp, *xs, nthreads=1, fast=False, raise_oob=True):
+    """hessian.(Ref(itp), xs...) on the CPU: array of shape xs.shape + (N, N) (float64 holding numbers already
+    rounded to their Julia type)."""
+    N = itp.ndims
+    arrs = [np.asarray(x) for x in xs]
+    dt = np.float64 if any(a.dtype == np.float64 or a.dtype.kind in "iu" for a in arrs) else np.float32
+    arrs = np.broadcast_arrays(*[a.astype(dt) for a in arrs])
+    shape = arrs[0].shape
+    cs = [np.ascontiguousarray(a.reshape(-1)) for a in arrs]
+    nq = cs[0].size
+    D = itp.descriptor(dt)
+    if D.etp_kind == 1:
+        D.etp_kind = 0  # hessian(etp, x) = hessian(parent(etp), x) in bounds, error outside (extrapolation.jl:84-90)
+    coefs = itp.coefficients()
+    if not isinstance(coefs, np.ndarray):
+        coefs = coefs.cpu().numpy()
+    out = np.empty(nq * N * N, np.float64)
+    ptrs = (C.c_void_p * N)(*[c.ctypes.data for c in cs])
+    foob = C.c_int64(-1)
+    fn = lib(fast).orc_hessian
+    fn.restype = C.c_int
+    rc = fn(C.byref(D), C.c_void_p(coefs.ctypes.data), ptrs, C.c_int64(nq), C.c_void_p(out.ctypes.data), C.byref(foob),
+            C.c_int(nthreads))
+    if rc:
+        raise ValueError(f"orc_hessian rc={rc}")
+    if raise_oob and foob.value >= 0:
+        raise pkg.BoundsError(f"oracle: BoundsError at query {foob.value}")
+    return out.reshape(shape + (N, N))
+
+
 def weights(degree_code, x, n, dtype=np.float64):
     """(value_weights, gradient_weights, first tap index) at coordinate x on an axis 1:n."""
     wv = (C.c_double * 4)()

@@ -505,3 +505,41 @@ def test_ordered_evaluation_fuzz(pkg):
             gb = m.gradient_sorted(itp, *coords).cpu().numpy()
             assert np.array_equal(ga, gb, equal_nan=True), (case, shape, it, nq, kind)
     L.b200itp_eval_sorted_set_min_queries(1 << 20)
+
+
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+def test_hessian_bit_exact(pkg, orc, coef_dtype, coord_dtype):
+    """`Interpolations.hessian.(Ref(itp), xs...)`: bare, scaled and extrapolated (in bounds) interpolants,
+    1-D to 3-D, every degree: == the oracle on the GPU's coefficients; symmetric; quadratic/linear structure; OOB raises."""
+    m = pkg
+    rng = np.random.default_rng(17)
+    specs_ = [m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Cubic(m.Periodic(m.OnCell()))),
+              m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), m.BSpline(m.Linear())]
+    for shape in ((23,), (14, 11), (9, 8, 7)):
+        A = rng.standard_normal(shape).astype(coef_dtype)
+        for it in specs_:
+            itp = m.interpolate(A, it)
+            rngs = [m.jrange(coord_dtype(2), coord_dtype(2) + coord_dtype(0.5) * (n - 1), length=n) for n in shape]
+            for obj in (itp, m.scale(itp, *rngs), m.extrapolate(itp, m.Flat()), m.extrapolate(m.scale(itp, *rngs), m.Line())):
+                bnds = obj.bounds()
+                k = 300
+                coords = []
+                for (l, u) in bnds:
+                    l, u = float(l), float(u)
+                    x = np.concatenate([[l, u, (l + u) / 2], rng.uniform(l, u, k - 3)]).astype(coord_dtype)
+                    x = np.where((x < l) | (x > u), coord_dtype((l + u) / 2), x)  # rounding of the cast at the bounds
+                    coords.append(x)
+                H = m.hessian(obj, *coords).cpu().numpy()
+                host = orc.with_coefs(obj, itp.coefs.cpu().numpy())
+                Ho = orc.hessian(host, *coords)
+                assert H.shape == (k, len(shape), len(shape))
+                assert np.array_equal(H, Ho.astype(H.dtype), equal_nan=True), (shape, it, type(obj).__name__)
+                assert np.array_equal(H, np.swapaxes(H, 1, 2))
+            if it.degree.code == 1:  # Linear: no curvature along an axis (linear.jl:58); mixed terms survive
+                assert not np.diagonal(H, axis1=1, axis2=2).any()
+    itp = m.interpolate(rng.standard_normal((10, 9)).astype(coef_dtype), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))))
+    with pytest.raises(m.BoundsError):
+        m.hessian(m.extrapolate(itp, m.Line()), np.array([0.5], coord_dtype), np.array([3.0], coord_dtype))
+    with pytest.raises(ValueError):
+        m.hessian(m.extrapolate(itp, 0.0), np.array([1.5], coord_dtype), np.array([3.0], coord_dtype))

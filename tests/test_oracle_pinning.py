@@ -419,3 +419,45 @@ def test_multithreaded_oracle_is_bit_identical(orc):
     a = orc.evaluate(itp, *q, want_grad=True, nthreads=1)
     b = orc.evaluate(itp, *q, want_grad=True, nthreads=4, fast=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_hessian_against_gradient_differences_and_exact_polynomials(orc):
+    """`hessian` (indexing.jl:37-41,114-144, cubic.jl:79, quadratic.jl:55, linear.jl:58, scaling.jl:150-160):
+    the reference checks it against ForwardDiff (test/hessian.jl via InterpolationTestUtils.jl:134-143); here against
+    central differences of the (already pinned) gradient, against exact polynomials under Free boundary conditions
+    (test/gradient.jl:95-116 style), and the chain rule of the scaled wrapper."""
+    m = orc.pkg
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((9, 8, 7))
+    eps = 1e-5
+    for it in (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Cubic(m.Periodic(m.OnCell()))),
+               m.BSpline(m.Quadratic(m.Free(m.OnCell())))):
+        itp = orc.interpolate(A, it)
+        q = [rng.uniform(2.2, 5.8, 40) for _ in range(3)]
+        H = orc.hessian(itp, *q)
+        assert np.array_equal(H, np.swapaxes(H, 1, 2))
+        if it.degree.code == 3:  # cubic: C2, central differences of the gradient are accurate everywhere
+            for d in range(3):
+                qp, qm = [c.copy() for c in q], [c.copy() for c in q]
+                qp[d] += eps
+                qm[d] -= eps
+                gp = orc.evaluate(itp, *qp, want_value=False, want_grad=True)[1]
+                gm = orc.evaluate(itp, *qm, want_value=False, want_grad=True)[1]
+                assert np.abs((gp - gm) / (2 * eps) - H[:, d, :]).max() < 1e-7
+    # exact on quadratics: f(x, y) = 2x^2 - 3xy + 0.5y^2 + x - y  ->  H = [[4, -3], [-3, 1]]
+    x = np.arange(1, 11.0)[:, None]
+    y = np.arange(1, 13.0)[None, :]
+    F = 2 * x**2 - 3 * x * y + 0.5 * y**2 + x - y
+    for it in (m.BSpline(m.Quadratic(m.Free(m.OnGrid()))), m.BSpline(m.Cubic(m.Free(m.OnGrid())))):
+        itp = orc.interpolate(F, it)
+        qs = [rng.uniform(1, 10, 30), rng.uniform(1, 12, 30)]
+        H = orc.hessian(itp, *qs)
+        assert np.abs(H - np.array([[4.0, -3.0], [-3.0, 1.0]])).max() < 1e-9
+        # scaled: h ./ (steps .* steps')
+        sitp = m.scale(itp, m.jrange(0.0, 4.5, length=10), m.jrange(-1.0, 4.5, length=12))
+        Hs = orc.hessian(sitp, (qs[0] - 1) * 0.5, (qs[1] - 1) * 0.5 - 1.0)
+        assert np.abs(Hs - np.array([[4.0, -3.0], [-3.0, 1.0]]) / 0.25).max() < 1e-8
+    # Linear: hessian_weights == (0, 0) (Interpolations.jl:361-365 doctest)
+    lin = orc.interpolate(A, m.BSpline(m.Linear()))
+    Hl = orc.hessian(lin, *[rng.uniform(1, 6, 10) for _ in range(3)])
+    assert not np.diagonal(Hl, axis1=1, axis2=2).any()
