@@ -101,7 +101,8 @@ struct OrdGeom {
   int cells[3];  // distinct first-tap indices per axis
   int fmin[3];   // smallest first-tap index (parent index space): -1 for periodic cubic axes (OnCell, x < 1), else 0
   int nbricks;
-  int ngroups;
+  int ngroups;   // groups of kGroupBricks bricks (split 1 bins)
+  int nsuper;    // super-groups of kMaxBins groups: > 1 adds a split level in front (arrays beyond 8192 bricks)
   int nfinal;    // nbricks * kClasses
 };
 
@@ -281,6 +282,8 @@ __global__ void __launch_bounds__(kScanBlock) scan_final_kernel(unsigned *hist, 
 // One CTA: cursors of split 1 (per group), chunk table of split 2 (per group), work items of the
 // evaluation (per brick), cursors of the two unsort levels (exact bin sizes).
 struct OrdPlan {
+  unsigned *cursor0;      // nsuper  (three-level geometry only)
+  unsigned *chunk_mid;    // nsuper + 1 : chunks of the middle split, per super-group
   unsigned *cursor1;      // ngroups
   unsigned *chunk_start;  // ngroups + 1 : split-2 chunks
   unsigned *item_start;   // nbricks + 1 : evaluation work items
@@ -297,12 +300,15 @@ __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restri
   const long long na = (nq + (1LL << shiftA) - 1) >> shiftA, nbw = (nq + (1LL << shiftB) - 1) >> shiftB;
   for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << shiftA);
   for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << shiftB);
-  // split-1 cursors
-  for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[(long long)g * kGroupBricks * kClasses];
-  // two exclusive scans: chunks per group, items per brick
-  for (int pass = 0; pass < 2; ++pass) {
-    const int n = pass == 0 ? G.ngroups : G.nbricks;
-    unsigned *dst = pass == 0 ? pl.chunk_start : pl.item_start;
+  // split cursors: first record of every group / super-group
+  constexpr long long FPG = (long long)kGroupBricks * kClasses;  // final bins per group
+  for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[min((long long)g * FPG, (long long)G.nfinal)];
+  if (G.nsuper > 1)
+    for (int sg = t; sg < G.nsuper; sg += 1024) pl.cursor0[sg] = start[min((long long)sg * kMaxBins * FPG, (long long)G.nfinal)];
+  // exclusive scans: chunks per group, items per brick, chunks per super-group
+  for (int pass = 0; pass < (G.nsuper > 1 ? 3 : 2); ++pass) {
+    const int n = pass == 0 ? G.ngroups : (pass == 1 ? G.nbricks : G.nsuper);
+    unsigned *dst = pass == 0 ? pl.chunk_start : (pass == 1 ? pl.item_start : pl.chunk_mid);
     if (t == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
@@ -314,10 +320,15 @@ __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restri
           const long long b = min((long long)(i + 1) * kGroupBricks * kClasses, (long long)G.nfinal);
           const unsigned cnt = start[b] - start[a];
           v = (cnt + kChunk16 - 1) / kChunk16;
-        } else {
+        } else if (pass == 1) {
           const unsigned cnt = start[(long long)(i + 1) * kClasses] - start[(long long)i * kClasses];
           const unsigned target = min(kItemTargetMax, max(kItemTargetMin, (unsigned)(nq / (8LL * ctas))));
           v = (cnt + target - 1) / target;
+        } else {
+          const long long a = min((long long)i * kMaxBins * FPG, (long long)G.nfinal);
+          const long long b = min((long long)(i + 1) * kMaxBins * FPG, (long long)G.nfinal);
+          const unsigned cnt = start[b] - start[a];
+          v = (cnt + kChunk16 - 1) / kChunk16;
         }
       }
       buf[t] = v;
@@ -437,7 +448,8 @@ __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
 }
 
 // split 1: coordinates -> {x,y,z,q} records grouped by brick group
-template <int N, int DEG>
+// SUPER: three-level geometry, the first pass splits by super-group (kMaxBins groups)
+template <int N, int DEG, bool SUPER>
 __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G, unsigned *__restrict__ cursor1,
                                                                    float4 *__restrict__ rec1) {
@@ -488,12 +500,12 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
         check_query<N>(G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
-        key[j] = (unsigned)(brick / kGroupBricks);
+        key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float(q));
       }
     }
     if (kPrefetch) fetch(ch + gridDim.x);
-    block_split<FULL, float4, kChunk16>(sm, r, key, G.ngroups, cnt, cursor1, rec1);
+    block_split<FULL, float4, kChunk16>(sm, r, key, SUPER ? G.nsuper : G.ngroups, cnt, cursor1, rec1);
   };
   if (kPrefetch) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -509,7 +521,7 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
 // Measured per kernel (1e9 queries): split 2 is fastest WITHOUT the register prefetch at two CTAs per SM (7.5 vs 8.6 ms);
 // split 1 and the unsort levels are fastest with it at one CTA per SM (7.6 vs 8.3 ms, 3.8 vs 4.2 ms).
 constexpr bool kPrefetchSplit2 = false;
-template <int N, int DEG>
+template <int N, int DEG, int LEVEL>
 __global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_THREADS > 512) ? 1 : 2) ord_split2_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G,
                                                                    const unsigned *__restrict__ start,
@@ -517,26 +529,50 @@ __global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_T
                                                                    unsigned *__restrict__ cursor2,
                                                                    const float4 *__restrict__ rec1,
                                                                    float4 *__restrict__ rec2) {
+  // LEVEL 2: the parent bins are the groups, the keys (brick, class) inside the group, the cursors the (brick, class)
+  //          streams.  LEVEL 1 (three-level geometry): parents = super-groups, keys = groups inside them.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
   __shared__ unsigned s_chunk[kMaxBins + 1];
   constexpr int RPT = kChunk16 / kSplitThreads;
-  for (int i = threadIdx.x; i <= G.ngroups; i += kSplitThreads) s_chunk[i] = chunk_start[i];
+  constexpr unsigned FPG = kGroupBricks * kClasses;                     // final bins per group
+  constexpr unsigned FPP = LEVEL == 2 ? FPG : FPG * (unsigned)kMaxBins;  // final bins per parent bin
+  const int nparents = LEVEL == 2 ? G.ngroups : G.nsuper;
+  const bool table_in_smem = nparents <= kMaxBins;
+  if (table_in_smem)
+    for (int i = threadIdx.x; i <= nparents; i += kSplitThreads) s_chunk[i] = chunk_start[i];
   __syncthreads();
-  const unsigned nchunks = s_chunk[G.ngroups];
-  // chunk descriptor: group, first record, count; the records of the next chunk are fetched early
+  const unsigned nchunks = chunk_start[nparents];
+  int cursor_parent = 0;  // large tables: the CTA's chunks come in increasing order, the parent only moves forward
+  // chunk descriptor: parent bin, first record, count; the records of the next chunk may be fetched early
   auto describe = [&](unsigned ch, int &g, unsigned &base, unsigned &cnt, unsigned &fa, unsigned &fb) {
-    int lo = 0, hi = G.ngroups - 1;  // last group with chunk_start <= ch
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_chunk[mid] <= ch) lo = mid; else hi = mid - 1;
+    unsigned c0;
+    if (table_in_smem) {
+      int lo = 0, hi = nparents - 1;  // last parent with chunk_start <= ch
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_chunk[mid] <= ch) lo = mid; else hi = mid - 1;
+      }
+      g = lo;
+      c0 = s_chunk[g];
+    } else {
+      if (cursor_parent == 0) {
+        int lo = 0, hi = nparents - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (chunk_start[mid] <= ch) lo = mid; else hi = mid - 1;
+        }
+        cursor_parent = lo;
+      }
+      while (cursor_parent + 1 < nparents && chunk_start[cursor_parent + 1] <= ch) ++cursor_parent;
+      g = cursor_parent;
+      c0 = chunk_start[g];
     }
-    g = lo;
-    fa = (unsigned)g * kGroupBricks * kClasses;
-    fb = min(fa + kGroupBricks * kClasses, (unsigned)G.nfinal);
+    fa = min((unsigned)g * FPP, (unsigned)G.nfinal);
+    fb = min(fa + FPP, (unsigned)G.nfinal);
     const unsigned gbeg = start[fa], gend = start[fb];
-    base = gbeg + (ch - s_chunk[g]) * kChunk16;
+    base = gbeg + (ch - c0) * kChunk16;
     cnt = min((unsigned)kChunk16, gend - base);
   };
   float4 nr[RPT];
@@ -560,6 +596,9 @@ __global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_T
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     if (!kPrefetchSplit2) fetch(ch);
     g = ng; base = nbase; cnt = ncnt; fa = nfa; fb = nfb;
+    // keys are relative to the parent; the cursor array is indexed by final bin (LEVEL 2) or by group (LEVEL 1)
+    const int nbins = LEVEL == 2 ? (int)(fb - fa) : min(kMaxBins, G.ngroups - g * kMaxBins);
+    unsigned *cur = LEVEL == 2 ? cursor2 + fa : cursor2 + (size_t)g * kMaxBins;
     auto run = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       float4 r[RPT];
@@ -573,11 +612,12 @@ __global__ void __launch_bounds__(kSplitThreads, (kPrefetchSplit2 || ORD_SPLIT_T
           const float x[3] = {r[j].x, r[j].y, r[j].z};
           int brick, cls;
           locate<N, DEG>(P, G, x, brick, cls);
-          key[j] = (unsigned)((brick - g * kGroupBricks) * kClasses + cls);
+          key[j] = LEVEL == 2 ? (unsigned)((brick - g * kGroupBricks) * kClasses + cls)
+                              : (unsigned)(brick / kGroupBricks - g * kMaxBins);
         }
       }
       if (kPrefetchSplit2) fetch(ch + gridDim.x);
-      block_split<FULL, float4, kChunk16>(sm, r, key, (int)(fb - fa), cnt, cursor2 + fa, rec2);
+      block_split<FULL, float4, kChunk16>(sm, r, key, nbins, cnt, cur, rec2);
     };
     if (cnt == kChunk16)
       run(std::true_type{});
@@ -940,7 +980,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
 
 // ------------------------------------------------------------------------------------------ host
 struct OrdLayout {
-  size_t rec1, rec2, hist, start, sums, cursor1, chunk_start, item_start, cursorA, cursorB, total;
+  size_t rec1, rec2, hist, start, sums, cursor0, chunk_mid, cursor1, chunk_start, item_start, cursorA, cursorB, total;
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -958,7 +998,9 @@ static OrdLayout ord_layout(long long nq, long long nfinal, long long nbricks, l
   Lo.hist = take((size_t)(nfinal + 1) * 4);
   Lo.start = take((size_t)(nfinal + 1) * 4);
   Lo.sums = take(65536 * 4);
-  Lo.cursor1 = take((size_t)ngroups * 4);
+  Lo.cursor0 = take((size_t)(kMaxBins + 1) * 4);
+  Lo.chunk_mid = take((size_t)(kMaxBins + 2) * 4);
+  Lo.cursor1 = take((size_t)(ngroups + 1) * 4);
   Lo.chunk_start = take((size_t)(ngroups + 1) * 4);
   Lo.item_start = take((size_t)(nbricks + 1) * 4);
   Lo.cursorA = take((size_t)(((nq + (1LL << Uns<true>::SA) - 1) >> Uns<true>::SA) + 1) * 4);  // gradient mode: the
@@ -997,9 +1039,13 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
     bricks *= G.nb[d];
   }
-  if (bricks > (long long)kGroupBricks * kMaxBins) return false;
+  // two split levels reach kMaxBins groups of kGroupBricks bricks (8192 bricks: 512^3 cells); a third level in front
+  // (super-groups of kMaxBins groups) reaches kMaxBins^2 groups; the stream table (4 bytes per (brick, class)) is the
+  // practical limit
+  if (bricks > (long long)kGroupBricks * kMaxBins * kMaxBins || bricks * kClasses > (1LL << 28)) return false;
   G.nbricks = (int)bricks;
   G.ngroups = (int)((bricks + kGroupBricks - 1) / kGroupBricks);
+  G.nsuper = G.ngroups <= kMaxBins ? 1 : (G.ngroups + kMaxBins - 1) / kMaxBins;
   G.nfinal = (int)bricks * kClasses;
   return true;
 }
@@ -1022,6 +1068,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   unsigned *start = reinterpret_cast<unsigned *>(sb + Lo.start);
   unsigned *sums = reinterpret_cast<unsigned *>(sb + Lo.sums);
   OrdPlan pl;
+  pl.cursor0 = reinterpret_cast<unsigned *>(sb + Lo.cursor0);
+  pl.chunk_mid = reinterpret_cast<unsigned *>(sb + Lo.chunk_mid);
   pl.cursor1 = reinterpret_cast<unsigned *>(sb + Lo.cursor1);
   pl.chunk_start = reinterpret_cast<unsigned *>(sb + Lo.chunk_start);
   pl.item_start = reinterpret_cast<unsigned *>(sb + Lo.item_start);
@@ -1041,8 +1089,10 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   constexpr int smem_place = (4 << U::SB) * (GRAD ? N : 1);
   static_assert(smem_eval <= 227 * 1024, "evaluation tile does not fit shared memory");
   static_assert(smem_place <= 227 * 1024, "placement window does not fit shared memory");
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
@@ -1062,13 +1112,29 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
     ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, U::SA, U::SB, pl);
   }
   const int sblocks = sms * 2;
-  {
-    StageScope sc("ord_split1", st);
-    ord_split1_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
-  }
-  {
-    StageScope sc("ord_split2", st);
-    ord_split2_kernel<N, DEG><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
+  if (G.nsuper == 1) {
+    {
+      StageScope sc("ord_split1", st);
+      ord_split1_kernel<N, DEG, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+    }
+    {
+      StageScope sc("ord_split2", st);
+      ord_split2_kernel<N, DEG, 2><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
+    }
+  } else {  // arrays beyond 8192 bricks: super-groups -> groups -> (brick, class) streams; the records end in rec2 again
+    {
+      StageScope sc("ord_split0", st);
+      ord_split1_kernel<N, DEG, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
+    }
+    {
+      StageScope sc("ord_split1", st);
+      ord_split2_kernel<N, DEG, 1><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_mid, pl.cursor1, rec2, rec1);
+    }
+    {
+      StageScope sc("ord_split2", st);
+      ord_split2_kernel<N, DEG, 2><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
+    }
+    count_launch();
   }
   {
     StageScope sc(GRAD ? "ord_eval_gradient" : "ord_eval", st);
@@ -1117,9 +1183,18 @@ extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
 
 extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
   if (!d || nq <= 0) return 0;
-  // upper bound over the supported geometries: kGroupBricks * kMaxBins bricks
-  const long long nbricks = (long long)kGroupBricks * kMaxBins;
-  return ord_layout(nq, nbricks * kClasses, nbricks, kMaxBins).total + 256;
+  // upper bound over the brick geometries of this descriptor (cells <= size + 1 per axis)
+  long long nbricks = 1;
+  const int bdim3[3] = {Brick<3>::BX, Brick<3>::BY, Brick<3>::BZ}, bdim2[3] = {Brick<2>::BX, Brick<2>::BY, 1};
+  for (int i = 0; i < d->ndims && i < 3; ++i) {
+    const long long cells = (d->size[i] > 0 ? d->size[i] : 1) + 1;
+    const int b = d->ndims == 3 ? bdim3[i] : bdim2[i];
+    nbricks *= (cells + b - 1) / b;
+  }
+  nbricks = std::max<long long>(nbricks, (long long)kGroupBricks * kMaxBins);
+  if (nbricks * kClasses > (1LL << 28)) nbricks = (1LL << 28) / kClasses;  // beyond: the call falls back anyway
+  const long long ngroups = (nbricks + kGroupBricks - 1) / kGroupBricks;
+  return ord_layout(nq, nbricks * kClasses, nbricks, ngroups).total + 256;
 }
 
 static int eval_sorted_common(int dev, const b200itp_desc *d, const void *coefs, const void *const *coords, int64_t nq,

@@ -164,3 +164,31 @@ def test_c5_linear_4d_128_f64(pkg, orc):
     W, X, Y, Z = torch.meshgrid(ii, ii, ii, ii, indexing="ij")
     vals = itp(W.reshape(-1), X.reshape(-1), Y.reshape(-1), Z.reshape(-1)).reshape((len(ii),) * 4)
     assert torch.equal(vals, A[::9, ::9, ::9, ::9])  # linear weights at nodes are exactly (1, 0)
+
+
+@pytest.mark.parametrize("shape", [(530, 530, 530), (12100, 12100)])
+def test_ordered_path_beyond_8192_bricks(pkg, shape):
+    """Arrays with more than 8192 bricks (512^3 cells / 11585^2 cells) take a third split level (super-groups): the
+    ordered pipeline must still serve the call and return exactly the direct kernel's values and gradients."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    A = torch.rand(shape, device="cuda", dtype=torch.float32, generator=g)
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))) if len(shape) == 3 else m.BSpline(m.Quadratic(m.Reflect(m.OnCell())))
+    itp = m.interpolate(A, it)
+    del A
+    nq = 30_000_000
+    coords = []
+    for (lb, ub) in itp.bounds():
+        lb, ub = float(lb), float(ub)
+        coords.append((torch.rand(nq, device="cuda", dtype=torch.float32, generator=g) * (ub - lb) + lb).clamp_(lb, ub))
+    n0 = L.b200itp_eval_sorted_ordered_calls()
+    v = m.evaluate_sorted(itp, *coords)
+    assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "the three-level ordered pipeline must serve this call"
+    k = 6_000_000
+    assert torch.equal(v[:k], itp(*[c[:k] for c in coords]))
+    assert torch.equal(v[-k:], itp(*[c[-k:] for c in coords]))
+    gs = m.gradient_sorted(itp, *[c[:k] for c in coords])
+    assert L.b200itp_eval_sorted_ordered_calls() == n0 + 2
+    assert torch.equal(gs, m.gradient(itp, *[c[:k] for c in coords]))
