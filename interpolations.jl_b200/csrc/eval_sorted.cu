@@ -750,6 +750,12 @@ struct TileReduce {
   }
 };
 
+__device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
 template <int N, int DEG>
 struct EvalSmem {
   float tile[TileCfg<N, DEG>::FLOATS];
@@ -869,8 +875,11 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
         const int lz = t / (TC::TX * TC::TY);
         const long long ox = sm.axoff[0][lx], oy = sm.axoff[1][ly], oz = N == 3 ? sm.axoff[2][lz] : 0;
         const bool ok = ox >= 0 && oy >= 0 && oz >= 0;
-        sm.tile[(lz * TC::TY + ly) * TC::PX + lx] = ok ? __ldg(coefs + (ox + oy + oz)) : 0.f;
+        // asynchronous 4-byte copies (zero fill outside the array): ~30 per thread in flight, no register round trip
+        cp_async4_zfill(&sm.tile[(lz * TC::TY + ly) * TC::PX + lx], coefs + (ok ? ox + oy + oz : 0), ok);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const int rounds = (sm.max_cnt + kRB - 1) / kRB;
