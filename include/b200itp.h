@@ -214,6 +214,18 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
                  int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
                  int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
 
+/* Tensor-product (grid) evaluation `itp(xvec, yvec, ...)` (src/b-splines/indexing.jl:16-23, src/scaling/scaling.jl:98-100,
+ * src/extrapolation/extrapolation.jl:59-70): `axis_coords[d]` is a DEVICE vector of `axis_len[d]` coordinates of
+ * d->coord_dtype; `out_value` receives prod(axis_len) elements of b200itp_out_dtype(d), first axis fastest (the Julia
+ * result array).  Every element is what b200itp_eval returns for that coordinate tuple.  The tuples are expanded on the
+ * device into `scratch` (at least b200itp_eval_grid_scratch_bytes bytes) and evaluated by the ordered pipeline where it
+ * applies, by the direct kernel otherwise.  `first_oob` is the linear index (first axis fastest) of the first tuple that
+ * throws. */
+B200ITP_API size_t b200itp_eval_grid_scratch_bytes(const b200itp_desc *d, const int64_t *axis_len);
+B200ITP_API int b200itp_eval_grid(int dev, const b200itp_desc *d, const void *coefs, const void *const *axis_coords,
+                      const int64_t *axis_len, void *out_value, int64_t *first_oob, void *scratch,
+                      size_t scratch_bytes, void *stream);
+
 /* Replaces `Base.copy(::Broadcasted)` of `Interpolations.hessian.(Ref(itp), xs...)` (src/b-splines/indexing.jl:37-41,
  * 114-144,201-229; src/scaling/scaling.jl:150-160; src/extrapolation/extrapolation.jl:84-90): `out_hess` receives
  * nq*ndims*ndims elements of b200itp_out_dtype(d), the full symmetric matrix per query (SMatrix layout).  Extrapolation
@@ -245,8 +257,9 @@ B200ITP_API int b200itp_eval_sorted(int dev, const b200itp_desc *d, const void *
 B200ITP_API int b200itp_gradient_sorted(int dev, const b200itp_desc *d, const void *coefs,
                             const void *const *coords, int64_t nq, void *out_grad, int64_t *first_oob,
                             void *scratch, size_t scratch_bytes, void *stream);
-/* threshold (queries per call) from which the ordered pipeline is used; default 2^20, and only for coefficient
- * arrays of at least 128 MiB (smaller ones stay L2-resident, where the direct kernel is faster).  Setting the
+/* threshold (queries per call) from which the ordered pipeline is used; default 2^20, and for 2-D arrays only
+ * from 128 MiB of coefficients (smaller images stay L2-resident, where the direct kernel is faster; 3-D arrays of any
+ * size take the ordered path).  Setting the
  * threshold to 1 (tests) also lifts the array-size condition. */
 B200ITP_API int64_t b200itp_eval_sorted_min_queries(void);
 B200ITP_API void b200itp_eval_sorted_set_min_queries(int64_t n);

@@ -8,14 +8,14 @@ from .flags import (BSpline, Cubic, Flat, Free, Line, Linear, Natural, OnCell, O
                     Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
-                   bounds, evaluate_debug, evaluate_from_host, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, lbounds, out_dtype,
+                   bounds, evaluate_debug, evaluate_from_host, evaluate_grid, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, lbounds, out_dtype,
                    prefilter_, scale, ubounds, value_and_gradient)
 from . import _lib, parallel
 
 __all__ = [
     "BSpline", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
-    "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host",
+    "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",
     "extrapolate", "gradient", "gradient_sorted", "hessian", "interpolate", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
     "value_and_gradient",

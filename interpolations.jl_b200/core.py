@@ -619,6 +619,58 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
     return out
 
 
+def evaluate_grid(itp, *vectors):
+    """`itp(xvec, yvec, ...)`: tensor-product evaluation (indexing.jl:16-23, scaling.jl:98-100, extrapolation.jl:59-70).
+    Returns a tensor of shape (len(xvec), len(yvec), ...) whose element [i, j, ...] is `itp(xvec[i], yvec[j], ...)`
+    (a permuted view of the Julia-ordered result: the first axis is the fastest in memory)."""
+    torch = _torch()
+    L = _lib.lib()
+    N = itp.ndims
+    if len(vectors) != N:
+        raise ValueError(f"expected {N} coordinate vectors, got {len(vectors)}")
+    dev = itp.device_index
+    tdev = torch.device("cuda", dev)
+    ts = []
+    for v in vectors:
+        t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.atleast_1d(np.asarray(v)))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        ts.append(t.reshape(-1).to(tdev))
+    dt = torch.float64 if any(t.dtype == torch.float64 for t in ts) else torch.float32
+    ts = [t.to(dt).contiguous() for t in ts]
+    npdt = np.float32 if dt == torch.float32 else np.float64
+    D = itp.descriptor(npdt)
+    ocode = L.b200itp_out_dtype(C.byref(D))
+    if ocode < 0:
+        raise ValueError("invalid descriptor")
+    odt = torch.float32 if ocode == F32 else torch.float64
+    lens = [int(t.numel()) for t in ts]
+    nq = int(np.prod(lens))
+    coefs = itp.coefficients()
+    foob = C.c_int64(-1)
+    with torch.cuda.device(dev):
+        out = torch.empty(nq, dtype=odt, device=tdev)
+        if nq > 0:
+            ptrs = (C.c_void_p * N)(*[t.data_ptr() for t in ts])
+            clens = (C.c_int64 * N)(*lens)
+            nbytes = int(L.b200itp_eval_grid_scratch_bytes(C.byref(D), clens))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=tdev)
+            rc = L.b200itp_eval_grid(dev, C.byref(D), C.c_void_p(coefs.data_ptr()), ptrs, clens,
+                                     C.c_void_p(out.data_ptr()), C.byref(foob), C.c_void_p(scratch.data_ptr()), nbytes,
+                                     _stream_ptr(dev))
+            _lib.check(rc, "b200itp_eval_grid")
+    if foob.value >= 0:
+        idx = np.unravel_index(foob.value, lens, order="F")
+        xq = tuple(float(ts[d][idx[d]].item()) for d in range(N))
+        raise BoundsError(f"attempt to access {itp!r} at index {xq}")
+    if isinstance(itp, Extrapolation):
+        # extrapolation.jl:61-64: the result array has eltype promote_type(T, eltype.(x)...) and stores converted values
+        b = itp._chain()[0]
+        tret = torch.float64 if (dt == torch.float64 or b.dtype_code == F64) else torch.float32
+        out = out.to(tret)
+    return out.reshape(tuple(reversed(lens))).permute(*reversed(range(N)))
+
+
 def hessian(itp, *xs):
     """`Interpolations.hessian.(Ref(itp), xs...)`: trailing axes (N, N) hold the symmetric matrix of every query
     (indexing.jl:37-41, scaling.jl:150-160; extrapolated interpolants: in bounds only, extrapolation.jl:84-90)."""

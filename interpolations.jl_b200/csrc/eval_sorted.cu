@@ -1228,7 +1228,9 @@ static int eval_sorted_common(int dev, const b200itp_desc *d, const void *coefs,
   // direct 36 vs ordered 20 Gevals/s; 8192^2, 256 MiB: 20 vs 21; 512^3, 512 MiB: 2.1 vs 23).
   long long coef_bytes = 4;
   for (int i = 0; i < d->ndims && i < B200ITP_MAX_DIMS; ++i) coef_bytes *= d->size[i];
-  if (plain && nq >= g_sorted_min_queries && coef_bytes >= g_sorted_min_coef_bytes &&
+  // (3-D: the direct tricubic kernel stays at 2-4 Gevals/s even from the L2 — 128^3: 4.0 vs 16.3, 256^3: 3.1 vs 20.5 — so
+  // every 3-D array takes the ordered path; the size condition applies to 2-D arrays only)
+  if (plain && nq >= g_sorted_min_queries && (d->ndims == 3 || coef_bytes >= g_sorted_min_coef_bytes) &&
       (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) && (d->ndims == 2 || d->ndims == 3)) {
     B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
     // the scratch pointer is aligned up to 256 bytes inside the caller's buffer
@@ -1281,4 +1283,103 @@ extern "C" int b200itp_gradient_sorted(int dev, const b200itp_desc *d, const voi
                                        size_t scratch_bytes, void *stream) {
   if (!out_grad) B200_FAIL(B200ITP_E_BADARG, "gradient_sorted: null output pointer");
   return eval_sorted_common(dev, d, coefs, coords, nq, nullptr, out_grad, first_oob, scratch, scratch_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------ grid evaluation
+// itp(xvec, yvec, ...) (indexing.jl:16-23, scaling.jl:98-100, extrapolation.jl:59-70) is the pointwise evaluation over
+// Iterators.product(x...), first axis fastest.  The coordinate tuples are expanded on the device into the caller's
+// scratch (one streaming write of N words per output, ~1 % of the evaluation time) and take the usual paths: the ordered
+// pipeline for bare Float32 2-D / 3-D interpolants (a coherent query set is just a very friendly distribution for it),
+// the direct kernel otherwise.
+namespace b200itp {
+template <typename T>
+__global__ void __launch_bounds__(256) grid_expand_kernel(const T *a0, const T *a1, const T *a2, const T *a3, long long l0,
+                                                          long long l1, long long l2, int ndims, long long nq, T *o0, T *o1,
+                                                          T *o2, T *o3) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    long long r = q;
+    const long long i0 = r % l0;
+    r /= l0;
+    o0[q] = a0[i0];
+    if (ndims > 1) {
+      const long long i1 = r % l1;
+      r /= l1;
+      o1[q] = a1[i1];
+    }
+    if (ndims > 2) {
+      const long long i2 = r % l2;
+      r /= l2;
+      o2[q] = a2[i2];
+    }
+    if (ndims > 3) o3[q] = a3[r];
+  }
+}
+}  // namespace b200itp
+
+static size_t grid_coord_bytes(const b200itp_desc *d, int64_t nq) {
+  const size_t es = d->coord_dtype == B200ITP_F64 ? 8 : 4;
+  return ((size_t)nq * es + 255) / 256 * 256;
+}
+
+extern "C" size_t b200itp_eval_grid_scratch_bytes(const b200itp_desc *d, const int64_t *axis_len) {
+  if (!d || !axis_len || d->ndims < 1 || d->ndims > B200ITP_MAX_DIMS) return 0;
+  int64_t nq = 1;
+  for (int i = 0; i < d->ndims; ++i) nq *= axis_len[i] > 0 ? axis_len[i] : 0;
+  if (nq <= 0) return 0;
+  return grid_coord_bytes(d, nq) * d->ndims + b200itp_eval_sorted_scratch_bytes(d, nq) + 512;
+}
+
+extern "C" int b200itp_eval_grid(int dev, const b200itp_desc *d, const void *coefs, const void *const *axis_coords,
+                                 const int64_t *axis_len, void *out_value, int64_t *first_oob, void *scratch,
+                                 size_t scratch_bytes, void *stream) {
+  if (!d || !coefs || !axis_coords || !axis_len || !out_value) B200_FAIL(B200ITP_E_BADARG, "eval_grid: null pointer");
+  if (d->ndims < 1 || d->ndims > B200ITP_MAX_DIMS) B200_FAIL(B200ITP_E_BADARG, "eval_grid: ndims must be 1..4");
+  if (d->coord_dtype != B200ITP_F32 && d->coord_dtype != B200ITP_F64) B200_FAIL(B200ITP_E_DTYPE, "eval_grid: bad coordinate dtype");
+  int64_t nq = 1;
+  for (int i = 0; i < d->ndims; ++i) {
+    if (axis_len[i] < 0) B200_FAIL(B200ITP_E_BADARG, "eval_grid: negative axis length");
+    if (axis_len[i] > 0 && !axis_coords[i]) B200_FAIL(B200ITP_E_BADARG, "eval_grid: null coordinate vector %d", i);
+    nq *= axis_len[i];
+  }
+  if (first_oob) *first_oob = -1;
+  if (nq == 0) return 0;
+  const size_t cb = grid_coord_bytes(d, nq);
+  unsigned char *sp = reinterpret_cast<unsigned char *>(scratch);
+  size_t sbytes = scratch_bytes;
+  if (sp) {
+    const size_t mis = (256 - ((uintptr_t)sp % 256)) % 256;
+    if (mis > sbytes) B200_FAIL(B200ITP_E_SIZE, "eval_grid: scratch too small");
+    sp += mis;
+    sbytes -= mis;
+  }
+  if (!sp || sbytes < cb * d->ndims) B200_FAIL(B200ITP_E_SIZE, "eval_grid: scratch too small (b200itp_eval_grid_scratch_bytes)");
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval_grid: cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const void *cptr[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
+  void *optr[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < d->ndims; ++i) {
+    optr[i] = sp + cb * i;
+    cptr[i] = optr[i];
+  }
+  const int blocks = (int)std::min<long long>((nq + 255) / 256, (long long)sm_count(dev) * 16);
+  {
+    StageScope sc("grid_expand", st);
+    const long long l0 = axis_len[0], l1 = d->ndims > 1 ? axis_len[1] : 1, l2 = d->ndims > 2 ? axis_len[2] : 1;
+    if (d->coord_dtype == B200ITP_F32)
+      grid_expand_kernel<float><<<blocks, 256, 0, st>>>((const float *)axis_coords[0], (const float *)(d->ndims > 1 ? axis_coords[1] : nullptr),
+                                                        (const float *)(d->ndims > 2 ? axis_coords[2] : nullptr),
+                                                        (const float *)(d->ndims > 3 ? axis_coords[3] : nullptr), l0, l1, l2, d->ndims, nq,
+                                                        (float *)optr[0], (float *)optr[1], (float *)optr[2], (float *)optr[3]);
+    else
+      grid_expand_kernel<double><<<blocks, 256, 0, st>>>((const double *)axis_coords[0], (const double *)(d->ndims > 1 ? axis_coords[1] : nullptr),
+                                                         (const double *)(d->ndims > 2 ? axis_coords[2] : nullptr),
+                                                         (const double *)(d->ndims > 3 ? axis_coords[3] : nullptr), l0, l1, l2, d->ndims, nq,
+                                                         (double *)optr[0], (double *)optr[1], (double *)optr[2], (double *)optr[3]);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return eval_sorted_common(dev, d, coefs, cptr, nq, out_value, nullptr, first_oob, sp + cb * d->ndims, sbytes - cb * d->ndims,
+                            stream);
 }

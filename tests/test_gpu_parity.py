@@ -543,3 +543,35 @@ def test_hessian_bit_exact(pkg, orc, coef_dtype, coord_dtype):
         m.hessian(m.extrapolate(itp, m.Line()), np.array([0.5], coord_dtype), np.array([3.0], coord_dtype))
     with pytest.raises(ValueError):
         m.hessian(m.extrapolate(itp, 0.0), np.array([1.5], coord_dtype), np.array([3.0], coord_dtype))
+
+
+def test_grid_evaluation_equals_pointwise(pkg):
+    """`itp(xvec, yvec, zvec)` (indexing.jl:16-23, scaling.jl:98-100, extrapolation.jl:59-70): element
+    [i, j, k] is exactly the pointwise / broadcast value, for bare, scaled and extrapolated interpolants, 1-D to 4-D."""
+    import torch
+    m = pkg
+    rng = np.random.default_rng(23)
+    for shape in ((40,), (21, 17), (12, 11, 10), (7, 6, 5, 6)):
+        N = len(shape)
+        A = rng.standard_normal(shape).astype(np.float32)
+        it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))) if N < 4 else m.BSpline(m.Linear())
+        itp = m.interpolate(A, it)
+        rngs = [m.jrange(np.float32(1), np.float32(3), length=n) for n in shape]
+        for obj in (itp, m.scale(itp, *rngs), m.extrapolate(itp, m.Line()), m.extrapolate(m.scale(itp, *rngs), 0.0)):
+            vecs = []
+            for (lb, ub) in obj.bounds():
+                lb, ub = float(lb), float(ub)
+                pad = 0.3 * (ub - lb) if isinstance(obj, (m.Extrapolation, m.FilledExtrapolation)) else 0.0
+                v = rng.uniform(lb - pad, ub + pad, int(rng.integers(3, 9))).astype(np.float32)
+                if pad == 0.0:
+                    v = np.clip(v, np.float32(lb), np.float32(ub))
+                    v = np.where((v < lb) | (v > ub), np.float32((lb + ub) / 2), v)
+                vecs.append(v)
+            got = m.evaluate_grid(obj, *vecs)
+            mesh = np.meshgrid(*vecs, indexing="ij")
+            ref = obj(*mesh)
+            assert tuple(got.shape) == tuple(len(v) for v in vecs)
+            assert torch.equal(got.to(ref.dtype), ref), (shape, type(obj).__name__)
+    itp = m.interpolate(rng.standard_normal((9, 9)).astype(np.float32), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))))
+    with pytest.raises(m.BoundsError):
+        m.evaluate_grid(itp, np.array([1.0, 2.0], np.float32), np.array([3.0, 9.5], np.float32))
