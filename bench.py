@@ -281,7 +281,7 @@ def main():
                            "frac": b / (avg * 1e-3) / 1e9 / peak if avg > 0 else None})
     eval_bytes = nq * (12 + 4) + 4 * ncoef          # coordinates in, results out, coefficients once
     pre_bytes = 2 * 4 * ncoef * 3                   # one read + one write per axis pass
-    if rank != 0 or not stages.get("prefilter_axis0_contiguous"):
+    if rank != 0 or not any(k.startswith("prefilter_axis0") for k in stages):
         # ranks other than 0 do not prefilter inside the step: time it once here for the report
         work = torch.empty(ncoef, dtype=torch.float32, device=dev).normal_()
         L.b200itp_profile_enable(1)

@@ -166,7 +166,10 @@ template <>
 struct Tune<float> {
   static constexpr int B = 16;       // block rows == look-ahead rows
   static constexpr int TP = 24;      // rows examined at each end for the Woodbury coefficients
-  static constexpr int ITEMS = 128;  // lines per CTA in the contiguous-axis kernel
+#ifndef PF_ITEMS_F32
+#define PF_ITEMS_F32 128
+#endif
+  static constexpr int ITEMS = PF_ITEMS_F32;  // lines per CTA in the contiguous-axis kernel
 };
 template <>
 struct Tune<double> {
@@ -332,8 +335,11 @@ struct ContigCfg {
   static constexpr size_t smem_bytes = (size_t)(STAGES + 1) * ITEMS * PITCH * 16 + (size_t)ITEMS * 16;
 };
 
+#ifndef PF_CONTIG_MINB
+#define PF_CONTIG_MINB 1
+#endif
 template <typename T, int VW>
-__global__ void __launch_bounds__(Tune<T>::ITEMS) prefilter_contig_kernel(const T *src, T *dst,
+__global__ void __launch_bounds__(Tune<T>::ITEMS, sizeof(T) == 4 ? PF_CONTIG_MINB : 1) prefilter_contig_kernel(const T *src, T *dst,
                                                                            const __grid_constant__ AxisPlan<T> p,
                                                                            int64_t nitems, int nseg, int seglen) {
   using Cfg = ContigCfg<T>;
@@ -479,6 +485,203 @@ __global__ void __launch_bounds__(Tune<T>::ITEMS) prefilter_contig_kernel(const 
   cp_async_wait<0>();
 }
 
+// ================================================================== kernel: axis 1, one warp per line
+// Lines along the contiguous axis that fit a warp's registers (n = 128 * nch <= 128 * NCH): chunks of 128 rows, lane l
+// holds rows 4l .. 4l+3 of the chunk in one float4, so every global access is a coalesced 128-bit access and no shared
+// memory is needed.  The two first-order recurrences  y[r] = v[r] - L[r] y[r-1]  and
+// x[r] = Dinv[r] y[r] - U[r] Dinv[r] x[r+1]  are evaluated per chunk as: (1) each lane composes its four rows into one
+// affine map, (2) a warp scan of the maps gives every lane the value entering its rows, (3) the four rows are
+// recomputed from it.  Four rows contract by |a|^4 <= 5.2e-3, so three scan steps (reach 8 lanes = 32 rows, |a|^32 ~
+// 5e-19) are exact to round-off.  Chunks past the LU head use the settled multiplier (a^4, a^8, a^16); the first chunk
+// scans (coefficient, value) pairs with the per-row head coefficients, which every lane keeps in registers for all the
+// lines of its warp (as it does the Woodbury columns z1 / zn of its rows).  Row n (no U, its own L and D) is the last
+// row of lane 31 in the last chunk.  The carry crosses chunks through lane 31 / lane 0.  The Woodbury correction is the
+// same  x -= z1*c1 + zn*cn  as in the other kernels.
+template <int NCH>
+__global__ void __launch_bounds__(128) prefilter_warpline_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                                 const __grid_constant__ AxisPlan<float> p, int64_t nlines) {
+  const int lane = threadIdx.x & 31;
+  const unsigned FULLMASK = 0xffffffffu;
+  const int n = p.n;
+  const int nch = n >> 7;
+  const float a1 = -p.Linf, a2 = a1 * a1, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8;
+  const float m1 = -p.Uinf * p.Dinf, m2 = m1 * m1, m4 = m2 * m2, m8 = m4 * m4, m16 = m8 * m8;
+  // a^(4(lane+1)) and m^(4(32-lane)): weight of the carry at the last / first row of the lane
+  float apw = 1.f, mpw = 1.f;
+  {
+    float af = a4, mf = m4;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (((lane + 1) >> k) & 1) apw *= af;
+      if (((32 - lane) >> k) & 1) mpw *= mf;
+      af *= af;
+      mf *= mf;
+    }
+  }
+  // per-lane coefficients of the first chunk and Woodbury columns of the first / last chunk
+  float ah[4], mh[4], dh[4], z1r[4], znr[4];
+  float Ah = 1.f, Mh = 1.f;  // products over the lane's four rows
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = 4 * lane + j + 1;
+    float L, U, Di;
+    row_coef(p, r, L, U, Di);
+    ah[j] = r == 1 ? 0.f : -L;
+    mh[j] = -U * Di;
+    dh[j] = Di;
+    Ah *= ah[j];
+    Mh *= mh[j];
+    z1r[j] = r <= p.Hz ? p.z1[r - 1] : 0.f;
+    const int qz = (n - 128 + r) - (n - p.Hz) - 1;
+    znr[j] = qz >= 0 ? p.zn[qz] : 0.f;
+  }
+  const float alast = lane == 31 ? -p.Llast : a1;    // row n: last row of lane 31 in the last chunk
+  const float dlast = lane == 31 ? p.Dlast : p.Dinf;
+  const bool wood = p.nv > 0;
+
+  const int64_t wstride = (int64_t)gridDim.x * 4;
+  for (int64_t line = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); line < nlines; line += wstride) {
+    const float4 *in = reinterpret_cast<const float4 *>(src + line * (int64_t)n);
+    float4 *out = reinterpret_cast<float4 *>(dst + line * (int64_t)n);
+    float v[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nch) q = __ldcs(in + c * 32 + lane);
+      v[c][0] = q.x;
+      v[c][1] = q.y;
+      v[c][2] = q.z;
+      v[c][3] = q.w;
+    }
+    // ---- forward sweep
+    float carry;
+    {
+      float A = Ah, Bv = v[0][0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) Bv = fmaf(ah[j], Bv, v[0][j]);
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        const float A2 = __shfl_up_sync(FULLMASK, A, d), B2 = __shfl_up_sync(FULLMASK, Bv, d);
+        if (lane >= d) {
+          Bv = fmaf(A, B2, Bv);
+          A = A * A2;
+        }
+      }
+      float yin = __shfl_up_sync(FULLMASK, Bv, 1);
+      if (lane == 0) yin = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[0][j] = fmaf(ah[j], yin, v[0][j]);
+        yin = v[0][j];
+      }
+      carry = __shfl_sync(FULLMASK, yin, 31);
+    }
+#pragma unroll
+    for (int c = 1; c < NCH; ++c) {
+      if (c < nch) {
+        const float a3 = c == nch - 1 ? alast : a1;
+        float Y = fmaf(a3, fmaf(a1, fmaf(a1, v[c][0], v[c][1]), v[c][2]), v[c][3]);
+        float t = __shfl_up_sync(FULLMASK, Y, 1);
+        if (lane >= 1) Y = fmaf(a4, t, Y);
+        t = __shfl_up_sync(FULLMASK, Y, 2);
+        if (lane >= 2) Y = fmaf(a8, t, Y);
+        t = __shfl_up_sync(FULLMASK, Y, 4);
+        if (lane >= 4) Y = fmaf(a16, t, Y);
+        Y = fmaf(apw, carry, Y);
+        float yin = __shfl_up_sync(FULLMASK, Y, 1);
+        if (lane == 0) yin = carry;
+        v[c][0] = fmaf(a1, yin, v[c][0]);
+        v[c][1] = fmaf(a1, v[c][0], v[c][1]);
+        v[c][2] = fmaf(a1, v[c][1], v[c][2]);
+        v[c][3] = fmaf(a3, v[c][2], v[c][3]);
+        carry = __shfl_sync(FULLMASK, v[c][3], 31);
+      }
+    }
+    // ---- backward sweep: x[r] = z[r] + m[r] x[r+1], z = Dinv y, m = -U Dinv (m = 0 at row n)
+    carry = 0.f;
+#pragma unroll
+    for (int c = NCH - 1; c >= 1; --c) {
+      if (c < nch) {
+        const float z0 = p.Dinf * v[c][0], z1 = p.Dinf * v[c][1], z2 = p.Dinf * v[c][2];
+        const float z3 = (c == nch - 1 ? dlast : p.Dinf) * v[c][3];
+        float X = fmaf(m1, fmaf(m1, fmaf(m1, z3, z2), z1), z0);  // x at the lane's first row, nothing entering
+        float t = __shfl_down_sync(FULLMASK, X, 1);
+        if (lane < 31) X = fmaf(m4, t, X);
+        t = __shfl_down_sync(FULLMASK, X, 2);
+        if (lane < 30) X = fmaf(m8, t, X);
+        t = __shfl_down_sync(FULLMASK, X, 4);
+        if (lane < 28) X = fmaf(m16, t, X);
+        X = fmaf(mpw, carry, X);
+        float xin = __shfl_down_sync(FULLMASK, X, 1);
+        if (lane == 31) xin = carry;
+        v[c][3] = fmaf(m1, xin, z3);
+        v[c][2] = fmaf(m1, v[c][3], z2);
+        v[c][1] = fmaf(m1, v[c][2], z1);
+        v[c][0] = fmaf(m1, v[c][1], z0);
+        carry = __shfl_sync(FULLMASK, v[c][0], 0);
+      }
+    }
+    {
+      float zl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) zl[j] = dh[j] * v[0][j];
+      float M = Mh, Z = zl[3];
+#pragma unroll
+      for (int j = 2; j >= 0; --j) Z = fmaf(mh[j], Z, zl[j]);
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        const float M2 = __shfl_down_sync(FULLMASK, M, d), Z2 = __shfl_down_sync(FULLMASK, Z, d);
+        if (lane + d < 32) {
+          Z = fmaf(M, Z2, Z);
+          M = M * M2;
+        }
+      }
+      // the carry from chunk 1 reaches the last lanes only: fold it in through lanes 31, 30, ... with the scanned M
+      const float X = fmaf(M, carry, Z);  // M = product over lanes lane..min(lane+7,31): exact for lane >= 24
+      float xin = __shfl_down_sync(FULLMASK, lane >= 24 ? X : Z, 1);
+      if (lane == 31) xin = carry;
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        v[0][j] = fmaf(mh[j], xin, zl[j]);
+        xin = v[0][j];
+      }
+    }
+    // ---- Woodbury correction
+    if (wood) {
+      float c1 = 0.f, cn = 0.f;
+      for (int q = 0; q < p.nv; ++q) {
+        const int r = p.vrow[q];
+        const int cr = (r - 1) >> 7, jr = (r - 1) & 3;
+        float pick = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pick = (c == cr && j == jr) ? v[c][j] : pick;
+        const float xv = __shfl_sync(FULLMASK, pick, ((r - 1) & 127) >> 2);
+        c1 = fmaf(p.W1[q], xv, c1);
+        cn = fmaf(p.Wn[q], xv, cn);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[0][j] = fmsub_(z1r[j], c1, v[0][j]);
+#pragma unroll
+      for (int c = 1; c < NCH; ++c) {
+        const float cc = c == nch - 1 ? cn : 0.f;  // (a branch here makes the compiler index v[] dynamically)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c][j] = fmsub_(znr[j], cc, v[c][j]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (c < nch) __stcs(out + c * 32 + lane, make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
+  }
+}
+
+// shapes the one-warp-per-line kernel takes: Float32, contiguous axis, 128 | n, enough lines to give every SM 16 warps
+template <typename T>
+static bool warpline_shape_ok(int dev, int axis, int64_t n, int64_t lines) {
+  return sizeof(T) == 4 && axis == 0 && n % 128 == 0 && n >= 256 && n <= 2048 && lines >= 16 * (int64_t)sm_count(dev);
+}
+
 // ================================================================== kernel: any n, any system
 // One thread per line, sweeps in global memory (2 reads + 2 writes): used for short lines (n < 128)
 // and for systems whose factors do not settle (never the case for the reference's systems).
@@ -606,6 +809,31 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
     B200_CUDA_OK(cudaGetLastError());
     return 0;
   }
+  if constexpr (sizeof(T) == 4) {
+    // Float32 lines along the contiguous axis that fit a warp's registers: one warp per line, warp-scan recurrences
+    const bool aligned = ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+    if (nseg == 1 && aligned && warpline_shape_ok<T>(dev, axis, n, lines) && job.plan.P <= 128 && job.plan.Hz <= 128) {
+      StageScope sc("prefilter_axis0_warpline", st);
+      auto go = [&](auto kern) -> int {
+        int per_sm = 0;
+        B200_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+        const int64_t blocks = std::min<int64_t>((lines + 3) / 4, (int64_t)sm_count(dev) * std::max(per_sm, 1));
+        kern<<<(unsigned)blocks, 128, 0, st>>>(src, dst, job.plan, lines);
+        return 0;
+      };
+      int rc;
+      if (n <= 512)
+        rc = go(prefilter_warpline_kernel<4>);
+      else if (n <= 1024)
+        rc = go(prefilter_warpline_kernel<8>);
+      else
+        rc = go(prefilter_warpline_kernel<16>);
+      if (rc) return rc;
+      count_launch();
+      B200_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
   StageScope sc(axis == 0 ? "prefilter_axis0_contiguous" : (axis == 1 ? "prefilter_axis1_strided" : "prefilter_axis2+_strided"), st);
   if (axis == 0) {
     using Cfg = ContigCfg<T>;
@@ -646,7 +874,7 @@ static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int
   const int mult = axis == 0 ? 32 : B;  // the contiguous-axis kernel works in 32-row chunks
   nseg = 1;
   const int64_t want = (int64_t)sm_count(dev) * 1024;
-  if (fast_ok && lines < want / 2) {
+  if (fast_ok && lines < want / 2 && !warpline_shape_ok<T>(dev, axis, n, lines)) {
     const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
     nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
   }

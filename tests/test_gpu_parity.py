@@ -97,6 +97,31 @@ def test_prefilter_axis_with_host_factors(pkg, orc):
         assert rel_err(got, ref) <= 1e-6 if dtype == np.float32 else rel_err(got, ref) <= 1e-14
 
 
+@pytest.mark.parametrize("n0", [256, 384, 512, 640, 1024, 1152, 2048])
+def test_prefilter_warp_per_line_kernel(pkg, orc, n0):
+    """Float32 lines along the contiguous axis whose padded length is a multiple of 128 (256..2048) take the
+    one-warp-per-line kernel (warp-scan recurrences, csrc/prefilter.cu): every system the reference defines, padded
+    and unpadded, against the oracle, and the stage list says which kernel ran."""
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(n0)
+    for it in specs(m):
+        if it.degree.code == 1:
+            continue
+        pad = 2 if m.core.needs_padding(it) else 0
+        A = rng.standard_normal((n0 - pad, 2400)).astype(np.float32)  # >= 16 lines per SM
+        ref = orc.prefilter(A, it)
+        L.b200itp_profile_enable(1)
+        itp = m.interpolate(A, it)
+        import torch
+        torch.cuda.synchronize()
+        L.b200itp_profile_enable(0)
+        assert "prefilter_axis0_warpline" in m._lib.profile_stages(), (it, n0)
+        got = itp.coefs_array()
+        assert got.shape == ref.shape and got.shape[0] == n0
+        assert rel_err(got, ref) <= TOL[np.dtype(np.float32)], (it, n0, rel_err(got, ref))
+
+
 def test_prefilter_c3_property_full_size(pkg):
     """BASELINE config C3 at full size (512^3 Float32, Cubic(Periodic(OnGrid()))): the oracle would take minutes,
     so check the size-independent property instead: applying the periodic (1/6, 2/3, 1/6) stencil along every
