@@ -291,6 +291,139 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? PF_STRIDED_MINB : 1) pre
   }
 }
 
+// ================================================================== kernel: axis > 1, Float32, bulk-copy ring
+// Same work split and arithmetic as prefilter_strided_kernel (thread <-> line, blocks of B rows, one block of
+// look-ahead), but HBM traffic never passes through registers: a row of the CTA's 128 lines is 512 contiguous bytes, so
+// one thread moves whole blocks with bulk async copies (cp.async.bulk, the TMA engine's 1-D form) into NS input stages
+// in shared memory, completion signalled on an mbarrier per stage, and finished blocks leave the same way from one
+// output stage (shared -> global bulk stores).  An input stage is refilled as soon as every thread has taken its
+// column, so NS blocks (8 KB each) are in flight per CTA while the register file only holds the three blocks the
+// recurrences work on.  Threads touch only their own column of a stage (bank = lane: conflict-free); the CTA-wide
+// hazards are the refill of an input stage and the bulk store reading the output stage: two __syncthreads per block
+// and a fence.proxy.async between the threads' writes and the store.
+__device__ __forceinline__ unsigned smem_addr(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef PF_BULK_STAGES
+#define PF_BULK_STAGES 2  // input stages; with the output stage 24 KB per CTA
+#endif
+#ifndef PF_BULK_LINES
+#define PF_BULK_LINES 128
+#endif
+#ifndef PF_BULK_MINB
+#define PF_BULK_MINB 7  // 7 CTAs per SM: the 2048 CTAs of a 512^3 pass are two full waves
+#endif
+struct BulkCfg {
+  static constexpr int B = Tune<float>::B;
+  static constexpr int NS = PF_BULK_STAGES;
+  static constexpr int LINES = PF_BULK_LINES;
+  static constexpr unsigned ROW_BYTES = LINES * 4;
+  static constexpr size_t smem_bytes = (size_t)(NS + 1) * B * ROW_BYTES + NS * sizeof(uint64_t);
+};
+
+__global__ void __launch_bounds__(BulkCfg::LINES, PF_BULK_MINB) prefilter_strided_bulk_kernel(
+    const float *src, float *dst, const __grid_constant__ AxisPlan<float> p, int64_t R1, int nb1) {
+  using T = float;
+  constexpr int B = BulkCfg::B, NS = BulkCfg::NS, LINES = BulkCfg::LINES;
+  extern __shared__ __align__(128) unsigned char pf_bulk_smem[];
+  T *ring = reinterpret_cast<T *>(pf_bulk_smem);            // [NS][B][LINES] input stages
+  T *ostage = ring + (size_t)NS * B * LINES;                // [B][LINES] output stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(pf_bulk_smem + (size_t)(NS + 1) * B * BulkCfg::ROW_BYTES);
+  const int tid = threadIdx.x;
+  const int b1 = (int)(blockIdx.x % nb1);
+  const int64_t i2 = blockIdx.x / nb1;
+  const int n = p.n;
+  const int nblk = n / B;  // n % B == 0 (host)
+  const int64_t off = (int64_t)b1 * LINES + R1 * (int64_t)n * i2;
+  const T *in = src + off;
+  T *out = dst + off;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_load = [&](int bi) {  // thread 0
+    const int slot = bi % NS;
+    mbar_arrive_expect_tx(&full[slot], B * BulkCfg::ROW_BYTES);
+#pragma unroll
+    for (int j = 0; j < B; ++j)
+      bulk_load(ring + ((size_t)slot * B + j) * LINES, in + (int64_t)(bi * B + j) * R1, BulkCfg::ROW_BYTES, &full[slot]);
+  };
+  if (tid == 0)
+    for (int bi = 0; bi < NS && bi < nblk; ++bi) issue_load(bi);
+
+  T c1 = T(0), cn = T(0);
+  if (p.nv > 0) woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[tid + (int64_t)(r - 1) * R1]; }, c1, cn);
+
+  T yprev[B], v[B], xout[B];
+  T carry = T(0);
+#pragma unroll 1
+  for (int bi = 0; bi <= nblk; ++bi) {
+    const int r0 = 1 + bi * B;
+    const int cnt = bi < nblk ? B : 0;
+    if (bi < nblk) {
+      const int slot = bi % NS;
+      mbar_wait(&full[slot], (unsigned)(bi / NS) & 1u);
+      const T *st = ring + (size_t)slot * B * LINES + tid;
+#pragma unroll
+      for (int j = 0; j < B; ++j) v[j] = st[j * LINES];
+    }
+    const bool emit = bi > 0;
+    pipeline_step<T, B>(p, r0, cnt, v, yprev, B, carry, emit, c1, cn, xout);
+    if (tid == 0) bulk_wait_read<0>();  // the previous block's stores have read the output stage
+    __syncthreads();                    // ... and every thread has taken its column of input stage bi % NS
+    if (tid == 0 && bi + NS < nblk) issue_load(bi + NS);
+    if (emit) {
+#pragma unroll
+      for (int j = 0; j < B; ++j) ostage[j * LINES + tid] = xout[j];
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0 && emit) {
+#pragma unroll
+      for (int j = 0; j < B; ++j)
+        bulk_store(out + (int64_t)((bi - 1) * B + j) * R1, ostage + (size_t)j * LINES, BulkCfg::ROW_BYTES);
+      bulk_commit();
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) yprev[j] = v[j];
+  }
+  if (tid == 0) bulk_wait_read<0>();  // the output stage must outlive the stores that read it
+}
+
 // ================================================================== kernel: axis 1 (contiguous lines)
 // Work item = (line, segment).  A CTA owns ITEMS consecutive items and walks them in chunks of 32 rows.
 // Input chunks are staged through a STAGES-deep ring of shared-memory tiles filled with cp.async
@@ -834,7 +967,12 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
       return 0;
     }
   }
-  StageScope sc(axis == 0 ? "prefilter_axis0_contiguous" : (axis == 1 ? "prefilter_axis1_strided" : "prefilter_axis2+_strided"), st);
+  const bool use_bulk = axis > 0 && sizeof(T) == 4 && nseg == 1 && R1 % BulkCfg::LINES == 0 && n % BulkCfg::B == 0 &&
+                        n >= 4 * BulkCfg::B && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+  StageScope sc(axis == 0 ? "prefilter_axis0_contiguous"
+                          : (axis == 1 ? (use_bulk ? "prefilter_axis1_strided_bulk" : "prefilter_axis1_strided")
+                                       : (use_bulk ? "prefilter_axis2+_strided_bulk" : "prefilter_axis2+_strided")),
+                st);
   if (axis == 0) {
     using Cfg = ContigCfg<T>;
     const int64_t nitems = lines * nseg;
@@ -856,6 +994,16 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
     else
       rc = go(prefilter_contig_kernel<T, (sizeof(T) == 8 ? 8 : 4)>);
     if (rc) return rc;
+  } else if (use_bulk) {
+    if constexpr (sizeof(T) == 4) {
+      const int64_t nb1 = R1 / BulkCfg::LINES;
+      const int64_t blocks = nb1 * R2;
+      if (blocks > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
+      B200_CUDA_OK(cudaFuncSetAttribute(prefilter_strided_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)BulkCfg::smem_bytes));
+      prefilter_strided_bulk_kernel<<<(unsigned)blocks, BulkCfg::LINES, BulkCfg::smem_bytes, st>>>(src, dst, job.plan, R1,
+                                                                                                    (int)nb1);
+    }
   } else {
     const int64_t nb1 = (R1 + 127) / 128;
     const int64_t blocks = nb1 * nseg * R2;

@@ -122,6 +122,34 @@ def test_prefilter_warp_per_line_kernel(pkg, orc, n0):
         assert rel_err(got, ref) <= TOL[np.dtype(np.float32)], (it, n0, rel_err(got, ref))
 
 
+@pytest.mark.parametrize("padded", [(256, 144, 8), (384, 208, 400)])
+def test_prefilter_strided_bulk_kernel(pkg, orc, padded):
+    """Float32 passes along non-contiguous axes with 128 | (lines per row) and 16 | n take the bulk-copy ring kernel
+    (cp.async.bulk + mbarrier stages, csrc/prefilter.cu): short lines (fewer blocks than stages) and long ones, padded
+    and unpadded systems, against the oracle; the stage list says which kernel ran."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(padded[1])
+    its = [m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Cubic(m.Free(m.OnGrid()))),
+           m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), m.BSpline(m.Cubic(m.Line(m.OnCell())))]
+    for it in its:
+        pad = 2 if m.core.needs_padding(it) else 0
+        A = rng.standard_normal(tuple(s - pad for s in padded)).astype(np.float32)
+        ref = orc.prefilter(A, it)
+        L.b200itp_profile_enable(1)
+        itp = m.interpolate(A, it)
+        torch.cuda.synchronize()
+        L.b200itp_profile_enable(0)
+        stages = m._lib.profile_stages()
+        assert "prefilter_axis1_strided_bulk" in stages, (it, list(stages))
+        if padded[2] >= 128:
+            assert "prefilter_axis2+_strided_bulk" in stages, (it, list(stages))
+        got = itp.coefs_array()
+        assert got.shape == ref.shape == padded
+        assert rel_err(got, ref) <= TOL[np.dtype(np.float32)], (it, padded, rel_err(got, ref))
+
+
 def test_prefilter_c3_property_full_size(pkg):
     """BASELINE config C3 at full size (512^3 Float32, Cubic(Periodic(OnGrid()))): the oracle would take minutes,
     so check the size-independent property instead: applying the periodic (1/6, 2/3, 1/6) stencil along every

@@ -5,6 +5,7 @@ import b200_loader, torch
 m = b200_loader.load(); L = m._lib.lib()
 n = 512
 it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+torch.manual_seed(0)
 A = torch.randn((n, n, n), device="cuda")
 work = A.reshape(-1).clone()
 for _ in range(3):
@@ -17,3 +18,7 @@ torch.cuda.synchronize()
 L.b200itp_profile_enable(0)
 st = m._lib.profile_stages()
 print({k: round(sum(v) / len(v), 4) for k, v in st.items()}, "total", round(sum(sum(v) / len(v) for v in st.values()), 4))
+chk = A.reshape(-1).clone()
+m.prefilter_(chk, (n, n, n), (it,) * 3, 0)
+torch.cuda.synchronize()
+print("checksum", float(chk.double().abs().sum()), float(chk[12345678]), float(chk[-1]))
