@@ -49,6 +49,11 @@ enum { B200ITP_TAG_EXACT = 0, B200ITP_TAG_F32 = 1, B200ITP_TAG_F64 = 2 };
 
 /* interpolation degree per axis (src/b-splines/{linear,quadratic,cubic}.jl) */
 enum { B200ITP_LINEAR = 1, B200ITP_QUADRATIC = 2, B200ITP_CUBIC = 3 };
+/* degree 0, `Constant{Nearest|Previous|Next}` (src/b-splines/constant.jl:69-108): one tap per axis, weight 1 (an Int:
+ * it does not widen the result type), gradient and hessian weights 0; bc is THROW (OnGrid) or PERIODIC (OnCell).
+ * Evaluated by the run-time-degree kernels; never prefiltered. */
+enum { B200ITP_CONSTANT_NEAREST = 4, B200ITP_CONSTANT_PREVIOUS = 5, B200ITP_CONSTANT_NEXT = 6 };
+#define B200ITP_IS_CONSTANT(deg) ((deg) >= B200ITP_CONSTANT_NEAREST && (deg) <= B200ITP_CONSTANT_NEXT)
 
 /* boundary conditions (src/Interpolations.jl:89-118); also the extrapolation flags
  * (src/extrapolation/extrapolation.jl:106-151) */

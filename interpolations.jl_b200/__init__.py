@@ -4,8 +4,8 @@ Public names mirror the reference (src/Interpolations.jl:3-31).  The directory n
 dot, so it is imported through `b200_loader.load()` (repo root) under the module name
 `interpolations_jl_b200`.
 """
-from .flags import (BSpline, Cubic, Flat, Free, Line, Linear, Natural, OnCell, OnGrid, Periodic, Quadratic,
-                    Reflect, Throw)
+from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural, Nearest, Next, OnCell, OnGrid, Periodic,
+                    Previous, Quadratic, Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
                    bounds, evaluate_debug, evaluate_from_host, evaluate_grid, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, lbounds, out_dtype,
@@ -13,7 +13,7 @@ from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtra
 from . import _lib, parallel
 
 __all__ = [
-    "BSpline", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
+    "BSpline", "Constant", "Nearest", "Previous", "Next", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
     "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .flags import (BC_FLAT, BC_LINE, BC_PERIODIC, BC_REFLECT, BC_THROW, CUBIC, ETP_FILL, ETP_FLAGS, ETP_NONE,
-                    F32, F64, LINEAR, ONCELL, ONGRID, QUADRATIC, TAG_EXACT, TAG_F32, TAG_F64, BoundaryCondition,
+                    CONSTANT_NEAREST, CONSTANT_NEXT, F32, F64, LINEAR, ONCELL, ONGRID, QUADRATIC, TAG_EXACT, TAG_F32, TAG_F64, BoundaryCondition,
                     BSpline, Flat, Free, Line, OnCell, OnGrid, Periodic, Reflect, Throw, iscomplete, needs_padding)
 from .ranges import AbstractRange, UnitRange
 
@@ -87,6 +87,8 @@ def out_dtype_code(D) -> int:
     """promote(weights type of every axis, eltype(coefs) [, fill value]) -> F32/F64; mirrors
     b200itp_out_dtype."""
     _, tw = stage_tags(D)
+    # Constant axes carry Int weights (constant.jl:106): they do not widen the result
+    tw = [t for d, t in enumerate(tw) if not (CONSTANT_NEAREST <= D.degree[d] <= CONSTANT_NEXT)]
     t = max(tw + [TAG_F32 if D.coef_dtype == F32 else TAG_F64])
     if D.etp_kind == ETP_FILL:
         t = max(t, D.fill_tag)

@@ -47,7 +47,7 @@ int derive_chain(const b200itp_desc *D, Chain &c) {
     c.t2[d] = t;
     if (D->has_scale) t = tmax(t, D->inner_tag[d]);
     c.tw[d] = t;
-    tacc = tmax(tacc, t);
+    if (!B200ITP_IS_CONSTANT(D->degree[d])) tacc = tmax(tacc, t);  // Constant weights are Ints (constant.jl:106)
     if (c.t1[d] != c.t1[0] || c.t2[d] != c.t2[0] || c.tw[d] != c.tw[0]) c.homogeneous = false;
   }
   if (D->etp_kind == B200ITP_ETP_FILL) tacc = tmax(tacc, D->fill_tag);
@@ -77,7 +77,16 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
     if (D->size[d] < 1 || D->parent_len[d] < 1) B200_FAIL(B200ITP_E_SIZE, "eval: empty axis %d", d);
     if (D->parent_len[d] > INT_MAX / 2) B200_FAIL(B200ITP_E_SIZE, "eval: axis %d too long", d);
     const int deg = D->degree[d];
-    if (deg < B200ITP_LINEAR || deg > B200ITP_CUBIC) B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: degree %d on axis %d is not on the hot path", deg, d);
+    if ((deg < B200ITP_LINEAR || deg > B200ITP_CUBIC) && !B200ITP_IS_CONSTANT(deg))
+      B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: degree %d on axis %d is not on the hot path", deg, d);
+    if (B200ITP_IS_CONSTANT(deg)) {
+      if (D->bc[d] != B200ITP_BC_THROW && D->bc[d] != B200ITP_BC_PERIODIC)
+        B200_FAIL(B200ITP_E_BADARG, "eval: Constant takes Throw(OnGrid()) or Periodic(OnCell()) (constant.jl:33)");
+      if (D->etp_kind == B200ITP_ETP_FLAGS && (D->etp_lo[d] == B200ITP_BC_LINE || D->etp_hi[d] == B200ITP_BC_LINE))
+        B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: Line extrapolation of a Constant axis is not on the hot path");
+      if (D->has_scale && out_grad)
+        B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: gradients of scaled Constant axes are not on the hot path");
+    }
     const int cf = D->coef_first[d];
     if (cf != 0 && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: coef_first must be 0 or 1");
     const int64_t need = D->parent_len[d] + (cf == 0 ? 2 : 0);
@@ -145,6 +154,7 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
   int deg = D->degree[0];
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
+  if (B200ITP_IS_CONSTANT(deg)) deg = 0;  // Constant axes are served by the run-time degree variant only
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
   StageScope sc(mode == 0 ? "eval_direct_value" : (mode == 1 ? "eval_direct_gradient" : "eval_direct_hessian"), st);
   int rc;
@@ -257,8 +267,11 @@ extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coe
   int rc = derive_chain(D, c);
   if (rc) B200_FAIL(rc, "hessian: invalid descriptor");
   if (!c.homogeneous) B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: mixed per-axis promotion is not on the hot path");
-  for (int d = 0; d < D->ndims; ++d)
+  for (int d = 0; d < D->ndims; ++d) {
     if (!coords[d]) B200_FAIL(B200ITP_E_BADARG, "hessian: null coordinate array %d", d);
+    if (D->has_scale && B200ITP_IS_CONSTANT(D->degree[d]))
+      B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: scaled Constant axes are not on the hot path");
+  }
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "hessian: cannot select device %d", dev);
   if (first_oob) *first_oob = -1;

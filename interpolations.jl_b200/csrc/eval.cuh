@@ -187,6 +187,32 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
   // NaN coordinates (undefined in the reference: unsafe_trunc(Int, NaN)) must not fault: the taps are
   // taken at node 1 and the NaN weights make the result NaN.
   const bool isnan_x = !(x == x);
+  if (DEG == 0 && B200ITP_IS_CONSTANT(deg)) {
+    // constant.jl:69-108: floorbounds / ceilbounds / roundbounds (indexing.jl:168-197) with ax = 1:n
+    TW xm;
+    if (deg == B200ITP_CONSTANT_PREVIOUS) {
+      xm = per ? s_floor<TW>(x) : (x < TW(1) ? s_floor<TW>(x + TW(0.5)) : s_floor<TW>(x + TW(0)));
+    } else if (deg == B200ITP_CONSTANT_NEXT) {
+      xm = x > TW(n) ? s_ceil<TW>(x + TW(0.5)) : s_ceil<TW>(x + TW(0));
+    } else {
+      const TW xh = x + TW(0.5);
+      xm = ((double)x < (double)n + 0.5) ? s_floor<TW>(xh) : s_ceil<TW>(xh) - TW(1);
+    }
+    first = isnan_x ? 1 : (int)xm;
+    // Previous/Next with Periodic(OnCell) wrap (constant.jl:91-104); Nearest does not (its in-bounds index is in 1:n)
+    if (per && deg != B200ITP_CONSTANT_NEAREST) first = modrange1(first, n);
+    A.L = 1;
+    A.wv[0] = TW(1);
+    A.wg[0] = TW(0);
+    A.wh[0] = TW(0);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) A.wv[k] = A.wg[k] = A.wh[k] = TW(0);
+    A.first = first;
+    A.contiguous = true;
+#pragma unroll
+    for (int k = 0; k < AxisTaps<DEG, TW>::LMAX; ++k) A.pos[k] = first - cf;
+    return;
+  }
   if (deg == B200ITP_CUBIC) {
     TW xf;
     if (!per) {  // cubic.jl:40-46, floorbounds indexing.jl:183-187

@@ -13,6 +13,7 @@ from typing import Optional
 F32, F64 = 0, 1
 TAG_EXACT, TAG_F32, TAG_F64 = 0, 1, 2
 LINEAR, QUADRATIC, CUBIC = 1, 2, 3
+CONSTANT_NEAREST, CONSTANT_PREVIOUS, CONSTANT_NEXT = 4, 5, 6
 BC_THROW, BC_FLAT, BC_LINE, BC_FREE, BC_PERIODIC, BC_REFLECT = 0, 1, 2, 3, 4, 5
 ONGRID, ONCELL = 0, 1
 ETP_NONE, ETP_FLAGS, ETP_FILL = 0, 1, 2
@@ -128,6 +129,67 @@ class Linear(Degree):
         self.bc = bc
 
 
+class ConstantInterpType:
+    """`Nearest` / `Previous` / `Next` (constant.jl:1-31)."""
+    code = -1
+
+    def __repr__(self):
+        return type(self).__name__
+
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+
+class Nearest(ConstantInterpType):
+    code = CONSTANT_NEAREST
+
+
+class Previous(ConstantInterpType):
+    code = CONSTANT_PREVIOUS
+
+
+class Next(ConstantInterpType):
+    code = CONSTANT_NEXT
+
+
+class Constant(Degree):
+    """`Constant()` == Constant{Nearest}(Throw(OnGrid())); `Constant(Previous)`, `Constant(Next)`;
+    `Constant(kind, Periodic())` == Constant{kind}(Periodic(OnCell())) (constant.jl:33-49)."""
+
+    def __init__(self, kind=None, bc: Optional[BoundaryCondition] = None):
+        if isinstance(kind, BoundaryCondition) and bc is None:  # Constant(bc) defaults to Nearest
+            kind, bc = None, kind
+        if kind is None:
+            kind = Nearest()
+        elif isinstance(kind, type) and issubclass(kind, ConstantInterpType):
+            kind = kind()
+        if not isinstance(kind, ConstantInterpType):
+            raise TypeError("Constant(kind): kind must be Nearest, Previous or Next")
+        if bc is None:
+            bc = Throw(OnGrid())
+        elif isinstance(bc, Periodic) and bc.gt is None:
+            bc = Periodic(OnCell())
+        ok = (isinstance(bc, Throw) and isinstance(bc.gt, OnGrid)) or (
+            isinstance(bc, Periodic) and isinstance(bc.gt, OnCell))
+        if not ok:
+            raise TypeError(f"Constant accepts only Throw(OnGrid()) or Periodic(OnCell()), got {bc!r}")
+        self.kind = kind
+        self.bc = bc
+        self.code = kind.code
+
+    def __repr__(self):
+        return f"Constant({self.kind!r}, {self.bc!r})"
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self.kind == other.kind and self.bc == other.bc
+
+    def __hash__(self):
+        return hash(("Constant", self.kind, self.bc))
+
+
 class Quadratic(Degree):
     """`Quadratic(bc)`; default Line(OnGrid()) (quadratic.jl:4-8)."""
     code = QUADRATIC
@@ -153,7 +215,7 @@ class BSpline:
 
     def __init__(self, degree: Degree):
         if not isinstance(degree, Degree):
-            raise TypeError("BSpline(degree): degree must be Linear/Quadratic/Cubic")
+            raise TypeError("BSpline(degree): degree must be Constant/Linear/Quadratic/Cubic")
         self.degree = degree
 
     def __repr__(self):

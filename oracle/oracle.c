@@ -178,6 +178,31 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
   tv dx;
   int64_t xi;
   A->edge = 0;
+  if (B200ITP_IS_CONSTANT(deg)) {
+    /* constant.jl:69-108 with floorbounds / ceilbounds / roundbounds (indexing.jl:168-197), ax = 1:n */
+    double xm;
+    if (deg == B200ITP_CONSTANT_PREVIOUS) {
+      if (periodic)
+        xm = floor(x.v); /* constant.jl:91-98 */
+      else
+        xm = x.v < 1.0 ? floor(rnd(t, x.v + 0.5)) : floor(rnd(t, x.v + 0.0));
+    } else if (deg == B200ITP_CONSTANT_NEXT) {
+      xm = x.v > (double)n ? ceil(rnd(t, x.v + 0.5)) : ceil(rnd(t, x.v + 0.0));
+    } else {
+      double xh = rnd(t, x.v + 0.5);
+      xm = x.v < (double)n + 0.5 ? floor(xh) : rnd(t, ceil(xh) - 1.0);
+    }
+    xi = isnan(x.v) ? 1 : (int64_t)xm;
+    if (periodic && deg != B200ITP_CONSTANT_NEAREST) xi = modrange(xi, n); /* constant.jl:97,103 */
+    A->L = 1;
+    A->base = (int)xi;
+    A->pos[0] = xi - D->coef_first[d];
+    /* value_weights (1,), gradient_weights (0,), hessian_weights (0,): Ints (constant.jl:106-108) */
+    A->wv[0] = mk(1.0, B200ITP_TAG_EXACT);
+    A->wg[0] = mk(0.0, B200ITP_TAG_EXACT);
+    A->wh[0] = mk(0.0, B200ITP_TAG_EXACT);
+    return;
+  }
   if (deg == B200ITP_CUBIC) {
     double xf;
     if (!periodic) {
@@ -328,7 +353,8 @@ static void bspline_eval(const b200itp_desc *D, const void *coefs, const tv *x, 
     if (edge_bits && ax[d].edge) *edge_bits |= (B200ITP_BR_EDGE << (4 * d));
   }
   C.lt[N] = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
-  for (int d = N - 1; d >= 0; d--) C.lt[d] = tmax(x[d].t, C.lt[d + 1]);
+  for (int d = N - 1; d >= 0; d--) /* Constant axes: Int weights do not widen the partial sums */
+    C.lt[d] = tmax(B200ITP_IS_CONSTANT(D->degree[d]) ? B200ITP_TAG_EXACT : x[d].t, C.lt[d + 1]);
   if (want_val) {
     for (int d = 0; d < N; d++) C.w[d] = ax[d].wv;
     *val = mk(reduce_level(&C, 0, 0), C.lt[0]);
@@ -614,7 +640,8 @@ static void inner_hess(const b200itp_desc *D, const void *coefs, const tv *x, tv
     s *= D->size[d];
   }
   C.lt[N] = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
-  for (int d = N - 1; d >= 0; d--) C.lt[d] = tmax(xl[d].t, C.lt[d + 1]);
+  for (int d = N - 1; d >= 0; d--)
+    C.lt[d] = tmax(B200ITP_IS_CONSTANT(D->degree[d]) ? B200ITP_TAG_EXACT : xl[d].t, C.lt[d + 1]);
   for (int i = 0; i < N; i++)
     for (int j = i; j < N; j++) {
       for (int d = 0; d < N; d++)
@@ -671,7 +698,7 @@ int orc_weights(int degree, int tag, double x, int64_t n, double *wv, double *wg
   D.ndims = 1;
   D.degree[0] = degree;
   D.parent_len[0] = n;
-  D.coef_first[0] = degree == B200ITP_LINEAR ? 1 : 0;
+  D.coef_first[0] = (degree == B200ITP_LINEAR || B200ITP_IS_CONSTANT(degree)) ? 1 : 0;
   axis_taps A;
   axis_setup(&D, 0, mk(rnd(tag, x), tag), &A);
   for (int j = 0; j < A.L; j++) {

@@ -560,6 +560,58 @@ def test_ordered_evaluation_fuzz(pkg):
     L.b200itp_eval_sorted_set_min_queries(1 << 20)
 
 
+def constant_specs(m):
+    out = []
+    for kind in (m.Nearest, m.Previous, m.Next):
+        out += [m.BSpline(m.Constant(kind)), m.BSpline(m.Constant(kind, m.Periodic()))]
+    return out
+
+
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+def test_constant_axes_bit_exact(pkg, orc, coef_dtype, coord_dtype):
+    """`Constant{Nearest|Previous|Next}` axes (constant.jl:69-108), alone and mixed with Linear /
+    Quadratic / Cubic axes, bare and under Flat / Periodic / Reflect extrapolation: values, gradients (zero along the
+    Constant axes), stencil indices and the result type `==` the oracle's."""
+    m = pkg
+    rng = np.random.default_rng(77)
+    for ndims, shape in ((1, (41,)), (2, (23, 19)), (3, (11, 9, 7))):
+        A = rng.standard_normal(shape).astype(coef_dtype)
+        for it in constant_specs(m):
+            itp = m.interpolate(A, it)
+            assert np.array_equal(itp.coefs_array(), A)  # never padded or prefiltered
+            coords = [adversarial_coords(rng, itp.lbounds()[d], itp.ubounds()[d], shape[d], 2500, coord_dtype)[:2000]
+                      for d in range(ndims)]
+            check_eval(m, orc, itp, coords)
+            assert m.out_dtype(itp, coord_dtype) == coef_dtype
+    A = rng.standard_normal((21, 18, 15)).astype(coef_dtype)
+    mixes = [(m.BSpline(m.Constant()), m.BSpline(m.Linear()), m.BSpline(m.Cubic(m.Line(m.OnGrid())))),
+             (m.BSpline(m.Cubic(m.Periodic(m.OnCell()))), m.BSpline(m.Constant(m.Previous, m.Periodic())),
+              m.BSpline(m.Quadratic(m.Reflect(m.OnCell())))),
+             (m.BSpline(m.Linear()), m.BSpline(m.Quadratic(m.Free(m.OnGrid()))), m.BSpline(m.Constant(m.Next)))]
+    for its in mixes:
+        itp = m.interpolate(A, its)
+        coords = [adversarial_coords(rng, itp.lbounds()[d], itp.ubounds()[d], A.shape[d], 2500, coord_dtype)[:2000]
+                  for d in range(3)]
+        check_eval(m, orc, itp, coords)
+        for flag in (m.Flat(), m.Periodic(), m.Reflect()):
+            etp = m.extrapolate(itp, flag)
+            wide = [rng.uniform(-3.0, A.shape[d] + 4.0, 2000).astype(coord_dtype) for d in range(3)]
+            check_eval(m, orc, etp, wide)
+
+
+def test_constant_unsupported_combinations_are_reported(pkg):
+    m = pkg
+    A = np.arange(30, dtype=np.float32).reshape(5, 6)
+    itp = m.interpolate(A, m.BSpline(m.Constant()))
+    x = np.linspace(1, 5, 7, dtype=np.float32)
+    y = np.linspace(1, 6, 7, dtype=np.float32)
+    with pytest.raises(ValueError):
+        m.extrapolate(itp, m.Line())(x, y)
+    want = A[np.floor(x + 0.5).astype(int) - 1, np.floor(y + 0.5).astype(int) - 1]
+    assert np.array_equal(itp(x, y).cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
 def test_hessian_bit_exact(pkg, orc, coef_dtype, coord_dtype):

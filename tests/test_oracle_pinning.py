@@ -461,3 +461,75 @@ def test_hessian_against_gradient_differences_and_exact_polynomials(orc):
     lin = orc.interpolate(A, m.BSpline(m.Linear()))
     Hl = orc.hessian(lin, *[rng.uniform(1, 6, 10) for _ in range(3)])
     assert not np.diagonal(Hl, axis1=1, axis2=2).any()
+
+
+def test_constant_reference_testset(orc):
+    """test/b-splines/constant.jl:20-182: Constant{Nearest|Previous|Next}, Throw(OnGrid()) and Periodic(OnCell()):
+    bounds, node reproduction, constancy between the nodes, the periodic wrap of the first/last half cells, zero
+    gradients."""
+    import interpolations_jl_b200 as m
+    rng = np.random.default_rng(11)
+    N1 = 10
+    A1 = rng.random(N1) * 100
+    A2 = rng.random((N1, N1)) * 100
+    A3 = rng.random((N1, N1, N1)) * 100
+    assert m.Constant() == m.Constant(m.Nearest) == m.Constant(m.Nearest(), m.Throw(m.OnGrid()))
+    assert m.Constant(m.Periodic()) == m.Constant(m.Nearest, m.Periodic(m.OnCell()))
+
+    def ev(itp, *x):
+        return orc.evaluate(itp, *[np.array([float(c)]) for c in x])[0][0]
+
+    for kind, lo_off, hi_off in ((m.Nearest, 0, 0), (m.Previous, -1, 0), (m.Next, 0, 1)):
+        it = m.BSpline(m.Constant(kind))
+        itp1, itp2, itp3 = orc.interpolate(A1, it), orc.interpolate(A2, it), orc.interpolate(A3, it)
+        assert itp1.lbounds() == (1,) and itp1.ubounds() == (N1,)
+        assert np.array_equal(itp1.coefs, A1)  # parent(itp) === itp.coefs: no padding, no prefilter
+        for i in range(1, N1 + 1):  # check_inbounds_values
+            assert ev(itp1, i) == A1[i - 1]
+        for i in range(2, N1):
+            assert ev(itp1, i + .3) == A1[i - 1 + (1 if kind is m.Next else 0)]
+            assert ev(itp1, i - .3) == A1[i - 1 + (-1 if kind is m.Previous else 0)]
+            for j in range(2, N1):
+                want = {m.Nearest: A2[i - 1, j - 1], m.Previous: A2[i - 1, j - 2], m.Next: A2[i, j - 1]}[kind]
+                assert ev(itp2, i + .4, j - .3) == want
+        want3 = {m.Nearest: A3[4, 5, 6], m.Previous: A3[4, 4, 6], m.Next: A3[5, 5, 7]}[kind]
+        assert ev(itp3, 5.4, 5.7, 7.1) == ev(itp3, 5.4, 5.7, 7.2) == want3
+        with pytest.raises(m.BoundsError):
+            ev(itp1, 0.9)
+        with pytest.raises(m.BoundsError):
+            ev(itp1, N1 + 0.1)
+        g = orc.evaluate(itp2, np.array([3.3]), np.array([4.6]), want_grad=True)[1]
+        assert np.array_equal(g, np.zeros((1, 2)))
+
+    per = orc.interpolate(A1, m.BSpline(m.Constant(m.Periodic())))
+    prev = orc.interpolate(A1, m.BSpline(m.Constant(m.Previous, m.Periodic())))
+    nxt = orc.interpolate(A1, m.BSpline(m.Constant(m.Next, m.Periodic())))
+    for itp in (per, prev, nxt):
+        assert itp.lbounds() == (0.5,) and itp.ubounds() == (N1 + 0.5,)
+        for i in range(1, N1 + 1):
+            assert ev(itp, i) == A1[i - 1]
+    for i in range(2, N1):
+        assert A1[i - 1] == ev(per, i + .3) == ev(per, i - .3)
+        assert A1[i - 1] == ev(prev, i + .3) == ev(prev, i + .6)
+        assert A1[i - 2] == ev(prev, i - .3) == ev(prev, i - .6)
+        assert A1[i] == ev(nxt, i + .3) == ev(nxt, i + .6)
+        assert A1[i - 1] == ev(nxt, i - .3) == ev(nxt, i - .6)
+    assert A1[0] == ev(per, 1 - .3) == ev(per, 1 + .3)
+    assert A1[-1] == ev(per, N1 - .3) == ev(per, N1 + .3)
+    assert A1[0] == ev(prev, 1 + .3)
+    assert A1[-1] == ev(prev, N1 + .3) == ev(prev, 1 - .3)
+    assert A1[0] == ev(nxt, 1 - .3) == ev(nxt, N1 + .3)
+    assert A1[-1] == ev(nxt, N1 - .3)
+
+
+def test_constant_axes_do_not_widen_the_result(orc):
+    """Constant weights are Ints (constant.jl:106): Float32 samples stay Float32 under Float64 coordinates, and a mixed
+    (Constant, Linear) interpolant takes its type from the Linear axis."""
+    import interpolations_jl_b200 as m
+    A = np.arange(1, 31, dtype=np.float32).reshape(5, 6)
+    allc = orc.interpolate(A, m.BSpline(m.Constant()))
+    assert m.out_dtype(allc, np.float64) == np.float32
+    mixed = orc.interpolate(A, (m.BSpline(m.Constant(m.Previous)), m.BSpline(m.Linear())))
+    assert m.out_dtype(mixed, np.float64) == np.float64 and m.out_dtype(mixed, np.float32) == np.float32
+    v = orc.evaluate(mixed, np.array([2.7]), np.array([3.25]))[0][0]
+    assert v == 0.75 * A[1, 2] + 0.25 * A[1, 3]
