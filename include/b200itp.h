@@ -54,6 +54,13 @@ enum { B200ITP_LINEAR = 1, B200ITP_QUADRATIC = 2, B200ITP_CUBIC = 3 };
  * Evaluated by the run-time-degree kernels; never prefiltered. */
 enum { B200ITP_CONSTANT_NEAREST = 4, B200ITP_CONSTANT_PREVIOUS = 5, B200ITP_CONSTANT_NEXT = 6 };
 #define B200ITP_IS_CONSTANT(deg) ((deg) >= B200ITP_CONSTANT_NEAREST && (deg) <= B200ITP_CONSTANT_NEXT)
+/* `NoInterp()` axis (src/nointerp/nointerp.jl:1-25, indexing.jl:74,108,137-140): the coordinate is an index — it must
+ * hold an integer value (`Int(x)`; anything else is reported through first_oob like a BoundsError, the reference
+ * raises InexactError) — weight 1; the axis has NO gradient component: out_grad holds G = (number of axes that are not
+ * NOINTERP) components per query.  bc/gridtype of such an axis are THROW/ONGRID; bare or scaled interpolants only
+ * (the range of a NoInterp axis is the axis itself, scaling.jl:46,108). */
+enum { B200ITP_NOINTERP = 7 };
+#define B200ITP_IS_INDEXLIKE(deg) (B200ITP_IS_CONSTANT(deg) || (deg) == B200ITP_NOINTERP)
 
 /* boundary conditions (src/Interpolations.jl:89-118); also the extrapolation flags
  * (src/extrapolation/extrapolation.jl:106-151) */

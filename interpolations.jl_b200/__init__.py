@@ -4,7 +4,7 @@ Public names mirror the reference (src/Interpolations.jl:3-31).  The directory n
 dot, so it is imported through `b200_loader.load()` (repo root) under the module name
 `interpolations_jl_b200`.
 """
-from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural, Nearest, Next, OnCell, OnGrid, Periodic,
+from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural, Nearest, Next, NoInterp, OnCell, OnGrid, Periodic,
                     Previous, Quadratic, Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
@@ -13,7 +13,7 @@ from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtra
 from . import _lib, parallel
 
 __all__ = [
-    "BSpline", "Constant", "Nearest", "Previous", "Next", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
+    "BSpline", "Constant", "Nearest", "Previous", "Next", "NoInterp", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
     "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .flags import (BC_FLAT, BC_LINE, BC_PERIODIC, BC_REFLECT, BC_THROW, CUBIC, ETP_FILL, ETP_FLAGS, ETP_NONE,
-                    CONSTANT_NEAREST, CONSTANT_NEXT, F32, F64, LINEAR, ONCELL, ONGRID, QUADRATIC, TAG_EXACT, TAG_F32, TAG_F64, BoundaryCondition,
+                    CONSTANT_NEAREST, NOINTERP, F32, F64, LINEAR, ONCELL, ONGRID, QUADRATIC, TAG_EXACT, TAG_F32, TAG_F64, BoundaryCondition,
                     BSpline, Flat, Free, Line, OnCell, OnGrid, Periodic, Reflect, Throw, iscomplete, needs_padding)
 from .ranges import AbstractRange, UnitRange
 
@@ -88,7 +88,7 @@ def out_dtype_code(D) -> int:
     b200itp_out_dtype."""
     _, tw = stage_tags(D)
     # Constant axes carry Int weights (constant.jl:106): they do not widen the result
-    tw = [t for d, t in enumerate(tw) if not (CONSTANT_NEAREST <= D.degree[d] <= CONSTANT_NEXT)]
+    tw = [t for d, t in enumerate(tw) if not (CONSTANT_NEAREST <= D.degree[d] <= NOINTERP)]
     t = max(tw + [TAG_F32 if D.coef_dtype == F32 else TAG_F64])
     if D.etp_kind == ETP_FILL:
         t = max(t, D.fill_tag)
@@ -226,6 +226,9 @@ class ScaledInterpolation(AbstractInterpolation):
                 raise ValueError(f"The range {r} is incommensurate with the corresponding axis 1:{itp.parent_len[d]}")
             if not r.step > 0:
                 raise ValueError(f"The range {r} is in decreasing order; only ranges with positive steps are supported by scale().")
+            if itp.its[d].degree.code == NOINTERP and not (float(r.first) == 1.0 and float(r.step) == 1.0):  # scaling.jl:46
+                raise ValueError(f"The range {r} did not equal the corresponding axis of the interpolation object "
+                                 f"1:{itp.parent_len[d]}")
         self.itp = itp
         self.ranges = ranges
         self.ndims = itp.ndims
@@ -399,7 +402,7 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
         if not iscomplete(i):
             raise ValueError(f"OnGrid/OnCell is not supplied for some of the interpolation modes in {it}")
     for d in range(N):  # is_singleton_ok b-splines.jl:114-121
-        if shape[d] == 1:
+        if shape[d] == 1 and its[d].degree.code != NOINTERP:
             raise ValueError(f"size {shape} is inconsistent with {it}, use NoInterp along singleton dimensions")
     pad = [1 if needs_padding(i) else 0 for i in its]
     psize = tuple(shape[d] + 2 * pad[d] for d in range(N))
@@ -489,7 +492,8 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
     with torch.cuda.device(dev):
         tdev = coefs.device
         val = torch.empty(nq, dtype=odt, device=tdev) if want_value else None
-        grad = torch.empty(nq * N, dtype=odt, device=tdev) if want_grad else None
+        G = sum(1 for d in range(N) if D.degree[d] != NOINTERP)  # NoInterp axes have no component (indexing.jl:108)
+        grad = torch.empty(nq * G, dtype=odt, device=tdev) if want_grad else None
         dbg_i = torch.empty(nq * N, dtype=torch.int32, device=tdev) if debug else None
         dbg_b = torch.empty(nq, dtype=torch.int32, device=tdev) if debug else None
         ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in coords])
@@ -522,7 +526,7 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
     if want_value:
         out[0] = val.reshape(shape)
     if want_grad:
-        out[1] = grad.reshape(shape + (N,))
+        out[1] = grad.reshape(shape + (G,))
     if debug:
         out[2] = dbg_i.reshape(shape + (N,))
         out[3] = dbg_b.reshape(shape)

@@ -47,8 +47,21 @@ int derive_chain(const b200itp_desc *D, Chain &c) {
     c.t2[d] = t;
     if (D->has_scale) t = tmax(t, D->inner_tag[d]);
     c.tw[d] = t;
-    if (!B200ITP_IS_CONSTANT(D->degree[d])) tacc = tmax(tacc, t);  // Constant weights are Ints (constant.jl:106)
-    if (c.t1[d] != c.t1[0] || c.t2[d] != c.t2[0] || c.tw[d] != c.tw[0]) c.homogeneous = false;
+    if (!B200ITP_IS_INDEXLIKE(D->degree[d])) tacc = tmax(tacc, t);  // Constant / NoInterp weights are Ints (constant.jl:106)
+  }
+  {
+    // every axis that computes weights runs in one type; a NoInterp axis holds an integer, which every type carries
+    int ref = -1;
+    for (int d = 0; d < D->ndims; ++d)
+      if (D->degree[d] != B200ITP_NOINTERP) {
+        if (ref < 0) ref = d;
+        if (c.t1[d] != c.t1[ref] || c.t2[d] != c.t2[ref] || c.tw[d] != c.tw[ref]) c.homogeneous = false;
+      }
+    if (ref > 0) {  // the kernel reads the types of axis 0
+      c.t1[0] = c.t1[ref];
+      c.t2[0] = c.t2[ref];
+      c.tw[0] = c.tw[ref];
+    }
   }
   if (D->etp_kind == B200ITP_ETP_FILL) tacc = tmax(tacc, D->fill_tag);
   c.out_f64 = tacc == B200ITP_TAG_F64;
@@ -77,8 +90,15 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
     if (D->size[d] < 1 || D->parent_len[d] < 1) B200_FAIL(B200ITP_E_SIZE, "eval: empty axis %d", d);
     if (D->parent_len[d] > INT_MAX / 2) B200_FAIL(B200ITP_E_SIZE, "eval: axis %d too long", d);
     const int deg = D->degree[d];
-    if ((deg < B200ITP_LINEAR || deg > B200ITP_CUBIC) && !B200ITP_IS_CONSTANT(deg))
+    if ((deg < B200ITP_LINEAR || deg > B200ITP_CUBIC) && !B200ITP_IS_INDEXLIKE(deg))
       B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: degree %d on axis %d is not on the hot path", deg, d);
+    if (deg == B200ITP_NOINTERP) {
+      if (D->etp_kind != B200ITP_ETP_NONE)
+        B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: extrapolation of NoInterp axes is not on the hot path");
+      if (D->bc[d] == B200ITP_BC_PERIODIC) B200_FAIL(B200ITP_E_BADARG, "eval: NoInterp axes have no boundary condition");
+      if (D->has_scale && !(D->range_first[d] == 1.0 && D->range_step[d] == 1.0))
+        B200_FAIL(B200ITP_E_BADARG, "eval: the range of a NoInterp axis must equal the axis (scaling.jl:46)");
+    }
     if (B200ITP_IS_CONSTANT(deg)) {
       if (D->bc[d] != B200ITP_BC_THROW && D->bc[d] != B200ITP_BC_PERIODIC)
         B200_FAIL(B200ITP_E_BADARG, "eval: Constant takes Throw(OnGrid()) or Periodic(OnCell()) (constant.jl:33)");
@@ -127,6 +147,8 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
         B200_FAIL(B200ITP_E_BADARG, "eval: axis %d has two different flags but is not marked as a pair", d);
     }
   }
+  P.ngrad = 0;
+  for (int d = 0; d < D->ndims; ++d) P.grad_slot[d] = D->degree[d] == B200ITP_NOINTERP ? -1 : P.ngrad++;
   P.total = stride;
   P.vec_ok = ((uintptr_t)coefs % 16) == 0;
   P.has_scale = D->has_scale != 0;
@@ -154,7 +176,7 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
   int deg = D->degree[0];
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
-  if (B200ITP_IS_CONSTANT(deg)) deg = 0;  // Constant axes are served by the run-time degree variant only
+  if (B200ITP_IS_INDEXLIKE(deg)) deg = 0;  // Constant / NoInterp axes are served by the run-time degree variant only
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
   StageScope sc(mode == 0 ? "eval_direct_value" : (mode == 1 ? "eval_direct_gradient" : "eval_direct_hessian"), st);
   int rc;
@@ -271,6 +293,8 @@ extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coe
     if (!coords[d]) B200_FAIL(B200ITP_E_BADARG, "hessian: null coordinate array %d", d);
     if (D->has_scale && B200ITP_IS_CONSTANT(D->degree[d]))
       B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: scaled Constant axes are not on the hot path");
+    if (D->degree[d] == B200ITP_NOINTERP)
+      B200_FAIL(B200ITP_E_UNSUPPORTED, "hessian: NoInterp axes are not on the hot path");
   }
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "hessian: cannot select device %d", dev);

@@ -58,6 +58,9 @@ struct EvalParams {
   unsigned long long *first_oob;
   long long nq;
   const int *perm;  // optional: query q reads coordinates / writes results at perm[q]
+  // (new fields go last: the offsets of everything above are part of what the tuned kernels were compiled against)
+  int grad_slot[4];  // position of the axis' component in the gradient (-1: NoInterp axis, no component)
+  int ngrad;         // gradient components per query
 };
 
 template <typename A, typename B>
@@ -187,10 +190,13 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
   // NaN coordinates (undefined in the reference: unsafe_trunc(Int, NaN)) must not fault: the taps are
   // taken at node 1 and the NaN weights make the result NaN.
   const bool isnan_x = !(x == x);
-  if (DEG == 0 && B200ITP_IS_CONSTANT(deg)) {
-    // constant.jl:69-108: floorbounds / ceilbounds / roundbounds (indexing.jl:168-197) with ax = 1:n
+  if (DEG == 0 && B200ITP_IS_INDEXLIKE(deg)) {
+    // constant.jl:69-108: floorbounds / ceilbounds / roundbounds (indexing.jl:168-197) with ax = 1:n;
+    // NoInterp: Int(x) (nointerp.jl:17), x holds an integer (checked by the kernel)
     TW xm;
-    if (deg == B200ITP_CONSTANT_PREVIOUS) {
+    if (deg == B200ITP_NOINTERP) {
+      xm = x;
+    } else if (deg == B200ITP_CONSTANT_PREVIOUS) {
       xm = per ? s_floor<TW>(x) : (x < TW(1) ? s_floor<TW>(x + TW(0.5)) : s_floor<TW>(x + TW(0)));
     } else if (deg == B200ITP_CONSTANT_NEXT) {
       xm = x > TW(n) ? s_ceil<TW>(x + TW(0.5)) : s_ceil<TW>(x + TW(0));
@@ -200,7 +206,7 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
     }
     first = isnan_x ? 1 : (int)xm;
     // Previous/Next with Periodic(OnCell) wrap (constant.jl:91-104); Nearest does not (its in-bounds index is in 1:n)
-    if (per && deg != B200ITP_CONSTANT_NEAREST) first = modrange1(first, n);
+    if (per && (deg == B200ITP_CONSTANT_PREVIOUS || deg == B200ITP_CONSTANT_NEXT)) first = modrange1(first, n);
     A.L = 1;
     A.wv[0] = TW(1);
     A.wg[0] = TW(0);
@@ -559,6 +565,9 @@ __global__ void __launch_bounds__(256, N >= 3 ? 2 : (MODE == 0 ? 0 : 3)) eval_ke
         br |= B200ITP_BR_ABOVE << (4 * d);
         inb = false;
       }
+      if constexpr (DEG == 0) {  // NoInterp: Int(x) of a non-integer throws (nointerp.jl:17)
+        if (P.degree[d] == B200ITP_NOINTERP && !(x[d] == s_floor<TX>(x[d]))) inb = false;
+      }
     }
     // ---- extrapolation stage: xs (in TW; exact widening when the stage ran in TX)
     TW xs[N];
@@ -719,6 +728,17 @@ __global__ void __launch_bounds__(256, N >= 3 ? 2 : (MODE == 0 ? 0 : 3)) eval_ke
         store_out<double>(P.out_value, q, P.fill, P.out_f64);
       } else {
         store_out<TA>(P.out_value, q, val, P.out_f64);
+      }
+    } else if (DEG == 0) {  // mixed specs: NoInterp axes have no gradient component (indexing.jl:108)
+      const long long G = P.ngrad;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const int slot = P.grad_slot[d];
+        if (slot < 0) continue;
+        if (threw)
+          store_out<double>(P.out_grad, q * G + slot, nan(""), P.out_f64);
+        else
+          store_out<TA>(P.out_grad, q * G + slot, filled ? TA(0) : grad[d], P.out_f64);
       }
     } else {
 #pragma unroll

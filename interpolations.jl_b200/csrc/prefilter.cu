@@ -1145,7 +1145,7 @@ static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *s
   std::shared_ptr<const AxisJob<T>> keep[B200ITP_MAX_DIMS];
   const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int ax = 0; ax < ndims; ++ax) {
-    if (degree[ax] == B200ITP_LINEAR || B200ITP_IS_CONSTANT(degree[ax])) continue;  // prefiltering.jl:30
+    if (degree[ax] == B200ITP_LINEAR || B200ITP_IS_INDEXLIKE(degree[ax])) continue;  // prefiltering.jl:30, nointerp.jl:12
     int rc = cached_job<T>(size[ax], degree[ax], bc[ax], grid[ax], &keep[ax]);
     jobs[ax] = keep[ax].get();
     if (rc == B200ITP_E_UNSUPPORTED) {

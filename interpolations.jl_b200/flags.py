@@ -14,6 +14,7 @@ F32, F64 = 0, 1
 TAG_EXACT, TAG_F32, TAG_F64 = 0, 1, 2
 LINEAR, QUADRATIC, CUBIC = 1, 2, 3
 CONSTANT_NEAREST, CONSTANT_PREVIOUS, CONSTANT_NEXT = 4, 5, 6
+NOINTERP = 7
 BC_THROW, BC_FLAT, BC_LINE, BC_FREE, BC_PERIODIC, BC_REFLECT = 0, 1, 2, 3, 4, 5
 ONGRID, ONCELL = 0, 1
 ETP_NONE, ETP_FLAGS, ETP_FILL = 0, 1, 2
@@ -226,6 +227,30 @@ class BSpline:
 
     def __hash__(self):
         return hash(("BSpline", self.degree))
+
+
+class _NoInterpDegree(Degree):
+    code = NOINTERP
+
+    def __init__(self):
+        self.bc = Throw(OnGrid())  # bounds first(ax)..last(ax) (nointerp.jl:14-15); no boundary condition of its own
+
+
+class NoInterp(BSpline):
+    """`NoInterp()`: the axis takes integer indices, no interpolation (Interpolations.jl:51-52, nointerp.jl).  Modelled
+    as a BSpline-like flag so that per-axis tuples `(BSpline(Linear()), NoInterp())` go through the same plumbing."""
+
+    def __init__(self):
+        self.degree = _NoInterpDegree()
+
+    def __repr__(self):
+        return "NoInterp()"
+
+    def __eq__(self, other):
+        return isinstance(other, NoInterp)
+
+    def __hash__(self):
+        return hash("NoInterp")
 
 
 def iscomplete(it: BSpline) -> bool:

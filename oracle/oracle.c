@@ -178,10 +178,13 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
   tv dx;
   int64_t xi;
   A->edge = 0;
-  if (B200ITP_IS_CONSTANT(deg)) {
-    /* constant.jl:69-108 with floorbounds / ceilbounds / roundbounds (indexing.jl:168-197), ax = 1:n */
+  if (B200ITP_IS_INDEXLIKE(deg)) {
+    /* constant.jl:69-108 with floorbounds / ceilbounds / roundbounds (indexing.jl:168-197), ax = 1:n;
+     * NoInterp: weightedindex_parts = Int(x) (nointerp.jl:17) */
     double xm;
-    if (deg == B200ITP_CONSTANT_PREVIOUS) {
+    if (deg == B200ITP_NOINTERP) {
+      xm = x.v;
+    } else if (deg == B200ITP_CONSTANT_PREVIOUS) {
       if (periodic)
         xm = floor(x.v); /* constant.jl:91-98 */
       else
@@ -193,7 +196,7 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
       xm = x.v < (double)n + 0.5 ? floor(xh) : rnd(t, ceil(xh) - 1.0);
     }
     xi = isnan(x.v) ? 1 : (int64_t)xm;
-    if (periodic && deg != B200ITP_CONSTANT_NEAREST) xi = modrange(xi, n); /* constant.jl:97,103 */
+    if (periodic && (deg == B200ITP_CONSTANT_PREVIOUS || deg == B200ITP_CONSTANT_NEXT)) xi = modrange(xi, n); /* constant.jl:97,103 */
     A->L = 1;
     A->base = (int)xi;
     A->pos[0] = xi - D->coef_first[d];
@@ -354,7 +357,7 @@ static void bspline_eval(const b200itp_desc *D, const void *coefs, const tv *x, 
   }
   C.lt[N] = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
   for (int d = N - 1; d >= 0; d--) /* Constant axes: Int weights do not widen the partial sums */
-    C.lt[d] = tmax(B200ITP_IS_CONSTANT(D->degree[d]) ? B200ITP_TAG_EXACT : x[d].t, C.lt[d + 1]);
+    C.lt[d] = tmax(B200ITP_IS_INDEXLIKE(D->degree[d]) ? B200ITP_TAG_EXACT : x[d].t, C.lt[d + 1]);
   if (want_val) {
     for (int d = 0; d < N; d++) C.w[d] = ax[d].wv;
     *val = mk(reduce_level(&C, 0, 0), C.lt[0]);
@@ -485,6 +488,7 @@ static int eval_one(const b200itp_desc *D, const void *coefs, const double *xin,
       br |= B200ITP_BR_ABOVE << (4 * d);
       inb = 0;
     }
+    if (D->degree[d] == B200ITP_NOINTERP && !(xin[d] == floor(xin[d]))) inb = 0; /* Int(x): InexactError */
     g[d] = mk(0, xt);
   }
   const double nan = NAN;
@@ -594,8 +598,12 @@ int orc_eval(const b200itp_desc *D, const void *coefs, const void *const *coords
     uint32_t br;
     int threw = eval_one(D, coefs, x, out_value != NULL, out_grad != NULL, &v, g, dbg_index ? base : NULL, &br);
     if (out_value) out_value[q] = v;
-    if (out_grad)
-      for (int d = 0; d < N; d++) out_grad[q * N + d] = g[d];
+    if (out_grad) { /* NoInterp axes have no gradient component (indexing.jl:108) */
+      int G = 0, k = 0;
+      for (int d = 0; d < N; d++) G += D->degree[d] != B200ITP_NOINTERP;
+      for (int d = 0; d < N; d++)
+        if (D->degree[d] != B200ITP_NOINTERP) out_grad[q * G + k++] = g[d];
+    }
     if (dbg_index)
       for (int d = 0; d < N; d++) dbg_index[q * N + d] = base[d];
     if (dbg_branch) dbg_branch[q] = br;
@@ -641,7 +649,7 @@ static void inner_hess(const b200itp_desc *D, const void *coefs, const tv *x, tv
   }
   C.lt[N] = D->coef_dtype == B200ITP_F32 ? B200ITP_TAG_F32 : B200ITP_TAG_F64;
   for (int d = N - 1; d >= 0; d--)
-    C.lt[d] = tmax(B200ITP_IS_CONSTANT(D->degree[d]) ? B200ITP_TAG_EXACT : xl[d].t, C.lt[d + 1]);
+    C.lt[d] = tmax(B200ITP_IS_INDEXLIKE(D->degree[d]) ? B200ITP_TAG_EXACT : xl[d].t, C.lt[d + 1]);
   for (int i = 0; i < N; i++)
     for (int j = i; j < N; j++) {
       for (int d = 0; d < N; d++)
@@ -698,7 +706,7 @@ int orc_weights(int degree, int tag, double x, int64_t n, double *wv, double *wg
   D.ndims = 1;
   D.degree[0] = degree;
   D.parent_len[0] = n;
-  D.coef_first[0] = (degree == B200ITP_LINEAR || B200ITP_IS_CONSTANT(degree)) ? 1 : 0;
+  D.coef_first[0] = (degree == B200ITP_LINEAR || B200ITP_IS_INDEXLIKE(degree)) ? 1 : 0;
   axis_taps A;
   axis_setup(&D, 0, mk(rnd(tag, x), tag), &A);
   for (int j = 0; j < A.L; j++) {

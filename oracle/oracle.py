@@ -165,7 +165,8 @@ def evaluate(itp, *xs, want_value=True, want_grad=False, debug=False, nthreads=1
     if not isinstance(coefs, np.ndarray):
         coefs = coefs.cpu().numpy()
     val = np.empty(nq, np.float64) if want_value else None
-    grad = np.empty(nq * N, np.float64) if want_grad else None
+    G = sum(1 for d in range(N) if D.degree[d] != 7)  # NoInterp axes (code 7) have no gradient component
+    grad = np.empty(nq * G, np.float64) if want_grad else None
     bi = np.empty(nq * N, np.int32) if debug else None
     br = np.empty(nq, np.uint32) if debug else None
     ptrs = (C.c_void_p * N)(*[c.ctypes.data for c in cs])
@@ -179,7 +180,7 @@ def evaluate(itp, *xs, want_value=True, want_grad=False, debug=False, nthreads=1
         raise ValueError(f"orc_eval rc={rc}")
     if raise_oob and foob.value >= 0:
         raise pkg.BoundsError(f"oracle: BoundsError at query {foob.value}")
-    return (val.reshape(shape) if want_value else None, grad.reshape(shape + (N,)) if want_grad else None,
+    return (val.reshape(shape) if want_value else None, grad.reshape(shape + (G,)) if want_grad else None,
             bi.reshape(shape + (N,)) if debug else None, br.reshape(shape) if debug else None, foob.value)
 
 

@@ -600,6 +600,49 @@ def test_constant_axes_bit_exact(pkg, orc, coef_dtype, coord_dtype):
             check_eval(m, orc, etp, wide)
 
 
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+def test_nointerp_axes_bit_exact(pkg, orc, coef_dtype, coord_dtype):
+    """`NoInterp()` axes (nointerp.jl, indexing.jl:74,108,137-140): image-stack style specs, bare
+    and scaled; values, the compacted gradient (no component for the NoInterp axes), stencil indices `==` the oracle's,
+    a non-integer index is reported like a BoundsError."""
+    m = pkg
+    rng = np.random.default_rng(99)
+    A = rng.standard_normal((17, 5, 13)).astype(coef_dtype)
+    q = m.BSpline(m.Quadratic(m.Reflect(m.OnCell())))
+    c = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    lin = m.BSpline(m.Linear())
+    for its in ((q, m.NoInterp(), lin), (m.NoInterp(), lin, c), (c, q, m.NoInterp()), (m.NoInterp(), m.NoInterp(), lin),
+                (m.NoInterp(),) * 3):
+        itp = m.interpolate(A, its)
+        coords = []
+        for d in range(3):
+            if isinstance(its[d], m.NoInterp):
+                coords.append(rng.integers(1, A.shape[d] + 1, 3000).astype(coord_dtype))
+            else:
+                coords.append(adversarial_coords(rng, itp.lbounds()[d], itp.ubounds()[d], A.shape[d], 3500,
+                                                 coord_dtype)[:3000])
+        G = sum(not isinstance(i, m.NoInterp) for i in its)
+        check_eval(m, orc, itp, coords, grad=G > 0)
+        if G > 0:
+            assert m.gradient(itp, *coords).shape == (3000, G)
+        bad = [x.copy() for x in coords]
+        k = [d for d in range(3) if isinstance(its[d], m.NoInterp)][0]
+        bad[k][1234] += 0.25
+        with pytest.raises(m.BoundsError):
+            itp(*bad)
+        with pytest.raises(ValueError):
+            m.extrapolate(itp, m.Flat())(*coords)
+    # scaled image stack: the stack axis keeps its own indices
+    # (all interpolating axes OnGrid: Float32 coordinates widened on some axes only are outside the hot path)
+    itp = m.interpolate(A, (m.BSpline(m.Quadratic(m.Free(m.OnGrid()))), m.NoInterp(), lin))
+    rdt = np.float32 if coord_dtype == np.float32 else np.float64
+    sitp = m.scale(itp, m.jrange(rdt(-1.0), rdt(1.0), length=17), m.UnitRange(1, 5), m.jrange(rdt(0.0), rdt(6.0), length=13))
+    coords = [rng.uniform(sitp.lbounds()[0], sitp.ubounds()[0], 3000).astype(coord_dtype),
+              rng.integers(1, 6, 3000).astype(coord_dtype), rng.uniform(0.0, 6.0, 3000).astype(coord_dtype)]
+    check_eval(m, orc, sitp, coords)
+
+
 def test_constant_unsupported_combinations_are_reported(pkg):
     m = pkg
     A = np.arange(30, dtype=np.float32).reshape(5, 6)

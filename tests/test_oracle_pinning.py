@@ -533,3 +533,50 @@ def test_constant_axes_do_not_widen_the_result(orc):
     assert m.out_dtype(mixed, np.float64) == np.float64 and m.out_dtype(mixed, np.float32) == np.float32
     v = orc.evaluate(mixed, np.array([2.7]), np.array([3.25]))[0][0]
     assert v == 0.75 * A[1, 2] + 0.25 * A[1, 3]
+
+
+def test_nointerp_reference_testset(orc):
+    """test/nointerp.jl:1-10, test/gradient.jl:134-160, test/scaling/nointerp.jl:3-21: NoInterp axes index with
+    integers (a non-integer is an error), reproduce the samples, carry no gradient component, and keep the other
+    axes' interpolation untouched."""
+    import interpolations_jl_b200 as m
+    a = np.arange(1, 13, dtype=np.float64).reshape(4, 3).T  # reshape(1:12, 3, 4)
+    ai = orc.interpolate(a, m.NoInterp())
+    ii, jj = np.meshgrid(np.arange(1, 4), np.arange(1, 5), indexing="ij")
+    assert np.array_equal(orc.evaluate(ai, ii.astype(np.float64), jj.astype(np.float64))[0], a)
+    for bad in ((2.2, 2.0), (2.0, 2.2), (0.0, 1.0), (4.0, 1.0)):
+        with pytest.raises(m.BoundsError):
+            orc.evaluate(ai, np.array([bad[0]]), np.array([bad[1]]))
+    rng = np.random.default_rng(5)
+    nx = 10
+    A2 = rng.random((nx, nx)) * 100
+    for BC in (m.Flat, m.Line, m.Free, m.Periodic, m.Reflect):
+        for GT in (m.OnGrid, m.OnCell):
+            q = m.BSpline(m.Quadratic(BC(GT())))
+            itp_c = orc.interpolate(A2, (m.NoInterp(), q))
+            itp_d = orc.interpolate(A2, (q, m.NoInterp()))
+            col = [orc.interpolate(A2[i, :], q) for i in range(nx)]   # the 1-D interpolants a NoInterp axis selects
+            row = [orc.interpolate(A2[:, j], q) for j in range(nx)]
+            for _ in range(6):
+                x, y = rng.random(2) * (nx - 2) + 1.5
+                ix, iy = int(round(x)), int(round(y))
+                v, g = orc.evaluate(itp_c, np.array([float(ix)]), np.array([y]), want_grad=True)[:2]
+                v1, g1 = orc.evaluate(col[ix - 1], np.array([y]), want_grad=True)[:2]
+                assert g.shape == (1, 1) and v[0] == v1[0] and g[0, 0] == g1[0, 0]
+                v, g = orc.evaluate(itp_d, np.array([x]), np.array([float(iy)]), want_grad=True)[:2]
+                v1, g1 = orc.evaluate(row[iy - 1], np.array([x]), want_grad=True)[:2]
+                assert g.shape == (1, 1) and v[0] == v1[0] and g[0, 0] == g1[0, 0]
+    # scaled: the range of a NoInterp axis is the axis itself
+    xs = m.jrange(-np.pi, np.pi, length=11)
+    xv = np.linspace(-np.pi, np.pi, 11)
+    A = np.stack([np.sin(xv), np.cos(xv), np.sin(xv) * np.cos(xv)], axis=1)[:-1]
+    xs = m.jrange(float(xv[0]), float(xv[-2]), length=10)
+    itp = orc.interpolate(A, (m.BSpline(m.Quadratic(m.Periodic(m.OnGrid()))), m.NoInterp()))
+    sitp = m.scale(itp, xs, m.UnitRange(1, 3))
+    for k, f in enumerate((np.sin, np.cos, lambda t: np.sin(t) * np.cos(t))):
+        v = orc.evaluate(sitp, xv[:-1], np.full(10, k + 1.0))[0]
+        assert np.abs(v - f(xv[:-1])).max() < 0.05
+    g = orc.evaluate(sitp, np.array([np.pi / 3]), np.array([2.0]), want_grad=True)[1]
+    assert g.shape == (1, 1)
+    with pytest.raises(ValueError):
+        m.scale(itp, xs, m.jrange(0.0, 1.0, length=3))
