@@ -133,6 +133,10 @@ typedef struct b200itp_desc {
   int32_t etp_lo[B200ITP_MAX_DIMS], etp_hi[B200ITP_MAX_DIMS]; /* per-axis, per-side flags */
   int32_t fill_tag; /* Julia type of the fill value                                    */
   double fill_value;
+  /* first.(itp.parentaxes): 0 or 1 = the axes 1:n of `interpolate`; 2 = the inset axes 2:n-1 that `interpolate!`
+   * leaves on an axis whose degree pads (b-splines.jl:236-241 `padinset`): the coefficients then occupy 1:n
+   * (coef_first = 1, size = parent_len + 2) and the bounds are those of 2:n-1.  Not combined with scale. */
+  int32_t parent_first[B200ITP_MAX_DIMS];
 } b200itp_desc;
 
 /*

@@ -7,16 +7,18 @@ dot, so it is imported through `b200_loader.load()` (repo root) under the module
 from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural, Nearest, Next, NoInterp, OnCell, OnGrid, Periodic,
                     Previous, Quadratic, Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
+from .core import (constant_interpolation, cubic_spline_interpolation, linear_interpolation)
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
-                   bounds, evaluate_debug, evaluate_from_host, evaluate_grid, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, lbounds, out_dtype,
+                   bounds, evaluate_debug, evaluate_from_host, evaluate_grid, evaluate_sorted, extrapolate, gradient, gradient_sorted, hessian, interpolate, interpolate_inplace, lbounds, out_dtype,
                    prefilter_, scale, ubounds, value_and_gradient)
 from . import _lib, parallel
 
 __all__ = [
+    "constant_interpolation", "cubic_spline_interpolation", "linear_interpolation",
     "BSpline", "Constant", "Nearest", "Previous", "Next", "NoInterp", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
     "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",
-    "extrapolate", "gradient", "gradient_sorted", "hessian", "interpolate", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
+    "extrapolate", "gradient", "gradient_sorted", "hessian", "interpolate", "interpolate_inplace", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
     "value_and_gradient",
 ]

@@ -43,6 +43,7 @@ class Desc(C.Structure):
         ("etp_hi", C.c_int32 * MAX_DIMS),
         ("fill_tag", C.c_int32),
         ("fill_value", C.c_double),
+        ("parent_first", C.c_int32 * MAX_DIMS),
     ]
 
 

@@ -126,7 +126,8 @@ class AbstractInterpolation:
             it = bsp.its[d]
             D.size[d] = bsp.size[d]
             D.parent_len[d] = bsp.parent_len[d]
-            D.coef_first[d] = 0 if needs_padding(it) else 1
+            D.coef_first[d] = 0 if (needs_padding(it) and bsp.parent_first[d] == 1) else 1
+            D.parent_first[d] = bsp.parent_first[d]
             D.degree[d] = it.degree.code
             D.bc[d] = it.degree.bc.code
             D.gridtype[d] = it.degree.bc.gt.code
@@ -169,26 +170,29 @@ class AbstractInterpolation:
 class BSplineInterpolation(AbstractInterpolation):
     """Fields as in b-splines.jl:74-78: `coefs` (device, column-major, padded), `parentaxes`, `it`."""
 
-    def __init__(self, coefs, size, parent_len, its, device_index):
+    def __init__(self, coefs, size, parent_len, its, device_index, parent_first=None):
         self.coefs = coefs  # 1-D torch CUDA tensor (column-major linearisation)
         self.size = tuple(int(s) for s in size)
         self.parent_len = tuple(int(s) for s in parent_len)
         self.its = tuple(its)
         self.ndims = len(self.size)
+        # first.(parentaxes): 1, or 2 on the axes `interpolate!` insets (b-splines.jl:236-241)
+        self.parent_first = tuple(int(f) for f in parent_first) if parent_first is not None else (1,) * self.ndims
         self.device_index = device_index
         self.dtype_code = F32 if str(coefs.dtype).endswith("float32") else F64  # torch or numpy dtype
 
     @property
     def parentaxes(self):
-        return tuple(UnitRange(1, n) for n in self.parent_len)
+        return tuple(UnitRange(f, f + n - 1) for f, n in zip(self.parent_first, self.parent_len))
 
     def _bound(self, d):
         """lbound/ubound (b-splines.jl:141-158): OnGrid -> (first, last) Ints; OnCell -> first-0.5, last+0.5 Float64."""
         n = self.parent_len[d]
+        f = self.parent_first[d]
         gt = self.its[d].degree.bc.gt
         if isinstance(gt, OnCell):
-            return 0.5, n + 0.5, TAG_F64
-        return 1.0, float(n), TAG_EXACT
+            return f - 0.5, f + n - 1 + 0.5, TAG_F64
+        return float(f), float(f + n - 1), TAG_EXACT
 
     def lbounds(self):
         return tuple(self._bound(d)[0] if self._bound(d)[2] != TAG_EXACT else int(self._bound(d)[0])
@@ -216,6 +220,9 @@ class ScaledInterpolation(AbstractInterpolation):
         if not isinstance(itp, BSplineInterpolation):
             raise ValueError("scale(): only scale(interpolate(...)) is on the B200 hot path "
                              "(scale(extrapolate(...)) is not supported; use extrapolate(scale(...)))")
+        if any(f != 1 for f in itp.parent_first):
+            raise ValueError("scale(): an interpolate_inplace object with inset axes cannot be scaled "
+                             "(coordlookup maps onto 1:n, scaling.jl:102-115)")
         ranges = tuple(ranges)
         if len(ranges) != itp.ndims:
             raise ValueError("scale(): need one range per dimension")
@@ -419,6 +426,30 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
     return BSplineInterpolation(coefs, psize, shape, its, dev)
 
 
+def interpolate_inplace(A, it, device=None) -> BSplineInterpolation:
+    """`interpolate!(A, it)` (b-splines.jl:236-241): prefilter `A` itself — no padded copy, the array becomes the
+    coefficient array (a torch CUDA tensor that is already column-major is overwritten; anything else is converted
+    first) — and trim the domain where the degree would have padded: those axes are `2:n-1` (`padinset`)."""
+    torch = _torch()
+    dev = _device_index(device)
+    src, shape = _to_colmajor_device(A, dev)
+    N = len(shape)
+    if not 1 <= N <= MAX_DIMS:
+        raise ValueError(f"1..{MAX_DIMS} dimensions are supported, got {N}")
+    its = _its_tuple(it, N)
+    for i in its:
+        if not iscomplete(i):
+            raise ValueError(f"OnGrid/OnCell is not supplied for some of the interpolation modes in {it}")
+    inset = [1 if needs_padding(i) else 0 for i in its]
+    for d in range(N):
+        if shape[d] - 2 * inset[d] < 1 or (shape[d] == 1 and its[d].degree.code != NOINTERP):
+            raise ValueError(f"size {shape} is inconsistent with {it}")
+    with torch.cuda.device(dev):
+        prefilter_(src, shape, its, dev)
+    return BSplineInterpolation(src, shape, tuple(shape[d] - 2 * inset[d] for d in range(N)), its, dev,
+                                parent_first=tuple(1 + inset[d] for d in range(N)))
+
+
 def scale(itp, *ranges) -> ScaledInterpolation:
     """`scale(itp, ranges...)` (scaling.jl:33-37)."""
     if len(ranges) == 1 and isinstance(ranges[0], (tuple, list)):
@@ -436,6 +467,39 @@ def extrapolate(itp, et) -> Union[Extrapolation, FilledExtrapolation]:
     if isinstance(et, (bool, int, float, np.integer, np.floating)):
         return FilledExtrapolation(itp, et)
     raise TypeError(f"extrapolate(): bad scheme {et!r}")
+
+
+# ----------------------------------------------------------------------------- convenience constructors
+def _knot_ranges(knots):
+    ranges = tuple(knots) if isinstance(knots, (tuple, list)) else (knots,)
+    if not all(isinstance(r, AbstractRange) for r in ranges):
+        raise TypeError("only range knots (the scaled B-spline path) are on the B200 hot path; "
+                        "vector knots are Gridded interpolation")
+    return ranges
+
+
+def constant_interpolation(knots, vs, extrapolation_bc=None, device=None):
+    """`constant_interpolation(ranges, vs; extrapolation_bc = Throw())` (convenience-constructors.jl:3-4,16-18):
+    extrapolate(scale(interpolate(vs, BSpline(Constant())), ranges...), extrapolation_bc)."""
+    from .flags import Constant
+    etp = Throw() if extrapolation_bc is None else extrapolation_bc
+    return extrapolate(scale(interpolate(vs, BSpline(Constant()), device), *_knot_ranges(knots)), etp)
+
+
+def linear_interpolation(knots, vs, extrapolation_bc=None, device=None):
+    """`linear_interpolation(ranges, vs; extrapolation_bc = Throw())` (convenience-constructors.jl:7-8,22-24)."""
+    from .flags import Linear
+    etp = Throw() if extrapolation_bc is None else extrapolation_bc
+    return extrapolate(scale(interpolate(vs, BSpline(Linear()), device), *_knot_ranges(knots)), etp)
+
+
+def cubic_spline_interpolation(knots, vs, bc=None, extrapolation_bc=None, device=None):
+    """`cubic_spline_interpolation(ranges, vs; bc = Line(OnGrid()), extrapolation_bc = Throw())`
+    (convenience-constructors.jl:11-13,28-30)."""
+    from .flags import Cubic
+    etp = Throw() if extrapolation_bc is None else extrapolation_bc
+    return extrapolate(scale(interpolate(vs, BSpline(Cubic(Line(OnGrid()) if bc is None else bc)), device),
+                             *_knot_ranges(knots)), etp)
 
 
 # ----------------------------------------------------------------------------- evaluation

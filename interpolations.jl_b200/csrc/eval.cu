@@ -107,8 +107,16 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
       if (D->has_scale && out_grad)
         B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: gradients of scaled Constant axes are not on the hot path");
     }
-    const int cf = D->coef_first[d];
+    int cf = D->coef_first[d];
     if (cf != 0 && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: coef_first must be 0 or 1");
+    const int pf = D->parent_first[d] == 0 ? 1 : D->parent_first[d];
+    if (pf != 1 && pf != 2) B200_FAIL(B200ITP_E_BADARG, "eval: parent_first must be 1 or 2");
+    if (pf == 2) {  // interpolate!: coefficients 1:n, parent axes 2:n-1 -> the padded layout seen from x - 1
+      if (cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: inset parent axes go with unpadded coefficients (coef_first = 1)");
+      if (D->has_scale) B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: scale of an interpolate! object with inset axes is not supported");
+      cf = 0;
+      P.xshift[d] = 1;
+    }
     const int64_t need = D->parent_len[d] + (cf == 0 ? 2 : 0);
     if (D->size[d] != need) B200_FAIL(B200ITP_E_SIZE, "eval: size[%d]=%lld inconsistent with parent length %lld", d, (long long)D->size[d], (long long)D->parent_len[d]);
     if (D->bc[d] == B200ITP_BC_PERIODIC && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: periodic axes are unpadded");
@@ -177,6 +185,8 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
   if (B200ITP_IS_INDEXLIKE(deg)) deg = 0;  // Constant / NoInterp axes are served by the run-time degree variant only
+  for (int d = 0; d < D->ndims; ++d)
+    if (P.xshift[d]) deg = 0;  // ... and so are the inset axes of interpolate!
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
   StageScope sc(mode == 0 ? "eval_direct_value" : (mode == 1 ? "eval_direct_gradient" : "eval_direct_hessian"), st);
   int rc;
@@ -342,7 +352,7 @@ int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void
     if (D->degree[d] != deg) deg = 0;
   *uniform_degree = deg;
   *plain_f32 = c.homogeneous && D->etp_kind == B200ITP_ETP_NONE && !D->has_scale && D->coef_dtype == B200ITP_F32 &&
-               D->coord_dtype == B200ITP_F32 && !c.w_wide;
+               D->coord_dtype == B200ITP_F32 && !c.w_wide && !(P.xshift[0] | P.xshift[1] | P.xshift[2] | P.xshift[3]);
   return 0;
 }
 }  // namespace b200itp

@@ -61,6 +61,7 @@ struct EvalParams {
   // (new fields go last: the offsets of everything above are part of what the tuned kernels were compiled against)
   int grad_slot[4];  // position of the axis' component in the gradient (-1: NoInterp axis, no component)
   int ngrad;         // gradient components per query
+  int xshift[4];     // first(parentaxes) - 1: subtracted from the coordinate before the B-spline stage (interpolate!)
 };
 
 template <typename A, typename B>
@@ -451,7 +452,7 @@ __device__ __forceinline__ void bspline_hessian(const EvalParams &P, const TC *c
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     axis_setup<DEG, TWW, true>(P, d, xl[d], ax[d]);
-    first_idx[d] = ax[d].pos[0] + P.coef_first[d];
+    first_idx[d] = ax[d].pos[0] + P.coef_first[d] + (DEG == 0 ? P.xshift[d] : 0);
     if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
   }
 #pragma unroll
@@ -531,7 +532,7 @@ __device__ __forceinline__ void bspline_stage(const EvalParams &P, const TC *coe
   }
 #pragma unroll
   for (int d = 0; d < N; ++d) {
-    first_idx[d] = ax[d].pos[0] + P.coef_first[d];
+    first_idx[d] = ax[d].pos[0] + P.coef_first[d] + (DEG == 0 ? P.xshift[d] : 0);
     if (ax[d].edge) br |= B200ITP_BR_EDGE << (4 * d);
     grad_out[d] = (TAO)grad[d];
   }
@@ -633,6 +634,8 @@ __global__ void __launch_bounds__(256, N >= 3 ? 2 : (MODE == 0 ? 0 : 3)) eval_ke
           const TW lo = (TW)P.inner_lb[d], hi = (TW)P.inner_ub[d];
           xv = xv > hi ? hi : (xv < lo ? lo : xv);
         }
+        // interpolate!: parent axes 2:n-1 over coefficients 1:n == the padded layout one index further (x - 1 is exact)
+        if constexpr (DEG == 0) xv = xv - (TW)P.xshift[d];
         xl[d] = xv;
       }
       // ---- B-spline stage (weights in TW; the in-bounds gradient of an extrapolated Float32 query whose

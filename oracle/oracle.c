@@ -348,8 +348,14 @@ static void bspline_eval(const b200itp_desc *D, const void *coefs, const tv *x, 
   C.coefs = coefs;
   C.ax = ax;
   int64_t s = 1;
+  /* interpolate! (b-splines.jl:236-241): parent axes 2:n-1 over coefficients 1:n are the padded layout one index
+   * further; x - 1 is exact, so positions and weights are those of the reference */
+  b200itp_desc DD = *D;
   for (int d = 0; d < N; d++) {
-    axis_setup(D, d, x[d], &ax[d]);
+    const int sh = D->parent_first[d] == 2;
+    DD.coef_first[d] -= sh;
+    axis_setup(&DD, d, mk(x[d].v - sh, x[d].t), &ax[d]);
+    ax[d].base += sh;
     C.stride[d] = s;
     s *= D->size[d];
     if (base) base[d] = ax[d].base;
@@ -642,8 +648,11 @@ static void inner_hess(const b200itp_desc *D, const void *coefs, const tv *x, tv
   C.coefs = coefs;
   C.ax = ax;
   int64_t s = 1;
+  b200itp_desc DD = *D;
   for (int d = 0; d < N; d++) {
-    axis_setup(D, d, xl[d], &ax[d]);
+    const int sh = D->parent_first[d] == 2; /* interpolate!: see bspline_eval */
+    DD.coef_first[d] -= sh;
+    axis_setup(&DD, d, mk(xl[d].v - sh, xl[d].t), &ax[d]);
     C.stride[d] = s;
     s *= D->size[d];
   }

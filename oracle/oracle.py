@@ -134,11 +134,26 @@ def interpolate(A, it, nthreads=1) -> BSplineInterpolation:
     return BSplineInterpolation(np.ascontiguousarray(c.reshape(-1, order="F")), c.shape, A.shape, its, None)
 
 
+def interpolate_inplace(A, it, nthreads=1) -> BSplineInterpolation:
+    """`interpolate!(A, it)` on the CPU (b-splines.jl:236-241): the system of size n is solved on the samples
+    themselves and the axes a degree would have padded are trimmed to 2:n-1."""
+    A = np.asarray(A)
+    if A.dtype not in (np.float32, np.float64):
+        A = A.astype(np.float64)
+    its = _its_tuple(it, A.ndim)
+    flat = np.ascontiguousarray(A.reshape(-1, order="F")).copy()
+    prefilter_inplace(flat, A.shape, its, nthreads)
+    inset = [1 if needs_padding(i) else 0 for i in its]
+    return BSplineInterpolation(flat, A.shape, tuple(n - 2 * k for n, k in zip(A.shape, inset)), its, None,
+                                parent_first=tuple(1 + k for k in inset))
+
+
 def with_coefs(itp, coefs_flat: np.ndarray):
     """The same wrapper chain around other coefficients (e.g. the GPU's, copied to the host)."""
     from interpolations_jl_b200.core import Extrapolation, FilledExtrapolation, ScaledInterpolation
     b, s, e = itp._chain()
-    nb = BSplineInterpolation(np.ascontiguousarray(coefs_flat), b.size, b.parent_len, b.its, None)
+    nb = BSplineInterpolation(np.ascontiguousarray(coefs_flat), b.size, b.parent_len, b.its, None,
+                              parent_first=b.parent_first)
     out = nb
     if s is not None:
         out = ScaledInterpolation(nb, s.ranges)

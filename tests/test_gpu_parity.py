@@ -643,6 +643,63 @@ def test_nointerp_axes_bit_exact(pkg, orc, coef_dtype, coord_dtype):
     check_eval(m, orc, sitp, coords)
 
 
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+def test_interpolate_inplace(pkg, orc, coef_dtype):
+    """`interpolate!` (b-splines.jl:236-241): no padded copy, inset parent axes.  Coefficients
+    against the oracle's in-place prefilter, evaluation / gradients / stencil indices bit-exact on the GPU's
+    coefficients, bare and extrapolated; scaling such an object is refused as in the reference."""
+    m = pkg
+    rng = np.random.default_rng(31)
+    for shape in ((40,), (23, 19), (13, 11, 9)):
+        A = rng.standard_normal(shape).astype(coef_dtype)
+        for it in specs(m):
+            ref = orc.interpolate_inplace(A, it)
+            itp = m.interpolate_inplace(A, it)
+            assert itp.size == tuple(shape) and itp.parent_first == ref.parent_first and itp.lbounds() == ref.lbounds()
+            got = itp.coefs_array()
+            assert got.shape == tuple(shape)
+            assert rel_err(got, ref.coefs.reshape(shape, order="F")) <= TOL[np.dtype(coef_dtype)], (it, shape)
+            coords = [adversarial_coords(rng, itp.lbounds()[d] - (itp.parent_first[d] - 1),
+                                         itp.ubounds()[d] - (itp.parent_first[d] - 1), itp.parent_len[d], 1500,
+                                         np.float64)[:1200] + (itp.parent_first[d] - 1) for d in range(len(shape))]
+            coords = [np.clip(c, itp.lbounds()[d], itp.ubounds()[d]).astype(coef_dtype) for d, c in enumerate(coords)]
+            check_eval(m, orc, itp, coords)
+            if len(shape) == 2:
+                for flag in (m.Flat(), m.Line()):
+                    wide = [rng.uniform(-2.0, n + 3.0, 1200).astype(np.float64) for n in shape]
+                    check_eval(m, orc, m.extrapolate(itp, flag), wide)
+    itp = m.interpolate_inplace(rng.standard_normal((20, 20)).astype(coef_dtype), m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+    with pytest.raises(m.BoundsError):
+        itp(np.array([1.5]), np.array([3.0]))
+    with pytest.raises(ValueError):
+        m.scale(itp, m.jrange(0.0, 1.0, length=18), m.jrange(0.0, 1.0, length=18))
+
+
+def test_convenience_constructors(pkg, orc):
+    """convenience-constructors.jl:3-30 with range knots: shorthands for extrapolate(scale(interpolate(...)))
+    (test/convenience-constructors.jl: the shorthand equals the explicit chain)."""
+    m = pkg
+    rng = np.random.default_rng(3)
+    xs = m.jrange(1.0, 5.0, length=40)
+    ys = m.jrange(-2.0, 2.0, length=30)
+    A = rng.standard_normal((40, 30))
+    qx = rng.uniform(1.0, 5.0, 500)
+    qy = rng.uniform(-2.0, 2.0, 500)
+    for short, explicit in (
+            (m.linear_interpolation((xs, ys), A), m.extrapolate(m.scale(m.interpolate(A, m.BSpline(m.Linear())), xs, ys), m.Throw())),
+            (m.constant_interpolation((xs, ys), A), m.extrapolate(m.scale(m.interpolate(A, m.BSpline(m.Constant())), xs, ys), m.Throw())),
+            (m.cubic_spline_interpolation((xs, ys), A, extrapolation_bc=m.Flat()),
+             m.extrapolate(m.scale(m.interpolate(A, m.BSpline(m.Cubic(m.Line(m.OnGrid())))), xs, ys), m.Flat()))):
+        a, b = short(qx, qy).cpu().numpy(), explicit(qx, qy).cpu().numpy()
+        assert np.array_equal(a, b)
+        check_eval(m, orc, short, [qx, qy], grad=False)
+    with pytest.raises(m.BoundsError):
+        m.linear_interpolation(xs, A[:, 0])(np.array([5.5]))
+    assert m.linear_interpolation(xs, A[:, 0], extrapolation_bc=m.Line())(np.array([5.5])).shape == (1,)
+    with pytest.raises(TypeError):
+        m.linear_interpolation(np.linspace(0, 1, 40), A[:, 0])
+
+
 def test_constant_unsupported_combinations_are_reported(pkg):
     m = pkg
     A = np.arange(30, dtype=np.float32).reshape(5, 6)
@@ -686,6 +743,17 @@ def test_hessian_bit_exact(pkg, orc, coef_dtype, coord_dtype):
                 assert np.array_equal(H, np.swapaxes(H, 1, 2))
             if it.degree.code == 1:  # Linear: no curvature along an axis (linear.jl:58); mixed terms survive
                 assert not np.diagonal(H, axis1=1, axis2=2).any()
+    # mixed specs with a Constant axis: its row and column of the hessian are zero (constant.jl:107-108)
+    A = rng.standard_normal((12, 10, 9)).astype(coef_dtype)
+    its = (m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Constant(m.Previous)), m.BSpline(m.Quadratic(m.Flat(m.OnGrid()))))
+    itp = m.interpolate(A, its)
+    coords = [rng.uniform(1.0, n, 300).astype(coord_dtype) for n in A.shape]
+    H = m.hessian(itp, *coords).cpu().numpy()
+    Ho = orc.hessian(orc.with_coefs(itp, itp.coefs.cpu().numpy()), *coords)
+    assert np.array_equal(H, Ho.astype(H.dtype), equal_nan=True)
+    assert not H[:, 1, :].any() and not H[:, :, 1].any() and H[:, 0, 0].any()
+    with pytest.raises(ValueError):
+        m.hessian(m.interpolate(A, (its[0], m.NoInterp(), its[2])), *coords)
     itp = m.interpolate(rng.standard_normal((10, 9)).astype(coef_dtype), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))))
     with pytest.raises(m.BoundsError):
         m.hessian(m.extrapolate(itp, m.Line()), np.array([0.5], coord_dtype), np.array([3.0], coord_dtype))

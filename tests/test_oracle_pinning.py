@@ -580,3 +580,39 @@ def test_nointerp_reference_testset(orc):
     assert g.shape == (1, 1)
     with pytest.raises(ValueError):
         m.scale(itp, xs, m.jrange(0.0, 1.0, length=3))
+
+
+def test_interpolate_inplace_reference_properties(orc):
+    """`interpolate!` (b-splines.jl:236-241; exercised by every `(interpolate!, copy)` loop of test/b-splines/*.jl with
+    InterpolationTestUtils.check_axes / check_inbounds_values / check_oob / can_eval_near_boundaries): the axes a
+    degree would pad are trimmed to 2:n-1, the samples are reproduced on them, the bounds move with them."""
+    import interpolations_jl_b200 as m
+    rng = np.random.default_rng(21)
+    A1 = rng.random(12) * 10
+    A2 = rng.random((11, 9)) * 10
+    for deg in (m.Cubic, m.Quadratic):
+        for BC in (m.Flat, m.Line, m.Free, m.Periodic) + ((m.Reflect,) if deg is m.Quadratic else ()):
+            for GT in (m.OnGrid, m.OnCell):
+                it = m.BSpline(deg(BC(GT())))
+                itp = orc.interpolate_inplace(A1, it)
+                padded = BC is not m.Periodic
+                first, last = (2, 11) if padded else (1, 12)
+                assert (itp.parentaxes[0].first, itp.parentaxes[0].last) == (first, last)  # check_axes
+                half = 0.5 if GT is m.OnCell else 0
+                assert itp.lbounds() == (first - half,) and itp.ubounds() == (last + half,)
+                nodes = np.arange(first, last + 1, dtype=np.float64)
+                assert np.allclose(orc.evaluate(itp, nodes)[0], A1[first - 1:last], rtol=0, atol=1e-12)
+                for x in (first - half, last + half):  # can_eval_near_boundaries
+                    assert np.isfinite(orc.evaluate(itp, np.array([float(x)]))[0][0])
+                for x in (first - half - 0.1, last + half + 0.1):  # check_oob
+                    with pytest.raises(m.BoundsError):
+                        orc.evaluate(itp, np.array([x]))
+                itp2 = orc.interpolate_inplace(A2, (it, m.BSpline(m.Linear())))
+                xs, ys = np.meshgrid(nodes[nodes <= 11 - (1 if padded else 0)], np.arange(1.0, 10.0), indexing="ij")
+                got = orc.evaluate(itp2, xs, ys)[0]
+                assert np.allclose(got, A2[xs.astype(int) - 1, ys.astype(int) - 1], rtol=0, atol=1e-12)
+    it = m.BSpline(m.Cubic(m.Line(m.OnGrid())))
+    with pytest.raises(ValueError):
+        m.scale(orc.interpolate_inplace(A1, it), m.jrange(0.0, 1.0, length=10))
+    lin = orc.interpolate_inplace(A1, m.BSpline(m.Linear()))  # nothing to trim
+    assert lin.lbounds() == (1,) and lin.ubounds() == (12,) and np.array_equal(lin.coefs, A1)
