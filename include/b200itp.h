@@ -70,8 +70,13 @@ enum {
   B200ITP_BC_LINE = 2, /* == Natural */
   B200ITP_BC_FREE = 3,
   B200ITP_BC_PERIODIC = 4,
-  B200ITP_BC_REFLECT = 5
+  B200ITP_BC_REFLECT = 5,
+  /* Quadratic(InPlace(OnCell())) / Quadratic(InPlaceQ(OnCell())) (src/Interpolations.jl:104-109,
+   * quadratic.jl:61-65,91-110): unpadded coefficients, the outer taps are clamped to the axis; not extrapolation flags */
+  B200ITP_BC_INPLACE = 6,
+  B200ITP_BC_INPLACEQ = 7
 };
+#define B200ITP_IS_INPLACE_BC(bc) ((bc) == B200ITP_BC_INPLACE || (bc) == B200ITP_BC_INPLACEQ)
 
 /* grid type (src/Interpolations.jl:53-56) */
 enum { B200ITP_ONGRID = 0, B200ITP_ONCELL = 1 };

@@ -4,6 +4,7 @@ Public names mirror the reference (src/Interpolations.jl:3-31).  The directory n
 dot, so it is imported through `b200_loader.load()` (repo root) under the module name
 `interpolations_jl_b200`.
 """
+from .flags import (InPlace, InPlaceQ)
 from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural, Nearest, Next, NoInterp, OnCell, OnGrid, Periodic,
                     Previous, Quadratic, Reflect, Throw)
 from .ranges import FloatRange, StepRange, UnitRange, jrange
@@ -15,7 +16,7 @@ from . import _lib, parallel
 
 __all__ = [
     "constant_interpolation", "cubic_spline_interpolation", "linear_interpolation",
-    "BSpline", "Constant", "Nearest", "Previous", "Next", "NoInterp", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
+    "InPlace", "InPlaceQ", "BSpline", "Constant", "Nearest", "Previous", "Next", "NoInterp", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
     "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",

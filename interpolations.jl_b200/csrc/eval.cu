@@ -111,6 +111,11 @@ int fill_params(const b200itp_desc *D, const Chain &c, const void *coefs, const 
     if (cf != 0 && cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: coef_first must be 0 or 1");
     const int pf = D->parent_first[d] == 0 ? 1 : D->parent_first[d];
     if (pf != 1 && pf != 2) B200_FAIL(B200ITP_E_BADARG, "eval: parent_first must be 1 or 2");
+    if (B200ITP_IS_INPLACE_BC(D->bc[d])) {
+      if (deg != B200ITP_QUADRATIC || D->gridtype[d] != B200ITP_ONCELL || cf != 1)
+        B200_FAIL(B200ITP_E_BADARG, "eval: InPlace/InPlaceQ go with unpadded Quadratic OnCell axes (quadratic.jl:61-65,91-110)");
+      P.clamp_taps[d] = 1;
+    }
     if (pf == 2) {  // interpolate!: coefficients 1:n, parent axes 2:n-1 -> the padded layout seen from x - 1
       if (cf != 1) B200_FAIL(B200ITP_E_BADARG, "eval: inset parent axes go with unpadded coefficients (coef_first = 1)");
       if (D->has_scale) B200_FAIL(B200ITP_E_UNSUPPORTED, "eval: scale of an interpolate! object with inset axes is not supported");
@@ -186,7 +191,7 @@ int dispatch(const b200itp_desc *D, const Chain &c, const EvalParams &P, int mod
     if (D->degree[d] != deg) deg = 0;  // mixed per-axis degrees: run-time degree variant
   if (B200ITP_IS_INDEXLIKE(deg)) deg = 0;  // Constant / NoInterp axes are served by the run-time degree variant only
   for (int d = 0; d < D->ndims; ++d)
-    if (P.xshift[d]) deg = 0;  // ... and so are the inset axes of interpolate!
+    if (P.xshift[d] || P.clamp_taps[d]) deg = 0;  // ... and so are the inset axes of interpolate! and InPlace axes
   const bool cf32 = D->coef_dtype == B200ITP_F32, xf32 = D->coord_dtype == B200ITP_F32, wf32 = !c.w_wide;
   StageScope sc(mode == 0 ? "eval_direct_value" : (mode == 1 ? "eval_direct_gradient" : "eval_direct_hessian"), st);
   int rc;
@@ -352,7 +357,8 @@ int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void
     if (D->degree[d] != deg) deg = 0;
   *uniform_degree = deg;
   *plain_f32 = c.homogeneous && D->etp_kind == B200ITP_ETP_NONE && !D->has_scale && D->coef_dtype == B200ITP_F32 &&
-               D->coord_dtype == B200ITP_F32 && !c.w_wide && !(P.xshift[0] | P.xshift[1] | P.xshift[2] | P.xshift[3]);
+               D->coord_dtype == B200ITP_F32 && !c.w_wide && !(P.xshift[0] | P.xshift[1] | P.xshift[2] | P.xshift[3] |
+                                                              P.clamp_taps[0] | P.clamp_taps[1] | P.clamp_taps[2] | P.clamp_taps[3]);
   return 0;
 }
 }  // namespace b200itp

@@ -62,6 +62,7 @@ struct EvalParams {
   int grad_slot[4];  // position of the axis' component in the gradient (-1: NoInterp axis, no component)
   int ngrad;         // gradient components per query
   int xshift[4];     // first(parentaxes) - 1: subtracted from the coordinate before the B-spline stage (interpolate!)
+  int clamp_taps[4]; // Quadratic(InPlace/InPlaceQ): outer taps clamped to the axis (quadratic.jl:61-62)
 };
 
 template <typename A, typename B>
@@ -320,6 +321,10 @@ __device__ __forceinline__ void axis_setup(const EvalParams &P, int d, TW x, Axi
     if (per) {
       idx = modrange1(idx, n);
       if (k > 0 && idx - cf != A.pos[0] + k) A.contiguous = false;
+    }
+    if (DEG == 0 && P.clamp_taps[d]) {  // expand_index of InPlace/InPlaceQ: (max(xi-1, 1), xi, min(xi+1, n))
+      idx = idx < 1 ? 1 : (idx > n ? n : idx);
+      A.contiguous = false;
     }
     A.pos[k] = idx - cf;
   }

@@ -72,6 +72,10 @@ inline bool edge_row(int degree, int bc, int grid, EdgeRow &e) {
         return set(1, -2, {{3, 1}});
       case B200ITP_BC_FREE:  // quadratic.jl:158-170
         return set(1, -3, {{3, 3}, {4, -1}});
+      case B200ITP_BC_INPLACE:  // quadratic.jl:91-95 (bare LU)
+        return grid == B200ITP_ONCELL ? set(0.875, 0.125, {}) : false;
+      case B200ITP_BC_INPLACEQ:  // quadratic.jl:98-110
+        return grid == B200ITP_ONCELL ? set(1.125, -0.25, {{3, 0.125}}) : false;
       default:
         return false;
     }

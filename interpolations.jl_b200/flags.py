@@ -16,6 +16,7 @@ LINEAR, QUADRATIC, CUBIC = 1, 2, 3
 CONSTANT_NEAREST, CONSTANT_PREVIOUS, CONSTANT_NEXT = 4, 5, 6
 NOINTERP = 7
 BC_THROW, BC_FLAT, BC_LINE, BC_FREE, BC_PERIODIC, BC_REFLECT = 0, 1, 2, 3, 4, 5
+BC_INPLACE, BC_INPLACEQ = 6, 7
 ONGRID, ONCELL = 0, 1
 ETP_NONE, ETP_FLAGS, ETP_FILL = 0, 1, 2
 
@@ -95,6 +96,17 @@ class Periodic(BoundaryCondition):
 
 class Reflect(BoundaryCondition):
     code = BC_REFLECT
+
+
+class InPlace(BoundaryCondition):
+    """`InPlace(gt)`: prefiltering in place, no padding (Interpolations.jl:104-105; Quadratic OnCell only,
+    quadratic.jl:91-95)."""
+    code = BC_INPLACE
+
+
+class InPlaceQ(BoundaryCondition):
+    """`InPlaceQ(gt)`: like InPlace, exact for an underlying quadratic (Interpolations.jl:106-109, quadratic.jl:98-110)."""
+    code = BC_INPLACEQ
 
 
 Natural = Line  # Interpolations.jl:110
@@ -262,4 +274,4 @@ def needs_padding(it: BSpline) -> bool:
     """padded_axis: Cubic/Quadratic pad by one on each side unless Periodic
     (cubic.jl:86-87, quadratic.jl:64-65); Linear never (linear.jl:60)."""
     d = it.degree
-    return d.code in (QUADRATIC, CUBIC) and not isinstance(d.bc, Periodic)
+    return d.code in (QUADRATIC, CUBIC) and not isinstance(d.bc, (Periodic, InPlace, InPlaceQ))

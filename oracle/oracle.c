@@ -82,7 +82,8 @@ int orc_prefilter(int dtype, int ndims, const int64_t *size_in, const void *A, c
     deg[i] = degree[i];
     b[i] = bc[i];
     g[i] = grid[i];
-    pad[i] = ((deg[i] == B200ITP_CUBIC || deg[i] == B200ITP_QUADRATIC) && b[i] != B200ITP_BC_PERIODIC) ? 1 : 0;
+    pad[i] = ((deg[i] == B200ITP_CUBIC || deg[i] == B200ITP_QUADRATIC) && b[i] != B200ITP_BC_PERIODIC &&
+              !B200ITP_IS_INPLACE_BC(b[i])) ? 1 : 0; /* cubic.jl:86-87, quadratic.jl:64-65 */
     psz[i] = size_in[i] + 2 * pad[i];
   }
   if (dtype == B200ITP_F32) {
@@ -265,9 +266,10 @@ static void axis_setup(const b200itp_desc *D, int d, tv x, axis_taps *A) {
     dx = mk(rnd(t, x.v - xm), t);
     xi = isnan(x.v) ? 1 : (int64_t)xm;
     A->L = 3;
-    for (int j = 0; j < 3; j++) { /* quadratic.jl:57-60 */
+    for (int j = 0; j < 3; j++) { /* quadratic.jl:57-62 */
       int64_t idx = xi - 1 + j;
       if (periodic) idx = modrange(idx, n);
+      if (B200ITP_IS_INPLACE_BC(D->bc[d])) idx = idx < 1 ? 1 : (idx > n ? n : idx); /* (max(xi-1, first), xi, min(xi+1, last)) */
       if (j == 0) A->base = (int)idx;
       A->pos[j] = idx - D->coef_first[d];
     }

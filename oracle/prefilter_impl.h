@@ -107,6 +107,13 @@ static int NAME(orc_system)(int64_t n, int degree, int bc, int grid, REAL *dl, R
     } else if (bc == B200ITP_BC_PERIODIC) { /* quadratic.jl:180-189 */
       WB(1, n, du[0]);
       WB(n, 1, dl[n - 2]);
+    } else if (bc == B200ITP_BC_INPLACE && grid == B200ITP_ONCELL) { /* quadratic.jl:91-95 */
+      d[0] = d[n - 1] = RATIO(7, 8);
+    } else if (bc == B200ITP_BC_INPLACEQ && grid == B200ITP_ONCELL) { /* quadratic.jl:98-110 */
+      d[0] = d[n - 1] = RATIO(9, 8);
+      dl[n - 2] = du[0] = RATIO(-1, 4);
+      WB(1, 3, RATIO(1, 8));
+      WB(n, n - 2, RATIO(1, 8));
     } else {
       return 2;
     }

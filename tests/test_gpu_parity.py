@@ -675,6 +675,34 @@ def test_interpolate_inplace(pkg, orc, coef_dtype):
         m.scale(itp, m.jrange(0.0, 1.0, length=18), m.jrange(0.0, 1.0, length=18))
 
 
+@pytest.mark.parametrize("coef_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coord_dtype", [np.float32, np.float64])
+def test_inplace_boundary_conditions(pkg, orc, coef_dtype, coord_dtype):
+    """Quadratic(InPlace(OnCell())) / Quadratic(InPlaceQ(OnCell())) (quadratic.jl:61-65,91-110): unpadded systems
+    (InPlaceQ through Woodbury), clamped outer taps; through `interpolate` and `interpolate!`, alone and mixed."""
+    m = pkg
+    rng = np.random.default_rng(41)
+    for shape in ((300,), (37, 29), (150, 140, 9)):
+        A = rng.standard_normal(shape).astype(coef_dtype)
+        for BC in (m.InPlace, m.InPlaceQ):
+            it = m.BSpline(m.Quadratic(BC(m.OnCell())))
+            its = it if len(shape) < 3 else (it, m.BSpline(m.Cubic(m.Line(m.OnGrid()))), m.BSpline(m.Linear()))
+            ref = orc.interpolate(A, its)
+            for ctor in (m.interpolate, m.interpolate_inplace):
+                itp = ctor(A, its)
+                if ctor is m.interpolate:
+                    assert rel_err(itp.coefs_array(), ref.coefs.reshape(ref.size, order="F")) <= TOL[np.dtype(coef_dtype)]
+                assert itp.parent_first[0] == 1 and itp.size[0] == shape[0] and itp.lbounds()[0] == 0.5
+                coords = [adversarial_coords(rng, 0.5 if d == 0 else 1.0 + (itp.parent_first[d] - 1),
+                                             shape[d] + 0.5 if d == 0 else float(shape[d] - (itp.parent_first[d] - 1)),
+                                             shape[d], 1500, coord_dtype)[:1200] for d in range(len(shape))]
+                coords = [np.clip(c, coord_dtype(itp.lbounds()[d]), coord_dtype(itp.ubounds()[d])) for d, c in enumerate(coords)]
+                check_eval(m, orc, itp, coords)
+    bad = m.interpolate(rng.standard_normal(30).astype(coef_dtype), m.BSpline(m.Cubic(m.InPlace(m.OnCell()))))
+    with pytest.raises(ValueError):  # the reference defines InPlace for Quadratic only (quadratic.jl:61-62,91-110)
+        bad(np.array([3.0], coord_dtype))
+
+
 def test_convenience_constructors(pkg, orc):
     """convenience-constructors.jl:3-30 with range knots: shorthands for extrapolate(scale(interpolate(...)))
     (test/convenience-constructors.jl: the shorthand equals the explicit chain)."""

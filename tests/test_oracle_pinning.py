@@ -616,3 +616,34 @@ def test_interpolate_inplace_reference_properties(orc):
         m.scale(orc.interpolate_inplace(A1, it), m.jrange(0.0, 1.0, length=10))
     lin = orc.interpolate_inplace(A1, m.BSpline(m.Linear()))  # nothing to trim
     assert lin.lbounds() == (1,) and lin.ubounds() == (12,) and np.array_equal(lin.coefs, A1)
+
+
+def test_inplace_boundary_conditions_reference_cases(orc):
+    """test/b-splines/quadratic.jl:47-62 and test/gradient.jl:108-131: Quadratic(InPlace(OnCell())) keeps the axes of
+    A and reproduces the samples; InPlaceQ is exact for an underlying quadratic (values and gradients)."""
+    import interpolations_jl_b200 as m
+    A = np.array([np.sin((x - 3) * 2 * np.pi / 9 - 1) for x in range(1, 11)])
+    itp1 = orc.interpolate_inplace(A, m.BSpline(m.Quadratic(m.InPlace(m.OnCell()))))
+    assert (itp1.parentaxes[0].first, itp1.parentaxes[0].last) == (1, 10) and itp1.size == (10,)
+    assert itp1.lbounds() == (0.5,) and itp1.ubounds() == (10.5,)
+    assert np.allclose(orc.evaluate(itp1, np.arange(1.0, 11.0))[0], A, rtol=0, atol=1e-13)
+    assert np.array_equal(orc.interpolate(A, m.BSpline(m.Quadratic(m.InPlace(m.OnCell())))).coefs, itp1.coefs)  # never padded
+    A2 = np.array([[np.sin(x / 10) * np.cos(y / 6) for y in range(1, 11)] for x in range(1, 31)])
+    itp2 = orc.interpolate_inplace(A2, m.BSpline(m.Quadratic(m.InPlace(m.OnCell()))))
+    xs, ys = np.meshgrid(np.arange(1.0, 31.0), np.arange(1.0, 11.0), indexing="ij")
+    assert np.allclose(orc.evaluate(itp2, xs, ys)[0], A2, rtol=0, atol=1e-13)
+    assert np.isfinite(orc.evaluate(itp2, np.array([0.5, 30.5]), np.array([0.5, 10.5]))[0]).all()  # clamped outer taps
+    p = np.array([(x - 1.75) ** 2 for x in range(1, 8)])
+    A = np.outer(p, p)
+    iq = orc.interpolate_inplace(A, m.BSpline(m.Quadratic(m.InPlace(m.OnCell()))))
+    v, g = orc.evaluate(iq, np.array([4.0, 4.0]), np.array([4.0, 3.0]), want_grad=True)[:2]
+    assert np.allclose(v, [(4 - 1.75) ** 4, (4 - 1.75) ** 2 * (3 - 1.75) ** 2])
+    assert abs(g[1, 0] - 2 * (4 - 1.75) * (3 - 1.75) ** 2) < 0.03 and abs(g[1, 1] - 2 * (4 - 1.75) ** 2 * (3 - 1.75)) < 0.2
+    iq = orc.interpolate_inplace(A, m.BSpline(m.Quadratic(m.InPlaceQ(m.OnCell()))))
+    v, g = orc.evaluate(iq, np.array([4.0, 4.0]), np.array([4.0, 3.0]), want_grad=True)[:2]
+    assert np.allclose(v, [(4 - 1.75) ** 4, (4 - 1.75) ** 2 * (3 - 1.75) ** 2])
+    assert np.allclose(g[1], [2 * (4 - 1.75) * (3 - 1.75) ** 2, 2 * (4 - 1.75) ** 2 * (3 - 1.75)])
+    # InPlaceQ: exact between the nodes too, wherever no tap is clamped (1.5 <= x < n - 0.5)
+    xq = np.array([1.5, 1.8, 2.3, 3.7, 5.9, 6.4])
+    v = orc.evaluate(iq, xq, np.full(6, 2.0))[0]
+    assert np.allclose(v, (xq - 1.75) ** 2 * (2 - 1.75) ** 2, rtol=0, atol=1e-12)
