@@ -469,6 +469,46 @@ def extrapolate(itp, et) -> Union[Extrapolation, FilledExtrapolation]:
     raise TypeError(f"extrapolate(): bad scheme {et!r}")
 
 
+# ----------------------------------------------------------------------------- rrule
+def rrule(itp, *xs):
+    """`ChainRulesCore.rrule(itp, x...)` (chainrules/chainrules.jl:9-16): returns `(y, pullback)`; `pullback(dy)` gives the
+    cotangents of the evaluation points, `dy .* gradient(itp, x...)` per axis (none for the data inside `itp`)."""
+    y, g = value_and_gradient(itp, *xs)
+
+    def interpolate_pullback(dy):
+        torch = _torch()
+        dy = torch.as_tensor(dy, dtype=g.dtype, device=g.device)
+        return tuple(dy * g[..., k] for k in range(g.shape[-1]))
+
+    return y, interpolate_pullback
+
+
+def differentiable(itp):
+    """The rrule wired into torch.autograd: `differentiable(itp)(x, y, ...)` evaluates `itp` on CUDA tensors and
+    back-propagates to the coordinates through `Interpolations.gradient` (both passes run in libb200itp)."""
+    torch = _torch()
+
+    class _Eval(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *xs):
+            y, g = value_and_gradient(itp, *[x.detach() for x in xs])
+            ctx.save_for_backward(g)
+            ctx.shapes = [x.shape for x in xs]
+            ctx.dtypes = [x.dtype for x in xs]
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            (g,) = ctx.saved_tensors
+            outs = []
+            for k, (shape, dt) in enumerate(zip(ctx.shapes, ctx.dtypes)):
+                t = (dy * g[..., k]).to(dt)
+                outs.append(t.sum_to_size(shape) if tuple(t.shape) != tuple(shape) else t)  # broadcast arguments
+            return tuple(outs)
+
+    return _Eval.apply
+
+
 # ----------------------------------------------------------------------------- convenience constructors
 def _knot_ranges(knots):
     ranges = tuple(knots) if isinstance(knots, (tuple, list)) else (knots,)

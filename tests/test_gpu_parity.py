@@ -703,6 +703,33 @@ def test_inplace_boundary_conditions(pkg, orc, coef_dtype, coord_dtype):
         bad(np.array([3.0], coord_dtype))
 
 
+def test_rrule_and_autograd(pkg):
+    """chainrules/chainrules.jl:9-16 (test/chainrules.jl): the pullback is `dy .* gradient(itp, x...)`; wired into
+    torch.autograd the coordinate gradients equal `Interpolations.gradient`."""
+    import torch
+    m = pkg
+    y = np.sin(np.arange(1, 11, dtype=np.float64))
+    itp = m.interpolate(y, m.BSpline(m.Linear()))
+    val, back = m.rrule(itp, np.array([1.0]))
+    assert torch.equal(back(1.0)[0], m.gradient(itp, np.array([1.0]))[..., 0]) and val.shape == (1,)
+    x2 = np.array([[i * j for j in range(1, 6)] for i in range(1, 6)], dtype=np.float64)
+    itp2 = m.interpolate(np.sin(x2), m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+    g = m.gradient(itp2, np.array([1.0]), np.array([2.0]))
+    _, back = m.rrule(itp2, np.array([1.0]), np.array([2.0]))
+    assert all(torch.equal(b, g[..., k]) for k, b in enumerate(back(1.0)))
+    xs = torch.linspace(1.2, 4.7, 50, dtype=torch.float64, device="cuda", requires_grad=True)
+    ys = torch.linspace(4.9, 1.1, 50, dtype=torch.float64, device="cuda", requires_grad=True)
+    f = m.differentiable(itp2)
+    out = f(xs, ys)
+    (out * torch.arange(50, device="cuda", dtype=torch.float64)).sum().backward()
+    gref = m.gradient(itp2, xs.detach(), ys.detach())
+    w = torch.arange(50, device="cuda", dtype=torch.float64)
+    assert torch.equal(xs.grad, w * gref[..., 0]) and torch.equal(ys.grad, w * gref[..., 1])
+    yb = torch.tensor([2.5], dtype=torch.float64, device="cuda", requires_grad=True)  # broadcast argument
+    f(xs.detach(), yb).sum().backward()
+    assert torch.allclose(yb.grad, m.gradient(itp2, xs.detach(), yb.detach().expand(50))[..., 1].sum().reshape(1))
+
+
 def test_convenience_constructors(pkg, orc):
     """convenience-constructors.jl:3-30 with range knots: shorthands for extrapolate(scale(interpolate(...)))
     (test/convenience-constructors.jl: the shorthand equals the explicit chain)."""
