@@ -215,6 +215,11 @@ B200ITP_API int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndim
 B200ITP_API int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
                       const int32_t *degree, const int32_t *bc, const int32_t *gridtype,
                       void *stream);
+/* Long lines of arrays with few lines are cut into segments (one warm-up and one look-ahead block each) to fill the
+ * machine; a segmented pass agrees with the unsegmented one to round-off (<= 1 ulp in ~1e-5 of the elements) but not
+ * bit for bit.  Callers that need results independent of how an array is split into slabs (the slab-sharded prefilter:
+ * same bits at every GPU count) switch segmentation off around their calls.  Returns the previous setting. */
+B200ITP_API int b200itp_prefilter_set_segmentation(int enable);
 
 /* ---- evaluation: itp.(xs...) and Interpolations.gradient.(Ref(itp), xs...) ---- */
 

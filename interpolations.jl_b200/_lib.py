@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "b200itp_gradient_sorted": (C.c_int, [i32, C.POINTER(Desc), vp, C.POINTER(vp), i64, vp, pi64, vp, sz, vp]),
         "b200itp_eval_sorted_min_queries": (i64, []),
         "b200itp_eval_sorted_set_min_queries": (None, [i64]),
+        "b200itp_prefilter_set_segmentation": (C.c_int, [C.c_int]),
         "b200itp_eval_sorted_ordered_calls": (C.c_uint64, []),
     }
     for name, (res, args) in sigs.items():
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "b200itp_memcpy_h2d", "b200itp_memcpy_d2h", "b200itp_sync", "b200itp_copy_with_padding",
     "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_eval", "b200itp_eval_grid", "b200itp_eval_grid_scratch_bytes", "b200itp_hessian",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted", "b200itp_gradient_sorted",
-    "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries",
+    "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_prefilter_set_segmentation",
     "b200itp_eval_sorted_ordered_calls",
 ]
 

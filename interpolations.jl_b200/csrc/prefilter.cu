@@ -1015,14 +1015,15 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
   return 0;
 }
 
-// segmentation: only when there are too few lines to fill the machine
+// segmentation: only when there are too few lines to fill the machine (and not switched off by the caller)
+static std::atomic<int> g_segmentation{1};
 template <typename T>
 static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int axis, int &nseg, int &seglen) {
   constexpr int B = Tune<T>::B;
   const int mult = axis == 0 ? 32 : B;  // the contiguous-axis kernel works in 32-row chunks
   nseg = 1;
   const int64_t want = (int64_t)sm_count(dev) * 1024;
-  if (fast_ok && lines < want / 2 && !warpline_shape_ok<T>(dev, axis, n, lines)) {
+  if (g_segmentation.load() && fast_ok && lines < want / 2 && !warpline_shape_ok<T>(dev, axis, n, lines)) {
     const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
     nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
   }
@@ -1166,6 +1167,8 @@ static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *s
 }  // namespace b200itp
 
 using namespace b200itp;
+
+extern "C" int b200itp_prefilter_set_segmentation(int enable) { return g_segmentation.exchange(enable ? 1 : 0); }
 
 extern "C" int b200itp_prefiltering_system(int dtype, int64_t n, int degree, int bc, int gridtype, void *dl, void *d,
                                            void *du, int32_t *k, int32_t *urow, int32_t *vcol, void *Cp) {

@@ -82,7 +82,14 @@ def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, de
 
 def _cuda_solver(device_index: int) -> Callable:
     def solve(t, julia_size, its):
-        core.prefilter_(t.view(-1), tuple(julia_size), its, device_index)  # raises without the CUDA library
+        # segmentation off: a line is then solved by the same arithmetic whatever slab it sits in, so the sharded
+        # result has the bits of the single-GPU one at every world size (include/b200itp.h)
+        L = core._lib.lib()
+        prev = L.b200itp_prefilter_set_segmentation(0)
+        try:
+            core.prefilter_(t.view(-1), tuple(julia_size), its, device_index)  # raises without the CUDA library
+        finally:
+            L.b200itp_prefilter_set_segmentation(prev)
     return solve
 
 
