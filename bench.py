@@ -30,6 +30,9 @@ N_GRID = 512
 DEFAULT_QUERIES = 10**9
 # DRAM bytes per query of one ordered evaluation call, from the ncu launch list in profiles/ (all launches summed)
 NCU_TRAFFIC_PER_QUERY = 142.3
+# dram__bytes_read + write of the three C3 prefilter passes in the same ncu launch list (profiles/): 1.012 GB (axis 1,
+# one warp per line) + 2 x 1.037 GB (strided passes: the Woodbury look at both line ends re-reads 48 of 512 rows)
+NCU_PREFILTER_TRAFFIC_C3 = 3.086e9
 METRIC = "Gevals/s tricubic + prefilter GB/s (512^3 f32) at 1/2/4/8 B200 vs HBM peak"
 
 
@@ -300,7 +303,8 @@ def main():
     roof_pre = {"bound": "hbm", "kernel": "prefilter (3 axis passes, 512^3 f32)",
                 "achieved": pre_bytes / (pre_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": pre_bytes / (pre_ms * 1e-3) / 1e9 / 8000,
-                "traffic": None, "algorithmic_bytes": pre_bytes, "ms": pre_ms}
+                "traffic": NCU_PREFILTER_TRAFFIC_C3, "traffic_source": "profiles/: ncu dram__bytes_read+write of the three passes",
+                "algorithmic_bytes": pre_bytes, "ms": pre_ms}
 
     # ---- N > 1: the slab-sharded prefilter (x/y passes on z-slabs, one all-to-all, z pass, all-gather), timed on the
     #      device as the max over ranks; GB/s uses the single-GPU algorithmic bytes
