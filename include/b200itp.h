@@ -230,7 +230,7 @@ B200ITP_API int b200itp_prefilter_set_segmentation(int enable);
  *   coefs      device, dtype d->coef_dtype, size d->size
  *   coords     host array of d->ndims DEVICE pointers (SoA), dtype d->coord_dtype, nq each
  *   out_value  device or NULL, nq elements of b200itp_out_dtype(d)
- *   out_grad   device or NULL, nq*ndims elements, ndims contiguous per query (SVector)
+ *   out_grad   device or NULL, nq*G elements, G contiguous per query (SVector); G = ndims minus the NOINTERP axes
  *   first_oob  host out (may be NULL): smallest query index that throws, -1 if none.
  *              When non-NULL the call synchronises `stream`.
  *   dbg_index  device or NULL: nq*ndims int32, the base tap index per axis (bit-exact contract)
