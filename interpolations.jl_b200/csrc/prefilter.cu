@@ -388,10 +388,12 @@ __global__ void __launch_bounds__(BulkCfg::LINES, PF_BULK_MINB) prefilter_stride
   T c1 = T(0), cn = T(0);
   if (p.nv > 0) woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[tid + (int64_t)(r - 1) * R1]; }, c1, cn);
 
-  T yprev[B], v[B], xout[B];
+  // Two register blocks that swap roles every iteration (the loop is unrolled by two): `cur` receives block bi and
+  // becomes its forward values, `prev` holds the forward values of block bi-1 and is turned into its solution in
+  // place.  Same operations in the same order as pipeline_step, without its block-to-block register copies.
+  T blkA[B], blkB[B];
   T carry = T(0);
-#pragma unroll 1
-  for (int bi = 0; bi <= nblk; ++bi) {
+  auto body = [&](int bi, T(&cur)[B], T(&prev)[B]) {
     const int r0 = 1 + bi * B;
     const int cnt = bi < nblk ? B : 0;
     if (bi < nblk) {
@@ -399,16 +401,33 @@ __global__ void __launch_bounds__(BulkCfg::LINES, PF_BULK_MINB) prefilter_stride
       mbar_wait(&full[slot], (unsigned)(bi / NS) & 1u);
       const T *st = ring + (size_t)slot * B * LINES + tid;
 #pragma unroll
-      for (int j = 0; j < B; ++j) v[j] = st[j * LINES];
+      for (int j = 0; j < B; ++j) cur[j] = st[j * LINES];
     }
+    const bool steady = block_is_steady<T, B>(p, r0) && cnt == B;
+    if (steady)
+      fwd_steady<T, B>(p.Linf, cur, carry);
+    else
+      fwd_generic<T, B>(p, r0, cnt, cur, carry);
     const bool emit = bi > 0;
-    pipeline_step<T, B>(p, r0, cnt, v, yprev, B, carry, emit, c1, cn, xout);
+    if (emit) {
+      T xn = T(0);
+      if (steady)
+        bwd_steady<T, B, false>(p.Uinf, p.Dinf, cur, xn);
+      else
+        bwd_generic<T, B, false>(p, r0, cnt, cur, xn);
+      const int rp = r0 - B;
+      if (block_is_steady<T, B>(p, rp))
+        bwd_steady<T, B, true>(p.Uinf, p.Dinf, prev, xn);
+      else
+        bwd_generic<T, B, true>(p, rp, B, prev, xn);
+      if (block_needs_correction<T, B>(p, rp)) correct_block<T, B>(p, rp, B, prev, c1, cn);
+    }
     if (tid == 0) bulk_wait_read<0>();  // the previous block's stores have read the output stage
     __syncthreads();                    // ... and every thread has taken its column of input stage bi % NS
     if (tid == 0 && bi + NS < nblk) issue_load(bi + NS);
     if (emit) {
 #pragma unroll
-      for (int j = 0; j < B; ++j) ostage[j * LINES + tid] = xout[j];
+      for (int j = 0; j < B; ++j) ostage[j * LINES + tid] = prev[j];
       fence_proxy_async_smem();
     }
     __syncthreads();
@@ -418,8 +437,11 @@ __global__ void __launch_bounds__(BulkCfg::LINES, PF_BULK_MINB) prefilter_stride
         bulk_store(out + (int64_t)((bi - 1) * B + j) * R1, ostage + (size_t)j * LINES, BulkCfg::ROW_BYTES);
       bulk_commit();
     }
-#pragma unroll
-    for (int j = 0; j < B; ++j) yprev[j] = v[j];
+  };
+#pragma unroll 1
+  for (int bi = 0; bi <= nblk; bi += 2) {
+    body(bi, blkA, blkB);
+    if (bi + 1 <= nblk) body(bi + 1, blkB, blkA);
   }
   if (tid == 0) bulk_wait_read<0>();  // the output stage must outlive the stores that read it
 }
