@@ -150,6 +150,35 @@ def test_prefilter_strided_bulk_kernel(pkg, orc, padded):
         assert rel_err(got, ref) <= TOL[np.dtype(np.float32)], (it, padded, rel_err(got, ref))
 
 
+def test_prefilter_fuzz(pkg, orc):
+    """Random shapes (1-D to 3-D, lengths on and off the multiples of 16 / 128 that select the warp-per-line, bulk-copy,
+    ring, strided, segmented and general kernels), random per-axis specs, both element types, `interpolate` and
+    `interpolate!`: coefficients against the oracle.  B200ITP_FUZZ_CASES scales the number of cases."""
+    m = pkg
+    ncases = max(12, int(os.environ.get("B200ITP_FUZZ_CASES", "12")) // 4)
+    rng = np.random.default_rng(2024)
+    pool = specs(m) + [m.BSpline(m.Quadratic(m.InPlace(m.OnCell()))), m.BSpline(m.Quadratic(m.InPlaceQ(m.OnCell())))]
+    lens0 = [130, 254, 256, 258, 384, 510, 512, 640, 1000, 1024, 2048, 2050]
+    lens = [7, 16, 33, 64, 128, 130, 144, 200, 256, 300]
+    for case in range(ncases):
+        nd = int(rng.integers(1, 4))
+        shape = [int(rng.choice(lens0))] + [int(rng.choice(lens)) for _ in range(nd - 1)]
+        while np.prod(shape) > 6e6:
+            shape[-1] = max(7, shape[-1] // 2)
+        dtype = np.float32 if rng.random() < 0.7 else np.float64
+        its = tuple(pool[int(rng.integers(len(pool)))] for _ in range(nd))
+        A = rng.standard_normal(shape).astype(dtype)
+        if rng.random() < 0.5:
+            ref = orc.prefilter(A, its)
+            got = m.interpolate(A, its).coefs_array()
+        else:
+            ref = orc.interpolate_inplace(A, its)
+            ref = ref.coefs.reshape(ref.size, order="F")
+            got = m.interpolate_inplace(A, its).coefs_array()
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert rel_err(got, ref) <= TOL[np.dtype(dtype)], (case, shape, its, dtype, rel_err(got, ref))
+
+
 def test_prefilter_c3_property_full_size(pkg):
     """BASELINE config C3 at full size (512^3 Float32, Cubic(Periodic(OnGrid()))): the oracle would take minutes,
     so check the size-independent property instead: applying the periodic (1/6, 2/3, 1/6) stencil along every
