@@ -1046,7 +1046,10 @@ static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int
   nseg = 1;
   const int64_t want = (int64_t)sm_count(dev) * 1024;
   if (g_segmentation.load() && fast_ok && lines < want / 2 && !warpline_shape_ok<T>(dev, axis, n, lines)) {
-    const int64_t maxseg = std::max<int64_t>(1, n / (8 * B));
+#ifndef PF_SEG_MIN_BLOCKS
+#define PF_SEG_MIN_BLOCKS 8  // a segment is at least this many blocks long (the warm-up + look-ahead blocks cost 2 more)
+#endif
+    const int64_t maxseg = std::max<int64_t>(1, n / (PF_SEG_MIN_BLOCKS * B));
     nseg = (int)std::min<int64_t>(maxseg, (want + lines - 1) / lines);
   }
   seglen = (int)(((n + nseg - 1) / nseg + mult - 1) / mult * mult);
