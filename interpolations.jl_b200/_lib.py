@@ -12,7 +12,8 @@ MAX_DIMS = 4
 MAX_WOODBURY = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200itp.so")
+# B200ITP_LIB selects another build of the same library (A/B timing of build-time variants, tools/ only)
+LIB_PATH = os.environ.get("B200ITP_LIB") or os.path.join(_HERE, "libb200itp.so")
 
 
 class Desc(C.Structure):

@@ -160,8 +160,10 @@ class AbstractInterpolation:
 
     # -- evaluation through the C ABI -----------------------------------------
     def __call__(self, *xs):
-        """Broadcast evaluation `itp.(xs...)` (gpu_support.jl:52-57)."""
-        return _broadcast_eval(self, xs, want_value=True, want_grad=False)[0]
+        """Broadcast evaluation `itp.(xs...)` (gpu_support.jl:52-57).  Large scattered broadcasts over arrays that do
+        not fit the L2 take the ordered pipeline (`b200itp_eval_sorted`), everything else the direct kernel; the
+        results are bit-identical."""
+        return _broadcast_eval(self, xs, want_value=True, want_grad=False, sorted_queries=True)[0]
 
     def coefficients(self):
         return self._chain()[0].coefs
@@ -349,9 +351,11 @@ def _device_index(device) -> int:
     return torch.device(device).index or 0
 
 
-def _to_colmajor_device(A, device_index):
+def _to_colmajor_device(A, device_index, alias_ok=False):
     """(flat column-major CUDA tensor, shape).  Integer arrays are converted like `tcoef` does
-    (b-splines.jl:229-233): Float32 stays Float32, integers become Float64."""
+    (b-splines.jl:229-233): Float32 stays Float32, integers become Float64.  A CUDA tensor that already is
+    column-major (its reversed-axes view is contiguous) is not transposed; it is cloned unless `alias_ok`
+    (`interpolate!`), because the prefilter works in place."""
     torch = _torch()
     dev = torch.device("cuda", device_index)
     if isinstance(A, np.ndarray):
@@ -366,9 +370,9 @@ def _to_colmajor_device(A, device_index):
         shape = tuple(A.shape)
         t = A.to(dev)
         if t.dim() > 1:
-            t = t.permute(*reversed(range(t.dim()))).contiguous()
+            t = t.permute(*reversed(range(t.dim()))).contiguous()  # no copy when A already is column-major
         flat = t.reshape(-1)
-        if flat.data_ptr() == A.data_ptr():  # never alias the caller's memory: the prefilter is in place
+        if flat.data_ptr() == A.data_ptr() and not alias_ok:  # interpolate(): never alias the caller's memory
             flat = flat.clone()
         return flat, shape
     return _to_colmajor_device(np.asarray(A), device_index)
@@ -394,6 +398,28 @@ def prefilter_(coefs, size, its, device_index):
     return coefs
 
 
+def _has_prefiltering_system(it: BSpline) -> bool:
+    """Does the reference define `prefiltering_system` for this spec (cubic.jl:101-264, quadratic.jl:71-189)?"""
+    deg, bc, gt = it.degree.code, it.degree.bc.code, it.degree.bc.gt.code
+    if deg == CUBIC:
+        return bc in (BC_FLAT, BC_LINE, 3, BC_PERIODIC)  # Flat, Line, Free, Periodic
+    if deg == QUADRATIC:
+        if bc in (6, 7):  # InPlace / InPlaceQ: OnCell only
+            return gt == ONCELL
+        return bc in (BC_FLAT, BC_LINE, 3, BC_PERIODIC, BC_REFLECT)
+    return True
+
+
+def _check_uniform_spec(it, its):
+    """`interpolate(A, BSpline(Cubic(Reflect(OnGrid()))))`: the single-spec method calls
+    `A_ldiv_B_md!(ret, nothing, ...)` and throws (prefiltering.jl:49-59); only the per-axis TUPLE method skips axes
+    without a system (prefiltering.jl:108-122)."""
+    if isinstance(it, BSpline):
+        for i in its[:1]:
+            if i.degree.code in (CUBIC, QUADRATIC) and not _has_prefiltering_system(i):
+                raise TypeError(f"no prefiltering system is defined for {i} (the reference throws a MethodError)")
+
+
 def interpolate(A, it, device=None) -> BSplineInterpolation:
     """`interpolate(A, it)` (b-splines.jl:167-170,191-193): pad (`copy_with_padding`), prefilter on
     the GPU, wrap.  `A`: numpy array or torch tensor, shape (n1..nN) in Julia index order."""
@@ -411,6 +437,7 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
     for d in range(N):  # is_singleton_ok b-splines.jl:114-121
         if shape[d] == 1 and its[d].degree.code != NOINTERP:
             raise ValueError(f"size {shape} is inconsistent with {it}, use NoInterp along singleton dimensions")
+    _check_uniform_spec(it, its)
     pad = [1 if needs_padding(i) else 0 for i in its]
     psize = tuple(shape[d] + 2 * pad[d] for d in range(N))
     code = F32 if src.dtype == torch.float32 else F64
@@ -427,12 +454,14 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
 
 
 def interpolate_inplace(A, it, device=None) -> BSplineInterpolation:
-    """`interpolate!(A, it)` (b-splines.jl:236-241): prefilter `A` itself — no padded copy, the array becomes the
-    coefficient array (a torch CUDA tensor that is already column-major is overwritten; anything else is converted
-    first) — and trim the domain where the degree would have padded: those axes are `2:n-1` (`padinset`)."""
+    """`interpolate!(A, it)` (b-splines.jl:236-241): the system of size n is solved on the samples themselves — no
+    padded copy — and the domain is trimmed where the degree would have padded: those axes are `2:n-1` (`padinset`).
+    A 1-D CUDA tensor, or an N-D CUDA tensor whose memory is already column-major (`A.permute(N-1..0)` contiguous, e.g.
+    `torch.empty(n3, n2, n1).permute(2, 1, 0)`), is prefiltered IN PLACE like the reference does; every other input
+    (numpy, CPU, row-major) is converted to a column-major device copy first and the caller's array is left alone."""
     torch = _torch()
     dev = _device_index(device)
-    src, shape = _to_colmajor_device(A, dev)
+    src, shape = _to_colmajor_device(A, dev, alias_ok=True)
     N = len(shape)
     if not 1 <= N <= MAX_DIMS:
         raise ValueError(f"1..{MAX_DIMS} dimensions are supported, got {N}")
@@ -440,6 +469,7 @@ def interpolate_inplace(A, it, device=None) -> BSplineInterpolation:
     for i in its:
         if not iscomplete(i):
             raise ValueError(f"OnGrid/OnCell is not supplied for some of the interpolation modes in {it}")
+    _check_uniform_spec(it, its)
     inset = [1 if needs_padding(i) else 0 for i in its]
     for d in range(N):
         if shape[d] - 2 * inset[d] < 1 or (shape[d] == 1 and its[d].degree.code != NOINTERP):
@@ -579,6 +609,38 @@ def out_dtype(itp, coord_dtype):
     return _np_dtype(code)
 
 
+_scratch_cache = {}
+
+
+def _scratch_tensor(nbytes, device):
+    """Ordered-pipeline scratch (~32 B/query), kept per (device, stream) and grown geometrically instead of a fresh
+    `torch.empty` per broadcast (10^9 queries: 32 GB)."""
+    torch = _torch()
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _scratch_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        _scratch_cache.pop(key, None)
+        t = None
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch_cache[key] = t
+    return t
+
+
+def release_scratch():
+    """Drop the cached ordered-pipeline scratch buffers."""
+    _scratch_cache.clear()
+
+
+def _can_throw(D) -> bool:
+    """Can a query raise BoundsError?  Not when every side of every axis extrapolates (or fills)."""
+    if D.etp_kind == ETP_FILL:
+        return False
+    if D.etp_kind == ETP_FLAGS:
+        return any(D.etp_lo[d] == BC_THROW or D.etp_hi[d] == BC_THROW for d in range(D.ndims)) or any(
+            D.degree[d] == NOINTERP for d in range(D.ndims))
+    return True
+
+
 def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=None):
     torch = _torch()
     L = _lib.lib()
@@ -602,24 +664,28 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
         dbg_b = torch.empty(nq, dtype=torch.int32, device=tdev) if debug else None
         ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in coords])
         foob = C.c_int64(-1)
+        # the out-of-bounds report costs a stream synchronisation: skipped when no query can throw
+        foob_ref = C.byref(foob) if _can_throw(D) else None
 
         def p(t):
             return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(None)
 
         if nq > 0:
-            if sorted_queries and (want_value != want_grad) and not debug:
-                nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq)
-                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=tdev)
+            # scratch_bytes is 0 when the ordered pipeline would not serve this call (small / L2-resident / wrapped)
+            nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq) if (
+                sorted_queries and (want_value != want_grad) and not debug) else 0
+            if nbytes:
+                scratch = _scratch_tensor(int(nbytes), tdev)
                 if want_value:
-                    rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), C.byref(foob), p(scratch),
+                    rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), foob_ref, p(scratch),
                                                nbytes, _stream_ptr(dev))
                     _lib.check(rc, "b200itp_eval_sorted")
                 else:
-                    rc = L.b200itp_gradient_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(grad), C.byref(foob),
+                    rc = L.b200itp_gradient_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(grad), foob_ref,
                                                    p(scratch), nbytes, _stream_ptr(dev))
                     _lib.check(rc, "b200itp_gradient_sorted")
             else:
-                rc = L.b200itp_eval(dev, C.byref(D), p(coefs), ptrs, nq, p(val), p(grad), C.byref(foob), p(dbg_i),
+                rc = L.b200itp_eval(dev, C.byref(D), p(coefs), ptrs, nq, p(val), p(grad), foob_ref, p(dbg_i),
                                     p(dbg_b), _stream_ptr(dev))
                 _lib.check(rc, "b200itp_eval")
     if foob.value >= 0:
@@ -640,7 +706,7 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
 def gradient(itp, *xs):
     """`Interpolations.gradient.(Ref(itp), xs...)`: result has a trailing axis of length N holding the
     SVector components contiguously (indexing.jl:25-31, scaling.jl:123-128, extrapolation.jl:71-82)."""
-    return _broadcast_eval(itp, xs, want_value=False, want_grad=True)[1]
+    return _broadcast_eval(itp, xs, want_value=False, want_grad=True, sorted_queries=True)[1]
 
 
 def value_and_gradient(itp, *xs):
@@ -726,6 +792,9 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
                 done_ev[b].record(s_out)
         main.wait_stream(s_out)
         main.wait_stream(s_in)
+        # `out` lives in host memory: the caller may read it as soon as this returns, so the last device->host copies
+        # must have LANDED (stream ordering alone does not block the CPU)
+        s_out.synchronize()
     return out
 
 

@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace b200itp {
@@ -30,14 +31,16 @@ struct Scratch {
   size_t bytes = 0;
 };
 std::mutex g_scratch_mu;
-std::map<std::pair<int, int>, Scratch> g_scratch;
+std::map<std::tuple<int, int, cudaStream_t>, Scratch> g_scratch;
 }  // namespace
 
-// Grow-only scratch, one buffer per (device, slot).  Callers use it on one stream at a time
-// (the ABI enqueues everything on the caller's stream; growth synchronises the device).
-int scratch_get(int dev, int slot, size_t bytes, void **out) {
+// Grow-only scratch, one buffer per (device, slot, stream): all work of a call is enqueued on the caller's stream, so
+// calls on different streams (or host threads driving different streams) never share a flag or a ping-pong array, and
+// calls on one stream are ordered by the stream.  Growth synchronises the device before the old buffer is freed.
+// (Two host threads issuing calls on the SAME stream concurrently are not supported; include/b200itp.h says so.)
+int scratch_get(int dev, int slot, cudaStream_t stream, size_t bytes, void **out) {
   std::lock_guard<std::mutex> lk(g_scratch_mu);
-  Scratch &s = g_scratch[{dev, slot}];
+  Scratch &s = g_scratch[std::make_tuple(dev, slot, stream)];
   if (s.bytes < bytes) {
     if (s.p) {
       B200_CUDA_OK(cudaDeviceSynchronize());

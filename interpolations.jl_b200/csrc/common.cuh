@@ -71,7 +71,7 @@ struct StageScope {
 };
 
 // per-device grow-only scratch buffer (guarded by a mutex; see api.cu)
-int scratch_get(int dev, int slot, size_t bytes, void **out);
+int scratch_get(int dev, int slot, cudaStream_t stream, size_t bytes, void **out);
 
 // ---- cache-hinted 128-bit global accesses -----------------------------------------------------
 // Streaming data that is touched exactly once per pass: do not allocate in L1.

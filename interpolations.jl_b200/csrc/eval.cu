@@ -250,7 +250,7 @@ static int eval_common(int dev, const b200itp_desc *D, const void *coefs, const 
   if (nq == 0 || (!out_value && !out_grad)) return 0;
 
   void *flag = nullptr;
-  rc = scratch_get(dev, 2, 256, &flag);
+  rc = scratch_get(dev, 2, st, 256, &flag);
   if (rc) return rc;
   B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
 
@@ -317,7 +317,7 @@ extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coe
   if (nq == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   void *flag = nullptr;
-  rc = scratch_get(dev, 2, 256, &flag);
+  rc = scratch_get(dev, 2, st, 256, &flag);
   if (rc) return rc;
   B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));
   // the hessian of an Extrapolation is the parent's, in bounds only: the chain of the in-bounds gradient path

@@ -417,7 +417,15 @@ template <int N, int DEG, typename TW>
 __device__ __forceinline__ void load_row4(const float *coefs, long long lin, long long total, float (&c)[4]) {
   const long long a = lin & ~3LL;
   const int sft = (int)(lin - a);
-  const float4 q0 = __ldg(reinterpret_cast<const float4 *>(coefs + a));
+  float4 q0;
+  if (a + 4 <= total) {
+    q0 = __ldg(reinterpret_cast<const float4 *>(coefs + a));
+  } else {  // the aligned quad would extend past the allocation (total % 4 != 0, Quadratic: 3 taps end at total - 1)
+    q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < total) q0.x = __ldg(coefs + a);
+    if (a + 1 < total) q0.y = __ldg(coefs + a + 1);
+    if (a + 2 < total) q0.z = __ldg(coefs + a + 2);
+  }
   float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (sft != 0) {
     if (a + 8 <= total) {

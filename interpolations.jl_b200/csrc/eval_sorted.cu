@@ -353,16 +353,142 @@ __global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restri
 // One chunk of S records, held in registers (RPT per thread), is counting-sorted by key in shared memory
 // and appended bin by bin to the global bins: one global atomic per (chunk, non-empty bin), stores of whole
 // runs.  key == 0xffffffff marks an absent record.
+// Ranking inside a chunk: shared-memory atomics (default) or warp votes (ORD_RANK_BALLOT=1: one ballot per key bit gives
+// every lane the mask of its peers, the lowest peer bumps a warp-private counter).  Measured on B200
+// (tools/ubench_misc.cu, profiles/r2_ubench_misc.txt): ATOMS ranking costs 2.6 SM cycles per 32 records, the vote
+// variant 25.6 (VOTE + SHFL are the slow instructions here), and the whole pipeline runs 42.7 vs 53.2 ms per 1e9
+// queries.  The split kernels are bound by the barrier-separated phases of a chunk, not by the atomics.
+#ifndef ORD_RANK_BALLOT
+#define ORD_RANK_BALLOT 0
+#endif
+constexpr int kKeyBits = 9;  // kMaxBins == 512
+static_assert((1 << kKeyBits) == kMaxBins, "key bits");
+
 template <typename Rec, int S>
 struct SplitSmem {
   Rec rec[S];  // records of the chunk in bin order
   unsigned short bin[S];
   unsigned gbase[kMaxBins];
+#if ORD_RANK_BALLOT
+  unsigned short whist[kSplitThreads / 32][kMaxBins];  // per warp: count, then first slot, of every bin
+#else
   unsigned hist[kMaxBins];
   unsigned start[kMaxBins];
+#endif
   unsigned wtot[32];
 };
 
+#if ORD_RANK_BALLOT
+// FULL: the chunk holds exactly S records (every chunk but the last of a bin/array): no per-record predicates, and the
+// copy-out loop has a constant trip count, so its shared-memory look-ups are issued back to back.
+template <bool FULL, typename Rec, int S>
+__device__ __forceinline__ void block_split(SplitSmem<Rec, S> &sm, const Rec (&r)[S / kSplitThreads],
+                                            const unsigned (&key)[S / kSplitThreads], int nbins, unsigned cnt,
+                                            unsigned *__restrict__ cursor, Rec *__restrict__ out) {
+  // sm.whist[warp][*] is all zero on entry (zeroed by split_init / by the warp itself at the end of the previous call)
+  constexpr int RPT = S / kSplitThreads;
+  constexpr int NW = kSplitThreads / 32;
+  static_assert(S <= 65536, "ranks are 16-bit");
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned short *wh = sm.whist[warp];
+  unsigned kr[RPT];  // key | (rank among the warp's records of that key) << 16
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const unsigned k = key[j];
+    const bool valid = FULL || k != 0xffffffffu;
+    unsigned peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < kKeyBits; ++b) {
+      const unsigned bit = (k >> b) & 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, bit);
+      peers &= m ^ (bit - 1u);  // bit set: lanes with the bit; clear: lanes without
+    }
+    const unsigned below = __popc(peers & lt);
+    unsigned base = 0;
+    if (valid && below == 0) {  // lowest peer: bump the warp's counter of this key
+      base = wh[k];
+      wh[k] = (unsigned short)(base + __popc(peers));
+    }
+    __syncwarp();
+    base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);  // (invalid lanes: peers may be 0 -> lane 31's value, unused)
+    kr[j] = valid ? (k | ((base + below) << 16)) : 0xffffffffu;
+  }
+  __syncthreads();  // (1) warp counters complete; the previous chunk's copy-out has finished in every warp
+  // bin owner t: total of its bin, exclusive scan over the bins, then the first slot of every warp's share
+  const bool owner = t < kMaxBins;
+  unsigned v = 0;
+  if (owner && t < nbins) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sm.whist[w][t];
+  }
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) sm.wtot[warp] = inc;
+  // the bin reservation's round trip to the L2 overlaps the scan and the shared-memory scatter below
+  unsigned gb = 0;
+  if (v) gb = atomicAdd(cursor + t, v);
+  __syncthreads();  // (2)
+  unsigned wv = lane < NW ? sm.wtot[lane] : 0u, winc = wv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += u;
+  }
+  const unsigned wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+  const unsigned st = wbase + inc - v;
+  if (owner && t < nbins) {
+    unsigned run = st;  // (re-read rather than 16 live registers across the barrier)
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const unsigned cw = sm.whist[w][t];
+      sm.whist[w][t] = (unsigned short)run;
+      run += cw;
+    }
+  }
+  __syncthreads();  // (3) first slots visible
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+    if (FULL || kr[j] != 0xffffffffu) {
+      const unsigned k = kr[j] & 0xffffu;
+      const unsigned slot = wh[k] + (kr[j] >> 16);
+      sm.rec[slot] = r[j];
+      sm.bin[slot] = (unsigned short)k;
+    }
+  asm volatile("" : "+r"(gb));
+  if (owner) sm.gbase[t] = gb - st;
+  __syncthreads();  // (4) records in bin order
+  // the warp's counters are only touched by the warp itself until barrier (1) of the next call: zero them now
+  {
+    unsigned *w32 = reinterpret_cast<unsigned *>(wh);
+#pragma unroll
+    for (int i = 0; i < kMaxBins / 64; ++i) w32[i * 32 + lane] = 0u;
+  }
+  // stores of whole runs, consecutive threads on consecutive records; no barrier after them: the next call touches
+  // only its own warp's counters before its barrier (1)
+  if (FULL) {
+#pragma unroll 8
+    for (int j = 0; j < RPT; ++j) {
+      const unsigned i = (unsigned)j * kSplitThreads + t;
+      out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
+    }
+  } else {
+    for (unsigned i = t; i < cnt; i += kSplitThreads) out[sm.gbase[sm.bin[i]] + i] = sm.rec[i];
+  }
+  __syncwarp();
+}
+
+template <typename Rec, int S>
+__device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
+  unsigned *w32 = reinterpret_cast<unsigned *>(&sm.whist[0][0]);
+  for (int i = threadIdx.x; i < (kSplitThreads / 32) * kMaxBins / 2; i += kSplitThreads) w32[i] = 0u;
+  __syncthreads();
+}
+#else
 // FULL: the chunk holds exactly S records (every chunk but the last of a bin/array): no per-record predicates, and the
 // copy-out loop has a constant trip count, so its shared-memory look-ups are issued back to back.
 template <bool FULL, typename Rec, int S>
@@ -446,6 +572,7 @@ __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
   if (threadIdx.x < kMaxBins) sm.hist[threadIdx.x] = 0;
   __syncthreads();
 }
+#endif
 
 // split 1: coordinates -> {x,y,z,q} records grouped by brick group
 // SUPER: three-level geometry, the first pass splits by super-group (kMaxBins groups)
@@ -1190,8 +1317,26 @@ extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
   g_sorted_min_coef_bytes = n <= 1 ? 0 : (128LL << 20);  // n == 1 (tests): every supported call takes the ordered path
 }
 
+// Descriptor-only test of the ordered pipeline's scope (the complete test, with the derived promotion chain, is in
+// eval_sorted_common; a candidate that fails it is served by the direct kernel and its scratch stays unused).
+static bool ordered_candidate(const b200itp_desc *d, int64_t nq) {
+  if (d->ndims != 2 && d->ndims != 3) return false;
+  if (d->coef_dtype != B200ITP_F32 || d->coord_dtype != B200ITP_F32) return false;
+  if (d->has_scale || d->etp_kind != B200ITP_ETP_NONE) return false;
+  const int deg = d->degree[0];
+  if (deg != B200ITP_CUBIC && deg != B200ITP_QUADRATIC) return false;
+  long long coef_bytes = 4;
+  for (int i = 0; i < d->ndims; ++i) {
+    if (d->degree[i] != deg || d->parent_first[i] > 1 || d->bc[i] >= 6) return false;  // mixed, interpolate!, InPlace
+    coef_bytes *= d->size[i];
+  }
+  if (nq < g_sorted_min_queries) return false;
+  return d->ndims == 3 || coef_bytes >= g_sorted_min_coef_bytes;
+}
+
 extern "C" size_t b200itp_eval_sorted_scratch_bytes(const b200itp_desc *d, int64_t nq) {
   if (!d || nq <= 0) return 0;
+  if (!ordered_candidate(d, nq)) return 0;  // the call is served by the direct kernel: no scratch needed
   // upper bound over the brick geometries of this descriptor (cells <= size + 1 per axis)
   long long nbricks = 1;
   const int bdim3[3] = {Brick<3>::BX, Brick<3>::BY, Brick<3>::BZ}, bdim2[3] = {Brick<2>::BX, Brick<2>::BY, 1};
@@ -1219,7 +1364,7 @@ static int eval_sorted_common(int dev, const b200itp_desc *d, const void *coefs,
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval_sorted: cannot select device %d", dev);
   void *flag = nullptr;
-  int rc = scratch_get(dev, 2, 256, &flag);
+  int rc = scratch_get(dev, 2, st, 256, &flag);
   if (rc) return rc;
   rc = fill_eval_params_public(d, coefs, coords, nq, out, (unsigned long long *)flag, P, &deg, &plain);
   if (rc) return rc;

@@ -946,7 +946,7 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
   if (!job.fast_ok) {
     void *tab = nullptr;
     const size_t bytes = sizeof(T) * (size_t)n * 5;
-    int rc = scratch_get(dev, 1, bytes, &tab);
+    int rc = scratch_get(dev, 1, st, bytes, &tab);
     if (rc) return rc;
     std::vector<T> h((size_t)n * 5);
     std::copy(job.F.L.begin(), job.F.L.end(), h.begin());
@@ -1075,7 +1075,7 @@ static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const A
     if (nseg > 1) {
       if (!other) {
         void *tmp = nullptr;
-        int rc = scratch_get(dev, 0, sizeof(T) * (size_t)total, &tmp);
+        int rc = scratch_get(dev, 0, st, sizeof(T) * (size_t)total, &tmp);
         if (rc) return rc;
         other = (T *)tmp;
       }

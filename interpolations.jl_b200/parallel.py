@@ -58,26 +58,27 @@ def _world(group):
 
 
 def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, device=None, group=None):
-    """Replicate `itp` (held by rank `src`) on every rank: metadata by object broadcast, the coefficient array by one
-    `broadcast` (NCCL: 512 MiB cross NVLink once)."""
+    """Replicate `itp` (held by rank `src` OF THE GROUP) on every rank: metadata by object broadcast, the coefficient
+    array by one `broadcast` (NCCL: 512 MiB cross NVLink once)."""
     torch, dist = _torch(), _dist()
     world, rank = _world(group)
+    gsrc = dist.get_global_rank(group, src) if group is not None else src  # the collectives take GLOBAL ranks
     meta = [None]
     if rank == src:
-        meta = [(tuple(itp.size), tuple(itp.parent_len), itp.its, str(itp.coefs.dtype))]
-    dist.broadcast_object_list(meta, src=src, group=group)
-    size, parent_len, its, dtype = meta[0]
+        meta = [(tuple(itp.size), tuple(itp.parent_len), itp.its, str(itp.coefs.dtype), tuple(itp.parent_first))]
+    dist.broadcast_object_list(meta, src=gsrc, group=group)
+    size, parent_len, its, dtype, parent_first = meta[0]
     tdtype = torch.float32 if dtype.endswith("float32") else torch.float64
     if rank == src:
         coefs = itp.coefs
     else:
         dev = torch.device("cuda", core._device_index(device)) if device is not None else torch.device("cpu")
         coefs = torch.empty(int(np.prod(size)), dtype=tdtype, device=dev)
-    dist.broadcast(coefs, src=src, group=group)
+    dist.broadcast(coefs, src=gsrc, group=group)
     if rank == src:
         return itp
     dev_index = coefs.device.index if coefs.device.type == "cuda" else None
-    return core.BSplineInterpolation(coefs, size, parent_len, its, dev_index)
+    return core.BSplineInterpolation(coefs, size, parent_len, its, dev_index, parent_first=parent_first)
 
 
 def _cuda_solver(device_index: int) -> Callable:
