@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B-spline hot path on B200 (BASELINE.json metric).
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
-  3-D tricubic `Cubic(Periodic(OnGrid()))`, 512^3 Float32 volume: prefilter + 10^9 scattered queries.
-One step = `interpolate(A, it)` (copy + 3 prefilter passes) followed by `itp.(xs, ys, zs)` over one batch of
-queries per GPU.  `value` = queries evaluated by all ranks / step time (Gevals/s), inputs resident in HBM.
-`e2e` = the same through the public API with HOST buffers (pinned): H2D of the step's coordinates and D2H of
-its results inside the timed region.  The prefilter's own GB/s is reported beside it.
+Headline workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+  C3: 3-D tricubic `Cubic(Periodic(OnGrid()))`, 512^3 Float32 volume: prefilter + 10^9 scattered queries.
+One step = `interpolate(A, it)` (copy + 3 prefilter passes) on rank 0, NCCL broadcast of the coefficient array (N > 1),
+then `itp.(xs, ys, zs)` over the rank's shard of the 10^9 queries (STRONG scaling: the query total is fixed, each rank
+evaluates 10^9 / N).  `value` = queries evaluated by all ranks / step time (Gevals/s), inputs resident in HBM.  The weak
+variant (10^9 queries on every rank) is reported beside it under "weak_scaling".
+`e2e` = the same step through the public API with HOST buffers (pinned): H2D of the step's samples and coordinates and
+D2H of its results inside the timed region.
+`configs` holds the other four BASELINE shapes (C1, C2 value+gradient, C4 scale+extrapolate fused, C5 4-D linear), each
+with prefilter GB/s, evaluation Gevals/s and its HBM-roofline fraction, query-sharded over the N ranks as well.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--queries Q] [--impl reference]
-N > 1 is launched by torchrun (one rank per GPU, NCCL): the coefficient array is computed on rank 0 and
-replicated with an NCCL broadcast inside the timed step; queries are sharded (weak scaling).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--queries Q] [--impl reference] [--configs 0|1]
+N > 1 is launched by torchrun (one rank per GPU, NCCL).
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -28,12 +30,11 @@ sys.path.insert(0, ROOT)
 
 N_GRID = 512
 DEFAULT_QUERIES = 10**9
-# DRAM bytes per query of one ordered evaluation call, from the ncu launch list in profiles/ (all launches summed)
-NCU_TRAFFIC_PER_QUERY = 142.3
-# dram__bytes_read + write of the three C3 prefilter passes in the same ncu launch list (profiles/): 1.012 GB (axis 1,
-# one warp per line) + 2 x 1.037 GB (strided passes: the Woodbury look at both line ends re-reads 48 of 512 rows)
-NCU_PREFILTER_TRAFFIC_C3 = 3.086e9
+# DRAM bytes per query of one ordered evaluation call and of the three C3 prefilter passes: ncu dram__bytes_read+write
+# per launch, summed (profiles/).  Refreshed from the launch list named in profiles/README.md when the pipeline changes.
+NCU = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
 METRIC = "Gevals/s tricubic + prefilter GB/s (512^3 f32) at 1/2/4/8 B200 vs HBM peak"
+C3_WORKLOAD = "C3: 3-D Cubic(Periodic(OnGrid())) 512^3 Float32, prefilter + 1e9 scattered queries"
 
 
 def measured_peak():
@@ -41,6 +42,15 @@ def measured_peak():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def host_threads():
+    """Threads the CPU legs use: the cores this process may run on (NOT the inherited OMP_NUM_THREADS, which torchrun
+    sets to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler(threading.Thread):
@@ -74,103 +84,232 @@ class ClockSampler(threading.Thread):
 
 
 def synthetic_volume(torch, dev, seed=20240601):
-    """Smooth sin-product field plus uniform noise, generated on the device."""
+    """Smooth sin-product field plus uniform noise, generated on the device.  Returned as a COLUMN-MAJOR
+    tensor (shape (n1, n2, n3) in Julia index order, first index contiguous): what a Julia array is in memory, so
+    `interpolate` does not have to transpose it."""
     g = torch.Generator(device=dev).manual_seed(seed)
     ax = torch.arange(1, N_GRID + 1, device=dev, dtype=torch.float32)
     s = torch.sin(ax * (2 * np.pi * 3 / N_GRID))
     A = s[:, None, None] * torch.cos(ax * (2 * np.pi * 5 / N_GRID))[None, :, None] * s[None, None, :]
     A = A + 0.1 * (torch.rand((N_GRID,) * 3, device=dev, dtype=torch.float32, generator=g) - 0.5)
-    return A.contiguous()
+    return A.contiguous().permute(2, 1, 0)  # a view: element [i1, i2, i3] at offset i1 + n*(i2 + n*i3)
+
+
+def uniform(torch, dev, n, lo, hi, dtype, gen):
+    x = torch.rand(n, device=dev, dtype=dtype, generator=gen) * (hi - lo) + lo
+    return x.clamp_(lo, hi)
 
 
 def synthetic_queries(torch, dev, nq, rank, seed=20240602):
     g = torch.Generator(device=dev).manual_seed(seed + rank)
-    out = []
-    for _ in range(3):
-        x = torch.rand(nq, device=dev, dtype=torch.float32, generator=g) * (N_GRID - 1) + 1.0
-        out.append(x.clamp_(1.0, float(N_GRID)))
-    return out
+    return [uniform(torch, dev, nq, 1.0, float(N_GRID), torch.float32, g) for _ in range(3)]
+
+
+# ------------------------------------------------------------------------------------------ CPU legs (oracle/)
+def cpu_c3_sample(steps, warmup, threads, nq_s):
+    """The reference's CPU path for C3 on this box's host cores: prefilter of the FULL 512^3 Float32 volume (the
+    oracle's LU + explicit Woodbury sweeps, OpenMP over lines) and a bounded sample of the 1e9 queries through the
+    type-specialised tricubic evaluator (what Julia compiles for this interpolant), OpenMP over queries.
+    Returns median seconds (prefilter, evaluation of nq_s queries, 1-thread Mevals/s)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc  # test infrastructure: here as the timed CPU baseline only
+    m = orc.pkg
+    rng = np.random.default_rng(20240601)
+    A = rng.standard_normal((N_GRID,) * 3).astype(np.float32)
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    q = [rng.uniform(1, N_GRID, nq_s).astype(np.float32) for _ in range(3)]
+    tp, te = [], []
+    coefs = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        c = orc.prefilter(A, it, nthreads=threads, fast=True)
+        t1 = time.perf_counter()
+        if coefs is None:
+            coefs = np.ascontiguousarray(c.reshape(-1, order="F"))
+        orc.evaluate_tricubic_periodic_f32(coefs, (N_GRID,) * 3, *q, nthreads=threads, fast=True)
+        t2 = time.perf_counter()
+        if i >= warmup:
+            tp.append(t1 - t0)
+            te.append(t2 - t1)
+    k1 = min(nq_s, 400_000)
+    t3 = time.perf_counter()
+    orc.evaluate_tricubic_periodic_f32(coefs, (N_GRID,) * 3, *[c[:k1] for c in q], nthreads=1, fast=True)
+    t4 = time.perf_counter()
+    return float(np.median(tp)), float(np.median(te)), k1 / (t4 - t3) / 1e6
+
+
+def cpu_baseline_dict(steps, warmup, nq_total, nq_s=20_000_000):
+    threads = host_threads()
+    tp, te, one = cpu_c3_sample(steps, warmup, threads, nq_s)
+    step_s = tp + te * (nq_total / nq_s)
+    pre_gbs = 2 * 4 * N_GRID**3 * 3 / tp / 1e9
+    return {"value": nq_total / step_s / 1e9, "unit": "Gevals/s", "cores": threads, "kind": "port",
+            "sample": f"prefilter of the full 512^3 Float32 volume ({tp*1e3:.0f} ms = {pre_gbs:.2f} GB/s) + {nq_s} of the "
+                      f"{nq_total} tricubic queries ({nq_s/te/1e6:.1f} Mevals/s on {threads} OpenMP threads, "
+                      f"{one:.2f} Mevals/s on 1), evaluation time scaled to {nq_total} queries; Julia absent: C "
+                      "restatement of the reference (oracle/), type-specialised Float32 tricubic loop",
+            "prefilter_gbs": pre_gbs, "eval_gevals": nq_s / te / 1e9, "eval_mevals_1thread": one,
+            "step_s": step_s}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's CPU path (C restatement in oracle/, all host threads) on a bounded
-    sample of the same workload.  Julia is not in the image, so kind = "port"."""
+    """`--impl reference`: rank 0 alone times the reference's CPU path (C port, all host threads) and prints the line."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as orc
-    m = orc.pkg
-    threads = orc.num_threads()
-    n_s = 256                       # prefilter sample: 256^3 (1/8 of the volume)
-    nq_s = 2_000_000                # query sample per step
-    rng = np.random.default_rng(20240601)
-    A_s = rng.standard_normal((n_s,) * 3).astype(np.float32)
-    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
-    # evaluation sample runs on a full-size 512^3 coefficient array (random: timing only)
-    coefs = rng.standard_normal(N_GRID**3).astype(np.float32)
-    from interpolations_jl_b200.core import BSplineInterpolation
-    itp = BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, None)
-    q = [rng.uniform(1, N_GRID, nq_s).astype(np.float32) for _ in range(3)]
-    times_p, times_e = [], []
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        orc.prefilter(A_s, it, nthreads=threads, fast=True)
-        t1 = time.perf_counter()
-        orc.evaluate(itp, *q, nthreads=threads, fast=True)
-        t2 = time.perf_counter()
-        if i >= args.warmup:
-            times_p.append(t1 - t0)
-            times_e.append(t2 - t1)
-    tp, te = float(np.median(times_p)), float(np.median(times_e))
-    gevals = nq_s / te / 1e9
-    pre_gbs = 2 * 4 * n_s**3 * 3 / tp / 1e9
-    # a step of the full workload = prefilter(512^3) + 1e9 queries; extrapolate linearly from the sample
-    step_s = tp * (N_GRID / n_s) ** 3 + te * (args.queries / nq_s)
-    value = args.queries / step_s / 1e9
+    cb = cpu_baseline_dict(args.steps, args.warmup, args.queries)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gevals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: 3-D Cubic(Periodic(OnGrid())) 512^3 Float32, prefilter + 1e9 scattered queries",
-                   "queries_per_step": args.queries, "sampled": True},
-        "cpu_baseline": {"value": value, "unit": "Gevals/s", "cores": threads, "kind": "port",
-                         "sample": f"prefilter 256^3 f32 ({tp*1e3:.0f} ms, {pre_gbs:.2f} GB/s) + {nq_s} queries on a "
-                                   f"512^3 volume ({gevals*1e3:.2f} Mevals/s), scaled to 512^3 + {args.queries} queries; "
-                                   "Julia absent: C restatement of the reference (oracle/), OpenMP over lines/queries",
-                         "prefilter_gbs": pre_gbs, "eval_gevals": gevals},
-        "e2e": {"value": value, "unit": "Gevals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gevals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["step_s"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": C3_WORKLOAD, "queries_per_step": args.queries,
+                   "sampled": "prefilter at full size; evaluation on a sample of the queries, time scaled linearly"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "Gevals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg():
-    """Bounded CPU timing of the oracle port on the box's host cores (rank 0, N = 1 only)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as orc
-    m = orc.pkg
-    threads = orc.num_threads()
-    rng = np.random.default_rng(1)
-    n_s, nq_s = 256, 2_000_000
-    A_s = rng.standard_normal((n_s,) * 3).astype(np.float32)
-    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
-    coefs = rng.standard_normal(N_GRID**3).astype(np.float32)
-    from interpolations_jl_b200.core import BSplineInterpolation
-    itp = BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, None)
-    q = [rng.uniform(1, N_GRID, nq_s).astype(np.float32) for _ in range(3)]
-    orc.evaluate(itp, *[c[:1000] for c in q], nthreads=threads, fast=True)
-    t0 = time.perf_counter()
-    orc.prefilter(A_s, it, nthreads=threads, fast=True)
-    t1 = time.perf_counter()
-    orc.evaluate(itp, *q, nthreads=threads, fast=True)
-    t2 = time.perf_counter()
-    t3 = time.perf_counter()
-    orc.evaluate(itp, *[c[:200_000] for c in q], nthreads=1, fast=True)
-    t4 = time.perf_counter()
-    return {"value": nq_s / (t2 - t1) / 1e9, "unit": "Gevals/s", "cores": threads, "kind": "port",
-            "sample": f"{nq_s} tricubic queries on a random 512^3 Float32 volume, {threads} OpenMP threads "
-                      f"(1 thread: {0.2 / (t4 - t3):.2f} Mevals/s); prefilter 256^3: {(t1-t0)*1e3:.0f} ms = "
-                      f"{2*4*n_s**3*3/(t1-t0)/1e9:.2f} GB/s. Julia absent: C restatement of the reference (oracle/)",
-            "prefilter_gbs": 2 * 4 * n_s**3 * 3 / (t1 - t0) / 1e9}
+# ------------------------------------------------------------------------------------------ GPU helpers
+class Ctx:
+    pass
+
+
+def flush_l2(ctx):
+    """Between timed iterations of workloads that fit the L2: overwrite a buffer larger than the L2 (256 MiB)."""
+    ctx.flush.add_(1.0)
+
+
+def timed(ctx, fn, steps, warmup, flush=False):
+    """Per-iteration CUDA-event times (ms) of fn() on the current stream, max over ranks of the mean."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        if flush:
+            flush_l2(ctx)
+        ctx.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    t = torch.tensor([float(np.mean(ts))], device=ctx.dev, dtype=torch.float64)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return t.item()
+
+
+def shard(nq, world, rank):
+    base, rem = divmod(nq, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def run_config(ctx, name, workload, make_samples, it_of, wrap, coord_bounds, cdtype, nq_total, want_grad, alg):
+    """One BASELINE shape: prefilter (replicated: every rank, SURVEY §8e 'replicas only') and query-sharded evaluation.
+    alg = dict(pre_bytes, eval_bytes(nq), grad_bytes(nq))."""
+    torch, m, L = ctx.torch, ctx.m, ctx.L
+    dev = ctx.dev
+    A = make_samples()
+    it = it_of(m)
+    peak = ctx.peak
+    out = {"workload": workload}
+    holder = {}
+
+    def build():
+        holder["itp"] = m.interpolate(A, it, device=dev)
+
+    pre_ms = timed(ctx, build, ctx.csteps, 3, flush=True)
+    itp = wrap(m, holder["itp"])
+    if alg["pre_bytes"]:
+        out["prefilter"] = {"ms": pre_ms, "algorithmic_bytes": alg["pre_bytes"],
+                            "gbs": alg["pre_bytes"] / (pre_ms * 1e-3) / 1e9,
+                            "frac": alg["pre_bytes"] / (pre_ms * 1e-3) / 1e9 / peak,
+                            "note": "interpolate(A, it): copy_with_padding + one pass per filtered axis, whole call timed"}
+    lo, hi = shard(nq_total, ctx.world, ctx.rank)
+    nq = hi - lo
+    g = torch.Generator(device=dev).manual_seed(977 + ctx.rank)
+    coords = [uniform(torch, dev, nq, b[0], b[1], cdtype, g) for b in coord_bounds]
+    before = L.b200itp_eval_sorted_ordered_calls()
+    res = {}
+
+    def ev():
+        res["v"] = itp(*coords)
+
+    ev_ms = timed(ctx, ev, ctx.csteps, 3, flush=True)
+    path = "ordered" if L.b200itp_eval_sorted_ordered_calls() > before else "direct"
+    eb = alg["eval_bytes"](nq_total)
+    out["eval"] = {"ms": ev_ms, "queries": nq_total, "gevals": nq_total / (ev_ms * 1e-3) / 1e9, "path": path,
+                   "algorithmic_bytes": eb, "gbs": eb / (ev_ms * 1e-3) / 1e9, "frac": eb / (ev_ms * 1e-3) / 1e9 / peak,
+                   "checksum": float(res["v"].double().sum().item())}
+    if want_grad:
+        before = L.b200itp_eval_sorted_ordered_calls()
+
+        def gr():
+            res["g"] = m.gradient(itp, *coords)
+
+        g_ms = timed(ctx, gr, ctx.csteps, 3, flush=True)
+        gb = alg["grad_bytes"](nq_total)
+        out["gradient"] = {"ms": g_ms, "queries": nq_total, "gevals": nq_total / (g_ms * 1e-3) / 1e9,
+                           "path": "ordered" if L.b200itp_eval_sorted_ordered_calls() > before else "direct",
+                           "algorithmic_bytes": gb, "gbs": gb / (g_ms * 1e-3) / 1e9,
+                           "frac": gb / (g_ms * 1e-3) / 1e9 / peak}
+    del coords, res, holder, itp, A
+    m.core.release_scratch()
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(ctx):
+    """C1, C2, C4, C5 of BASELINE.json (SURVEY §8 sizes and synthetic inputs; §8d algorithmic bytes)."""
+    torch, dev = ctx.torch, ctx.dev
+    g = torch.Generator(device=dev).manual_seed(20240601)
+    out = {}
+
+    def rnd(shape, dt):  # column-major view (Julia memory order), no transposition inside interpolate
+        t = torch.rand(tuple(reversed(shape)), device=dev, dtype=dt, generator=g)
+        return t.permute(*reversed(range(len(shape)))) if len(shape) > 1 else t
+
+    # C1: 1-D Cubic(Line(OnGrid())), 1e6 Float64 samples, 1e7 queries
+    n1 = 10**6
+    out["C1"] = run_config(
+        ctx, "C1", "C1: 1-D Cubic(Line(OnGrid())) 1e6 Float64 samples, 1e7 random queries",
+        lambda: rnd((n1,), torch.float64), lambda m: m.BSpline(m.Cubic(m.Line(m.OnGrid()))), lambda m, itp: itp,
+        [(1.0, float(n1))], torch.float64, 10**7, False,
+        {"pre_bytes": 2 * 8 * (n1 + 2), "eval_bytes": lambda q: q * 16 + 8 * (n1 + 2)})
+    # C2: 2-D bicubic Cubic(Flat(OnCell())) 4096^2 Float32, 1e8 queries + gradient
+    n2 = 4096
+    out["C2"] = run_config(
+        ctx, "C2", "C2: 2-D Cubic(Flat(OnCell())) 4096^2 Float32, 1e8 scattered queries + gradient",
+        lambda: rnd((n2, n2), torch.float32), lambda m: m.BSpline(m.Cubic(m.Flat(m.OnCell()))), lambda m, itp: itp,
+        [(0.5, n2 + 0.5)] * 2, torch.float32, 10**8, True,
+        {"pre_bytes": 2 * 4 * (n2 + 2) ** 2 * 2, "eval_bytes": lambda q: q * (8 + 4) + 4 * (n2 + 2) ** 2,
+         "grad_bytes": lambda q: q * (8 + 8) + 4 * (n2 + 2) ** 2})
+    # C4: 2-D Quadratic(Reflect(OnCell())) 8192^2 Float32, scale(ranges) + extrapolate(Line()) fused; ~30 % of the
+    # queries fall outside [0,1]^2 and take the Line branch (SURVEY §8d)
+    n4 = 8192
+
+    def wrap4(m, itp):
+        r = m.jrange(np.float32(0), np.float32(1), length=n4, dtype=np.float32)
+        return m.extrapolate(m.scale(itp, r, r), m.Line())
+
+    out["C4"] = run_config(
+        ctx, "C4", "C4: 2-D Quadratic(Reflect(OnCell())) 8192^2 Float32, scale(range(0f0,1f0,8192)) + extrapolate(Line()), "
+                   "1e8 queries uniform over [-0.1,1.1]^2",
+        lambda: rnd((n4, n4), torch.float32), lambda m: m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), wrap4,
+        [(-0.1, 1.1)] * 2, torch.float32, 10**8, True,
+        {"pre_bytes": 2 * 4 * (n4 + 2) ** 2 * 2, "eval_bytes": lambda q: q * (8 + 4) + 4 * (n4 + 2) ** 2,
+         "grad_bytes": lambda q: q * (8 + 8) + 4 * (n4 + 2) ** 2})
+    # C5: 4-D Linear() 128^4 Float64, 1e9 queries (no prefilter)
+    n5 = 128
+    out["C5"] = run_config(
+        ctx, "C5", "C5: 4-D Linear() 128^4 Float64 grid, 1e9 queries (2^4 stencil gather, no prefilter)",
+        lambda: rnd((n5,) * 4, torch.float64), lambda m: m.BSpline(m.Linear()), lambda m, itp: itp,
+        [(1.0, float(n5))] * 4, torch.float64, ctx.c5_queries, False,
+        {"pre_bytes": 0, "eval_bytes": lambda q: q * (32 + 8) + 8 * n5**4})
+    return out
 
 
 def main():
@@ -178,10 +317,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--queries", type=int, default=DEFAULT_QUERIES, help="queries per GPU per step")
+    ap.add_argument("--queries", type=int, default=DEFAULT_QUERIES, help="queries per step in TOTAL (sharded over the GPUs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sorted", type=int, default=1, help="use the L2-friendly ordered evaluation path")
+    ap.add_argument("--configs", type=int, default=1, help="also run C1, C2, C4, C5")
+    ap.add_argument("--c5-queries", type=int, default=10**9)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -207,58 +348,70 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.m, ctx.L, ctx.dev, ctx.rank, ctx.world, ctx.barrier = torch, dist, m, L, dev, rank, world, barrier
+    ctx.peak, peak_kind = measured_peak()
+    ctx.flush = torch.zeros(64 << 20, device=dev, dtype=torch.float32)
+    ctx.csteps = max(2, min(args.steps, 5))
+    ctx.c5_queries = args.c5_queries
+    peak = ctx.peak
+
     it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
-    nq = args.queries
     A = synthetic_volume(torch, dev)
-    coords = synthetic_queries(torch, dev, nq, rank)
+    ncoef = N_GRID**3
 
-    def step():
-        # rank 0 prefilters; the coefficient array is replicated over NVLink; every rank evaluates its shard
-        if rank == 0:
-            itp = m.interpolate(A, it, device=dev)
-            coefs = itp.coefs
-        else:
-            coefs = torch.empty(N_GRID**3, dtype=torch.float32, device=dev)
+    def make_step(coords):
+        def step():
+            # rank 0 prefilters; the coefficient array is replicated over NVLink; every rank evaluates its shard
+            if rank == 0:
+                coefs = m.interpolate(A, it, device=dev).coefs
+            else:
+                coefs = torch.empty(ncoef, dtype=torch.float32, device=dev)
+            if world > 1:
+                dist.broadcast(coefs, src=0)
+            itp = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
+            return itp(*coords)  # the drop-in call: takes the ordered pipeline for this size
+        return step
+
+    def run_steps(step, steps, warmup):
+        for _ in range(warmup):
+            out = step()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        L.b200itp_profile_enable(1)
+        barrier()
+        ev[0].record()
+        for _ in range(steps):
+            out = step()
+        ev[1].record()
+        barrier()
+        L.b200itp_profile_enable(0)
+        t_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.broadcast(coefs, src=0)
-        itp = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
-        if args.sorted:
-            return m.evaluate_sorted(itp, *coords)
-        return itp(*coords)
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return t_ms.item() / steps, out
 
-    # ---- device-resident throughput; every kernel launch of the timed steps is bracketed by CUDA events on the
-    #      launching stream (b200itp_profile_*), which is where the roofline's per-kernel durations come from
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
+    # ---- headline: 1e9 queries in total, sharded (strong scaling); every kernel launch of the timed steps is bracketed
+    #      by CUDA events on the launching stream (b200itp_profile_*): the roofline's per-kernel durations
+    lo, hi = shard(args.queries, world, rank)
+    nq = hi - lo
+    coords = synthetic_queries(torch, dev, nq, rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = L.b200itp_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    L.b200itp_profile_enable(1)
-    barrier()
-    ev[0].record()
-    for _ in range(args.steps):
-        out = step()
-    ev[1].record()
-    barrier()
-    L.b200itp_profile_enable(0)
+    oc0 = L.b200itp_eval_sorted_ordered_calls()
+    ms_per_step, out = run_steps(make_step(coords), args.steps, args.warmup)
     stages = m._lib.profile_stages()
     launches = L.b200itp_launch_count() - l0
-    if args.sorted and L.b200itp_eval_sorted_ordered_calls() == 0:
+    if L.b200itp_eval_sorted_ordered_calls() == oc0:
         raise RuntimeError("bench: the ordered evaluation pipeline did not run (fell back to the direct kernel)")
-    t_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = t_ms.item() / args.steps
-    value = nq * world / (ms_per_step * 1e-3) / 1e9
+    launches_per_step = launches / (args.steps + args.warmup)
+    value = args.queries / (ms_per_step * 1e-3) / 1e9
     checksum = float(out.double().sum().item())
+    del out
 
-    itp_check = m.interpolate(A, it, device=dev) if (world > 1 and rank == 0) else None
-    # ---- roofline (HBM): algorithmic bytes per launch / live CUDA-event duration (DESIGN.md §6)
-    peak, peak_kind = measured_peak()
-    ncoef = N_GRID**3
+    # ---- roofline (HBM): algorithmic bytes per launch / live CUDA-event duration (DESIGN.md §4)
     per_query = {"ord_count": 12, "ord_split1": 12 + 16, "ord_split2": 16 + 16, "ord_eval": 16 + 8,
                  "ord_unsortA": 8 + 8, "ord_unsortB": 8 + 8, "ord_place": 8 + 4, "eval_direct_value": 12 + 4}
     stage_rows = []
@@ -284,7 +437,7 @@ def main():
                            "frac": b / (avg * 1e-3) / 1e9 / peak if avg > 0 else None})
     eval_bytes = nq * (12 + 4) + 4 * ncoef          # coordinates in, results out, coefficients once
     pre_bytes = 2 * 4 * ncoef * 3                   # one read + one write per axis pass
-    if rank != 0 or not any(k.startswith("prefilter_axis0") for k in stages):
+    if rank != 0 or pre_ms == 0.0:
         # ranks other than 0 do not prefilter inside the step: time it once here for the report
         work = torch.empty(ncoef, dtype=torch.float32, device=dev).normal_()
         L.b200itp_profile_enable(1)
@@ -294,25 +447,38 @@ def main():
         L.b200itp_profile_enable(0)
         st2 = m._lib.profile_stages()
         pre_ms = float(sum(np.mean(v) for k, v in st2.items() if k.startswith("prefilter_axis")))
-    roof = {"bound": "hbm", "kernel": "ordered evaluation: all launches of one b200itp_eval_sorted call "
-                                      "(count, scan, split1, split2, eval, unsortA, unsortB, place)",
+        del work
+    roof = {"bound": "hbm", "kernel": "ordered evaluation: all launches of one b200itp_eval_sorted call on this rank's "
+                                      f"{nq} queries",
             "achieved": eval_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-            "frac": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC_PER_QUERY * nq + 4 * ncoef,
-            "traffic_source": "profiles/: ncu dram__bytes_read+write per launch, summed over the call, scaled per query",
-            "algorithmic_bytes": eval_bytes, "ms": eval_ms, "stages": stage_rows}
+            "frac": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak,
+            "traffic": NCU["ordered_eval_bytes_per_query"] * nq + 4 * ncoef,
+            "traffic_source": NCU["source"], "algorithmic_bytes": eval_bytes, "ms": eval_ms, "stages": stage_rows}
     roof_pre = {"bound": "hbm", "kernel": "prefilter (3 axis passes, 512^3 f32)",
                 "achieved": pre_bytes / (pre_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": pre_bytes / (pre_ms * 1e-3) / 1e9 / 8000,
-                "traffic": NCU_PREFILTER_TRAFFIC_C3, "traffic_source": "profiles/: ncu dram__bytes_read+write of the three passes",
+                "traffic": NCU["prefilter_c3_bytes"], "traffic_source": NCU["source"],
                 "algorithmic_bytes": pre_bytes, "ms": pre_ms}
 
-    # ---- N > 1: the slab-sharded prefilter (x/y passes on z-slabs, one all-to-all, z pass, all-gather), timed on the
-    #      device as the max over ranks; GB/s uses the single-GPU algorithmic bytes
+    # ---- N > 1: the weak variant (every rank its own 1e9 queries) and the slab-sharded prefilter
+    weak = None
     sharded = None
     if world > 1:
+        del coords
+        m.core.release_scratch()
+        torch.cuda.empty_cache()
+        wcoords = synthetic_queries(torch, dev, args.queries, rank)
+        w_ms, wout = run_steps(make_step(wcoords), max(2, args.steps // 2), 2)
+        weak = {"value": args.queries * world / (w_ms * 1e-3) / 1e9, "unit": "Gevals/s", "ms_per_step": w_ms,
+                "queries_per_gpu_per_step": args.queries, "scaling": "weak"}
+        del wcoords, wout
+        m.core.release_scratch()
+        torch.cuda.empty_cache()
+        coords = synthetic_queries(torch, dev, nq, rank)
         from interpolations_jl_b200 import parallel as par
-        lo, hi = par.shard_bounds(N_GRID, world, rank)
-        slab = A.permute(2, 1, 0)[lo:hi].contiguous()   # torch layout (nz_local, ny, nx) of the Julia array (nx, ny, nz)
+        itp_check = m.interpolate(A, it, device=dev) if rank == 0 else None
+        zlo, zhi = par.shard_bounds(N_GRID, world, rank)
+        slab = A.permute(2, 1, 0)[zlo:zhi].contiguous()   # torch layout (nz_local, ny, nx) of the Julia array (nx, ny, nz)
         ts_solve, ts_all = [], []
         for i in range(4):
             barrier()
@@ -331,70 +497,83 @@ def main():
         ok = bool(torch.equal(full, itp_check.coefs)) if rank == 0 else True
         sharded = {"prefilter_ms": t2[0].item(), "prefilter_plus_allgather_ms": t2[1].item(),
                    "prefilter_gbs": pre_bytes / (t2[0].item() * 1e-3) / 1e9, "matches_single_gpu": ok,
-                   "note": "includes the torch-side slab packing; one all-to-all between the y and z passes"}
-        del full, ysh, slab
+                   "single_gpu_prefilter_ms": pre_ms,
+                   "note": "z-slabs, local x/y passes, one all-to-all, local z pass; then all-gather for evaluation"}
+        del full, ysh, slab, itp_check
 
-    # ---- end to end through the public API with host buffers (pinned): H2D coords + D2H result per step
-    del out
-    # host-buffer leg: the full batch at N = 1; capped per rank at N > 1 so that 8 ranks do not pin 130 GB of host memory
-    nq_e = nq if world == 1 else min(nq, 250_000_000)
-    host_coords = [torch.empty(nq_e, dtype=torch.float32, pin_memory=True) for _ in range(3)]
-    for h, c in zip(host_coords, coords):
-        h.copy_(c[:nq_e])
-    host_A = torch.empty((N_GRID,) * 3, dtype=torch.float32, pin_memory=True)
-    host_A.copy_(A)
-    host_out = torch.empty(nq_e, dtype=torch.float32, pin_memory=True)
-    torch.cuda.synchronize()
-
-    def step_e2e():
-        # host buffers in, host buffer out: H2D of the samples + prefilter on rank 0, broadcast, then the public
-        # host-buffer call (chunked: H2D / evaluation / D2H overlap on three streams)
-        if rank == 0:
-            Ad = host_A.to(dev, non_blocking=True)
-            coefs = m.interpolate(Ad, it, device=dev).coefs
-        else:
-            coefs = torch.empty(N_GRID**3, dtype=torch.float32, device=dev)
-        if world > 1:
-            dist.broadcast(coefs, src=0)
-        itp2 = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
-        m.evaluate_from_host(itp2, *host_coords, out=host_out, ordered=bool(args.sorted))
+    # ---- end to end through the public API with host buffers (pinned): H2D samples + coords, D2H results, per step
+    e2e = None
+    if not args.no_e2e:
+        host_coords = [torch.empty(nq, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        for h, c in zip(host_coords, coords):
+            h.copy_(c)
+        host_A = torch.empty((N_GRID,) * 3, dtype=torch.float32, pin_memory=True)  # memory order of the Julia array
+        host_A.copy_(A.permute(2, 1, 0))
+        host_out = torch.empty(nq, dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
 
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_steps = max(2, min(args.steps, 3))
-    e0.record()
-    for _ in range(e_steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = nq_e * world / (te.item() / e_steps * 1e-3) / 1e9
+        def step_e2e():
+            if rank == 0:
+                Ad = host_A.to(dev, non_blocking=True).permute(2, 1, 0)
+                coefs = m.interpolate(Ad, it, device=dev).coefs
+            else:
+                coefs = torch.empty(ncoef, dtype=torch.float32, device=dev)
+            if world > 1:
+                dist.broadcast(coefs, src=0)
+            itp2 = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
+            m.evaluate_from_host(itp2, *host_coords, out=host_out)
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_steps = max(2, min(args.steps, 3))
+        e0.record()
+        for _ in range(e_steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.queries / (te.item() / e_steps * 1e-3) / 1e9, "unit": "Gevals/s",
+               "h2d_bytes_per_step": 12 * args.queries + 4 * ncoef, "d2h_bytes_per_step": 4 * args.queries,
+               "queries_per_step": args.queries, "queries_per_gpu_per_step": nq, "ms_per_step": te.item() / e_steps}
+        del host_coords, host_A, host_out
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
+    del coords
+    m.core.release_scratch()
+    torch.cuda.empty_cache()
+
+    configs = other_configs(ctx) if args.configs else None
+    if configs is not None:
+        configs["C3"] = {"workload": C3_WORKLOAD,
+                         "prefilter": {"ms": pre_ms, "gbs": roof_pre["achieved"], "frac": roof_pre["frac"],
+                                       "algorithmic_bytes": pre_bytes},
+                         "eval": {"ms": eval_ms, "queries": args.queries, "gevals": value, "path": "ordered",
+                                  "algorithmic_bytes": eval_bytes, "frac": roof["frac"]}}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Gevals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: 3-D Cubic(Periodic(OnGrid())) 512^3 Float32, prefilter + 1e9 scattered queries",
-                       "queries_per_gpu_per_step": nq, "ordered_eval": bool(args.sorted),
-                       "l2": "inputs larger than L2 (coefficients 512 MiB, coordinates 12 B/query)",
-                       "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
-            "prefilter_gbs": roof_pre["achieved"], "prefilter_ms": pre_ms, "eval_gevals_kernel": nq / (eval_ms * 1e-3) / 1e9,
-            "roofline": roof, "roofline_prefilter": roof_pre, "prefilter_sharded": sharded,
-            "e2e": {"value": e2e_val, "unit": "Gevals/s", "h2d_bytes_per_step": (12 * nq_e) * world + 4 * N_GRID**3,
-                    "d2h_bytes_per_step": 4 * nq_e * world, "queries_per_gpu_per_step": nq_e},
-            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "checksum": checksum,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C3_WORKLOAD, "queries_per_step": args.queries, "queries_per_gpu_per_step": nq,
+                       "call": "itp(xs, ys, zs) (the drop-in broadcast; served by the ordered pipeline)",
+                       "l2": "inputs larger than L2 (coefficients 512 MiB, coordinates 12 B/query); the small configs "
+                             "flush the L2 between timed iterations",
+                       "parallelism": f"query-sharded x{world} (fixed total), coefficients replicated by NCCL broadcast"},
+            "prefilter_gbs": roof_pre["achieved"], "prefilter_ms": pre_ms,
+            "eval_gevals_kernel": nq * world / (eval_ms * 1e-3) / 1e9,
+            "roofline": roof, "roofline_prefilter": roof_pre, "weak_scaling": weak, "prefilter_sharded": sharded,
+            "configs": configs, "e2e": e2e,
+            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+            "clocks": sampler.summary() if sampler else None, "checksum": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg()
+            line["cpu_baseline"] = cpu_baseline_dict(1, 1, args.queries)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -220,6 +220,12 @@ B200ITP_API int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, co
  * bit for bit.  Callers that need results independent of how an array is split into slabs (the slab-sharded prefilter:
  * same bits at every GPU count) switch segmentation off around their calls.  Returns the previous setting. */
 B200ITP_API int b200itp_prefilter_set_segmentation(int enable);
+/* Verification mode: every prefilter call runs `A_ldiv_B_md!` exactly as the reference does (filter1d.jl:21-85) —
+ * forward / backward LU sweeps with the zero offset, the explicit six-step Woodbury correction with a full-size
+ * temporary and a second sweep, no fused multiply-add — one thread per line.  Given the same factors it reproduces the
+ * reference's CPU arithmetic bit for bit, so |fast - strict| isolates the fast kernels' truncation and re-association
+ * error.  Slow (3 passes + temporary); never the default.  Returns the previous setting. */
+B200ITP_API int b200itp_prefilter_set_strict(int enable);
 
 /* ---- evaluation: itp.(xs...) and Interpolations.gradient.(Ref(itp), xs...) ---- */
 

@@ -1057,6 +1057,12 @@ static void choose_segments(int dev, int64_t lines, int64_t n, bool fast_ok, int
 }
 
 // Runs the axis passes described by jobs[] (nullptr = skip).  Segmented passes are out of place and
+// strict mode (prefilter_strict.cu): the reference's operation order, no FMA, explicit Woodbury with a full temporary
+extern std::atomic<int> g_prefilter_strict;
+template <typename T>
+int prefilter_strict_axis(int dev, T *coefs, int ndims, const int64_t *size, int axis, const T *dl, const T *d,
+                          const T *du, int k, const int32_t *urow, const int32_t *vcol, const T *Cp, cudaStream_t st);
+
 // ping-pong between `coefs` and a scratch array; the result always ends in `coefs`.
 template <typename T>
 static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const AxisJob<T> *const *jobs,
@@ -1097,6 +1103,9 @@ static int prefilter_axis_typed(int dev, void *coefs, int ndims, const int64_t *
                                 const b200itp_axis_system *sys, cudaStream_t st) {
   const int64_t n = sys->n;
   const T *dl = (const T *)sys->dl, *d = (const T *)sys->d, *du = (const T *)sys->du;
+  if (g_prefilter_strict.load(std::memory_order_relaxed))
+    return prefilter_strict_axis<T>(dev, (T *)coefs, ndims, size, axis, dl, d, du, sys->k, sys->urow, sys->vcol,
+                                    (const T *)sys->Cp, st);
   AxisJob<T> job;
   int rc;
   if (n <= kSurrogate) {
@@ -1168,6 +1177,21 @@ static int cached_job(int64_t n, int degree, int bc, int grid, std::shared_ptr<c
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
                                const int32_t *bc, const int32_t *grid, cudaStream_t st) {
+  if (g_prefilter_strict.load(std::memory_order_relaxed)) {
+    for (int ax = 0; ax < ndims; ++ax) {
+      if (degree[ax] != B200ITP_CUBIC && degree[ax] != B200ITP_QUADRATIC) continue;
+      HostSystem<T> S;  // full-length system (no surrogate), the product's own assembly
+      int rc = assemble_system<T>(size[ax], degree[ax], bc[ax], grid[ax], S);
+      if (rc == B200ITP_E_UNSUPPORTED) continue;
+      if (rc) B200_FAIL(rc, "prefilter(strict): no system for axis %d", ax);
+      rc = woodbury_cp<T>(S);
+      if (rc) B200_FAIL(rc, "prefilter(strict): singular Woodbury capacitance matrix");
+      rc = prefilter_strict_axis<T>(dev, (T *)coefs, ndims, size, ax, S.dl.data(), S.d.data(), S.du.data(), S.k, S.urow,
+                                    S.vcol, S.Cp, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   std::shared_ptr<const AxisJob<T>> keep[B200ITP_MAX_DIMS];
   const AxisJob<T> *jobs[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int ax = 0; ax < ndims; ++ax) {

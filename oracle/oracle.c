@@ -727,3 +727,52 @@ int orc_weights(int degree, int tag, double x, int64_t n, double *wv, double *wg
   *base = A.base;
   return A.L;
 }
+
+/* ------------------------------------------------------------------ type-specialised evaluator (timing legs)
+ * What Julia compiles for `itp.(xs, ys, zs)` with itp = interpolate(A::Array{Float32,3}, BSpline(Cubic(Periodic(OnGrid())))):
+ * every type is known, so the loop body is straight-line Float32 code — no tags, no recursion.  Same operations in the
+ * same order as the interpreter above (cubic.jl:50-69 positions/weights, Interpolations.jl:304-316 reduction);
+ * tests/test_oracle_pinning.py checks it against the interpreter bit for bit.  Used by bench.py's CPU legs only: the
+ * interpreter (1.5 Mevals/s/thread) would understate what the reference does on a CPU. */
+static inline void cubic_periodic_axis_f32(float x, int64_t n, int64_t *idx, float *w) {
+  const float xf = floorf(x);                 /* cubic.jl:50-57 */
+  const float dx = x - xf;
+  const int64_t xi = (int64_t)xf;
+  for (int j = 0; j < 4; j++) idx[j] = modrange(xi - 1 + j, n) - 1; /* expand_index cubic.jl:59-61, 0-based */
+  const float omd = 1.0f - dx;                /* value_weights cubic.jl:63-69 */
+  const float x3 = (dx * dx) * dx, xc3 = (omd * omd) * omd;
+  const float r16 = 1.0f / 6.0f, r23 = (float)(2.0 / 3.0);
+  w[0] = r16 * xc3;
+  w[1] = (r23 - dx * dx) + 0.5f * x3;
+  w[2] = (r23 - omd * omd) + 0.5f * xc3;
+  w[3] = r16 * x3;
+}
+
+int orc_eval_tricubic_periodic_f32(const float *coefs, int64_t n0, int64_t n1, int64_t n2, const float *xs,
+                                   const float *ys, const float *zs, int64_t nq, float *out, int nthreads) {
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t q = 0; q < nq; q++) {
+    int64_t i0[4], i1[4], i2[4];
+    float w0[4], w1[4], w2[4];
+    cubic_periodic_axis_f32(xs[q], n0, i0, w0);
+    cubic_periodic_axis_f32(ys[q], n1, i1, w1);
+    cubic_periodic_axis_f32(zs[q], n2, i2, w2);
+    float val = 0.f;
+    for (int a = 0; a < 4; a++) {             /* axis 1 outermost; first tap a bare product, then w*v + acc */
+      float v0 = 0.f;
+      for (int b = 0; b < 4; b++) {
+        float v1 = 0.f;
+        for (int c = 0; c < 4; c++) {
+          const float t = w2[c] * coefs[(i2[c] * n1 + i1[b]) * n0 + i0[a]];
+          v1 = c == 0 ? t : t + v1;
+        }
+        const float t = w1[b] * v1;
+        v0 = b == 0 ? t : t + v0;
+      }
+      const float t = w0[a] * v0;
+      val = a == 0 ? t : t + val;
+    }
+    out[q] = val;
+  }
+  return 0;
+}

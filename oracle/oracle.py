@@ -2,9 +2,12 @@
 
 ctypes front end of the CPU oracle (oracle/oracle.c), a literal restatement of the reference's
 B-spline hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-`--impl reference` legs may import this module.  It reuses the package's pure-host classes
-(flags, ranges, wrapper objects, descriptor) so that the oracle and the CUDA path are driven by
-the same description of the interpolant; all arithmetic is done by liboracle.so on the CPU.
+`--impl reference` legs may import this module.  The package's pure-host classes (flags, ranges,
+wrapper objects) are used as CONTAINERS of the specification only: the descriptor the C oracle
+consumes (padding, first coefficient index, bounds, types) is derived independently in
+oracle/describe.py from the reference's rules, not by the product's `descriptor()`; all arithmetic
+is done by liboracle.so on the CPU.  Parity is unpinned at the last ulp: the
+reference holds no golden vectors for this path and Julia is absent from the image.
 """
 from __future__ import annotations
 
@@ -19,12 +22,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
 import b200_loader  # noqa: E402
 
 pkg = b200_loader.load()
 from interpolations_jl_b200 import _lib as _pl  # noqa: E402  (struct layouts only)
 from interpolations_jl_b200.core import BSplineInterpolation, _its_tuple  # noqa: E402
 from interpolations_jl_b200.flags import F32, F64, needs_padding  # noqa: E402
+from describe import describe  # noqa: E402  (the oracle's own descriptor derivation)
 
 _libs = {}
 
@@ -55,6 +61,8 @@ def lib(fast=False) -> C.CDLL:
     L.orc_eval.argtypes = [C.POINTER(_pl.Desc), vp, C.POINTER(vp), i64, vp, vp, pi64, vp, vp, i32]
     L.orc_weights.restype = C.c_int
     L.orc_weights.argtypes = [i32, i32, C.c_double, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), pi32]
+    L.orc_eval_tricubic_periodic_f32.restype = C.c_int
+    L.orc_eval_tricubic_periodic_f32.argtypes = [vp, i64, i64, i64, vp, vp, vp, i64, vp, i32]
     _libs[key] = L
     return L
 
@@ -175,7 +183,7 @@ def evaluate(itp, *xs, want_value=True, want_grad=False, debug=False, nthreads=1
     shape = arrs[0].shape
     cs = [np.ascontiguousarray(a.reshape(-1)) for a in arrs]
     nq = cs[0].size
-    D = itp.descriptor(dt)
+    D = describe(itp, dt)
     coefs = itp.coefficients()
     if not isinstance(coefs, np.ndarray):
         coefs = coefs.cpu().numpy()
@@ -199,6 +207,19 @@ def evaluate(itp, *xs, want_value=True, want_grad=False, debug=False, nthreads=1
             bi.reshape(shape + (N,)) if debug else None, br.reshape(shape) if debug else None, foob.value)
 
 
+def evaluate_tricubic_periodic_f32(coefs_flat, shape, xs, ys, zs, nthreads=1, fast=True):
+    """Type-specialised `itp.(xs, ys, zs)` for a Float32 Cubic(Periodic(OnGrid())) volume (what Julia compiles for this
+    interpolant; bench.py's CPU legs).  In-bounds coordinates only; same bits as `evaluate`."""
+    n0, n1, n2 = (int(v) for v in shape)
+    xs, ys, zs = (np.ascontiguousarray(a, np.float32) for a in (xs, ys, zs))
+    out = np.empty(xs.size, np.float32)
+    rc = lib(fast).orc_eval_tricubic_periodic_f32(coefs_flat.ctypes.data, n0, n1, n2, xs.ctypes.data, ys.ctypes.data,
+                                                  zs.ctypes.data, xs.size, out.ctypes.data, nthreads)
+    if rc:
+        raise ValueError(f"orc_eval_tricubic_periodic_f32 rc={rc}")
+    return out
+
+
 def hessian(itp, *xs, nthreads=1, fast=False, raise_oob=True):
     """hessian.(Ref(itp), xs...) on the CPU: array of shape xs.shape + (N, N) (float64 holding numbers already
     rounded to their Julia type)."""
@@ -209,7 +230,7 @@ def hessian(itp, *xs, nthreads=1, fast=False, raise_oob=True):
     shape = arrs[0].shape
     cs = [np.ascontiguousarray(a.reshape(-1)) for a in arrs]
     nq = cs[0].size
-    D = itp.descriptor(dt)
+    D = describe(itp, dt)
     if D.etp_kind == 1:
         D.etp_kind = 0  # hessian(etp, x) = hessian(parent(etp), x) in bounds, error outside (extrapolation.jl:84-90)
     coefs = itp.coefficients()

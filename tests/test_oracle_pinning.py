@@ -647,3 +647,77 @@ def test_inplace_boundary_conditions_reference_cases(orc):
     xq = np.array([1.5, 1.8, 2.3, 3.7, 5.9, 6.4])
     v = orc.evaluate(iq, xq, np.full(6, 2.0))[0]
     assert np.allclose(v, (xq - 1.75) ** 2 * (2 - 1.75) ** 2, rtol=0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------- (d) the oracle's descriptor is its own
+def test_descriptor_derivations_agree(orc):
+    """The oracle derives padding, first coefficient index, bounds and types itself (oracle/describe.py, following
+    b-splines.jl:141-158, cubic.jl:86-87, quadratic.jl:64-65, prefiltering.jl:6, scaling.jl:60-75,116); the product
+    derives them in core.descriptor().  Field-by-field agreement over every spec / wrapper combination in scope."""
+    import describe as dsc
+    m = orc.pkg
+    specs = []
+    for gt in (m.OnGrid, m.OnCell):
+        for bc in (m.Line, m.Flat, m.Free, m.Periodic):
+            specs.append(m.BSpline(m.Cubic(bc(gt()))))
+        for bc in (m.Line, m.Flat, m.Free, m.Periodic, m.Reflect):
+            specs.append(m.BSpline(m.Quadratic(bc(gt()))))
+    specs += [m.BSpline(m.Quadratic(m.InPlace(m.OnCell()))), m.BSpline(m.Quadratic(m.InPlaceQ(m.OnCell()))),
+              m.BSpline(m.Linear()), m.BSpline(m.Linear(m.Periodic(m.OnCell()))), m.BSpline(m.Constant()),
+              m.BSpline(m.Constant(m.Previous(), m.Periodic(m.OnCell())))]
+    rng = np.random.default_rng(3)
+    n_checked = 0
+    for it in specs:
+        for ndims, dt in ((1, np.float64), (2, np.float32), (3, np.float64)):
+            shape = tuple(int(v) for v in rng.integers(6, 11, ndims))
+            A = rng.standard_normal(shape).astype(dt)
+            itps = [orc.interpolate(A, it)]
+            if it.degree.code in (2, 3):
+                itps.append(orc.interpolate_inplace(A, it))
+            for itp in itps:
+                chains = [itp]
+                if all(f == 1 for f in itp.parent_first):
+                    for rdt in (np.float32, np.float64, None):
+                        if rdt is None:
+                            ranges = [m.jrange(2, 2 + n - 1) for n in shape]                   # UnitRange
+                        else:
+                            ranges = [m.jrange(-1.0, 2.5, length=n, dtype=rdt) for n in shape]  # StepRangeLen
+                        chains.append(m.scale(itp, *ranges))
+                wrapped = list(chains)
+                for c in chains:
+                    wrapped.append(m.extrapolate(c, m.Line()))
+                    wrapped.append(m.extrapolate(c, ((m.Flat(), m.Periodic()),)) if ndims == 1 else
+                                   m.extrapolate(c, tuple([m.Reflect()] + [m.Flat()] * (ndims - 1))))
+                    wrapped.append(m.extrapolate(c, np.float32(1.5)))
+                    wrapped.append(m.extrapolate(c, 0))
+                for w in wrapped:
+                    for cdt in (np.float32, np.float64):
+                        diff = dsc.differences(dsc.describe(w, cdt), w.descriptor(cdt))
+                        assert not diff, (it, shape, w, cdt, diff)
+                        n_checked += 1
+    assert n_checked > 1000
+
+
+def test_oracle_does_not_use_the_product_descriptor():
+    """oracle.py must build its descriptors with oracle/describe.py, never with core.descriptor()."""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "oracle.py")).read()
+    assert ".descriptor(" not in src
+
+
+def test_specialised_tricubic_evaluator_equals_the_interpreter(orc):
+    """bench.py's CPU legs time a type-specialised Float32 tricubic evaluator (what Julia compiles for C3); it must
+    return the interpreter's bits, in the parity build and in the -O3 timing build."""
+    m = orc.pkg
+    rng = np.random.default_rng(5)
+    shape = (19, 23, 17)
+    A = rng.standard_normal(shape).astype(np.float32)
+    itp = orc.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
+    q = [rng.uniform(1, n, 20000).astype(np.float32) for n in shape]
+    for k, n in enumerate(shape):  # integers, both bounds
+        q[k][:50] = rng.integers(1, n + 1, 50).astype(np.float32)
+        q[k][50], q[k][51] = 1.0, float(n)
+    ref = orc.evaluate(itp, *q)[0].astype(np.float32)
+    for fast in (False, True):
+        got = orc.evaluate_tricubic_periodic_f32(itp.coefs, shape, *q, nthreads=2, fast=fast)
+        assert np.array_equal(got, ref), fast
