@@ -7,8 +7,8 @@
 // correction with a FULL-SIZE temporary and a second full sweep (filter1d.jl:77-85) — with no contraction of a*b+c
 // (compiled -fmad=false; Julia never fuses).  One thread per line, three passes over the array plus the temporary:
 // slow by design.  Given the same factors (`b200itp_axis_system`, e.g. computed by the reference's own
-// `prefiltering_system` on the host), the result equals the CPU oracle bit for bit, which separates the two error
-// sources of the fast path: strict == oracle (rounding identical), |fast - strict| = truncation + re-association.
+// `prefiltering_system` on the host), the result equals the reference's CPU arithmetic bit for bit, which separates the two error
+// sources of the fast path: strict == reference (rounding identical), |fast - strict| = truncation + re-association.
 //
 // Switched on with b200itp_prefilter_set_strict(1); verification only.
 #include "common.cuh"
