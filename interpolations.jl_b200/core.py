@@ -719,6 +719,17 @@ def evaluate_debug(itp, *xs, want_grad=False):
     return _broadcast_eval(itp, xs, want_value=True, want_grad=want_grad, debug=True)
 
 
+def evaluate_direct(itp, *xs):
+    """`itp.(xs...)` through the direct kernel only (one thread per query, no reordering): the reference point the
+    ordered pipeline is compared with bit for bit."""
+    return _broadcast_eval(itp, xs, want_value=True, want_grad=False, sorted_queries=False)[0]
+
+
+def gradient_direct(itp, *xs):
+    """`Interpolations.gradient.(Ref(itp), xs...)` through the direct kernel only."""
+    return _broadcast_eval(itp, xs, want_value=False, want_grad=True, sorted_queries=False)[1]
+
+
 def evaluate_sorted(itp, *xs):
     """`itp.(xs...)` with on-device L2-friendly query reordering (results in the caller's order)."""
     return _broadcast_eval(itp, xs, want_value=True, want_grad=False, sorted_queries=True)[0]

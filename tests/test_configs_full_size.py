@@ -67,10 +67,11 @@ def test_c2_bicubic_flat_oncell_4096_f32(pkg, orc):
     assert err < 5e-6, err
     coords = [torch.rand(nq, device="cuda", dtype=torch.float32, generator=g) * n + 0.5 for _ in range(2)]
     coords = [c_.clamp_(0.5, n + 0.5) for c_ in coords]
-    v = itp(*coords)
+    v = m.evaluate_direct(itp, *coords)
     gr = m.gradient(itp, *coords)
     assert torch.isfinite(v).all() and torch.isfinite(gr).all() and gr.shape == (nq, 2)
     assert torch.equal(v, m.evaluate_sorted(itp, *coords))
+    assert torch.equal(v, itp(*coords))
     _sample_check(m, orc, itp, itp, coords)
     # node reproduction on a strided subset
     ii = torch.arange(1, n + 1, 61, device="cuda", dtype=torch.float32)
@@ -94,8 +95,10 @@ def test_c3_tricubic_periodic_512_f32(pkg, orc):
     v = m.evaluate_sorted(itp, *coords)
     assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "C3 must be served by the ordered pipeline"
     k = 20_000_000
-    assert torch.equal(v[:k], itp(*[c[:k] for c in coords]))          # ordered pipeline == direct kernel
-    assert torch.equal(v[-k:], itp(*[c[-k:] for c in coords]))
+    assert torch.equal(v[:k], m.evaluate_direct(itp, *[c[:k] for c in coords]))          # ordered pipeline == direct kernel
+    assert torch.equal(v[-k:], m.evaluate_direct(itp, *[c[-k:] for c in coords]))
+    n2 = L.b200itp_eval_sorted_ordered_calls()
+    assert torch.equal(v, itp(*coords)) and L.b200itp_eval_sorted_ordered_calls() == n2 + 1   # the drop-in call takes it too
     _sample_check(m, orc, itp, itp, coords, grad=True)
     # gradients of 5*10^7 queries through the ordered pipeline == the direct kernel's
     kg = 50_000_000
@@ -103,8 +106,8 @@ def test_c3_tricubic_periodic_512_f32(pkg, orc):
     gs = m.gradient_sorted(itp, *[c[:kg] for c in coords])
     assert L.b200itp_eval_sorted_ordered_calls() == n1 + 1
     kd = 4_000_000
-    assert torch.equal(gs[:kd], m.gradient(itp, *[c[:kd] for c in coords]))
-    assert torch.equal(gs[-kd:], m.gradient(itp, *[c[kg - kd:kg] for c in coords]))
+    assert torch.equal(gs[:kd], m.gradient_direct(itp, *[c[:kd] for c in coords]))
+    assert torch.equal(gs[-kd:], m.gradient_direct(itp, *[c[kg - kd:kg] for c in coords]))
     del gs
     # checksum of checksums: a permutation of the queries permutes the results
     perm = torch.randperm(1 << 22, device="cuda", generator=g)
@@ -187,8 +190,8 @@ def test_ordered_path_beyond_8192_bricks(pkg, shape):
     v = m.evaluate_sorted(itp, *coords)
     assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1, "the three-level ordered pipeline must serve this call"
     k = 6_000_000
-    assert torch.equal(v[:k], itp(*[c[:k] for c in coords]))
-    assert torch.equal(v[-k:], itp(*[c[-k:] for c in coords]))
+    assert torch.equal(v[:k], m.evaluate_direct(itp, *[c[:k] for c in coords]))
+    assert torch.equal(v[-k:], m.evaluate_direct(itp, *[c[-k:] for c in coords]))
     gs = m.gradient_sorted(itp, *[c[:k] for c in coords])
     assert L.b200itp_eval_sorted_ordered_calls() == n0 + 2
-    assert torch.equal(gs, m.gradient(itp, *[c[:k] for c in coords]))
+    assert torch.equal(gs, m.gradient_direct(itp, *[c[:k] for c in coords]))
