@@ -254,6 +254,14 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
  * applies, by the direct kernel otherwise.  `first_oob` is the linear index (first axis fastest) of the first tuple that
  * throws. */
 B200ITP_API size_t b200itp_eval_grid_scratch_bytes(const b200itp_desc *d, const int64_t *axis_len);
+/* Where the per-axis structure allows (every case but Line extrapolation, fill values and NoInterp axes) the grid is
+ * evaluated SEPARABLY: the reference's nested reduction (Interpolations.jl:304-316) run as ndims one-dimensional
+ * resampling passes, last axis first — the same operations in the same order, so the same bits as the pointwise
+ * evaluation, but coalesced streams instead of prod(axis_len) scattered stencil gathers (`eachvalue(sitp)`,
+ * scaling.jl:174-256, is this call on the knots of the ranges).  set_separable(0) forces the tuple-expansion path
+ * (verification); separable_calls() counts the calls the separable kernels served. */
+B200ITP_API int b200itp_eval_grid_set_separable(int enable);
+B200ITP_API uint64_t b200itp_eval_grid_separable_calls(void);
 B200ITP_API int b200itp_eval_grid(int dev, const b200itp_desc *d, const void *coefs, const void *const *axis_coords,
                       const int64_t *axis_len, void *out_value, int64_t *first_oob, void *scratch,
                       size_t scratch_bytes, void *stream);

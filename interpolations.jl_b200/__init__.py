@@ -10,7 +10,7 @@ from .flags import (BSpline, Constant, Cubic, Flat, Free, Line, Linear, Natural,
 from .ranges import FloatRange, StepRange, UnitRange, jrange
 from .core import (constant_interpolation, cubic_spline_interpolation, differentiable, linear_interpolation, rrule)
 from .core import (BoundsError, BSplineInterpolation, Extrapolation, FilledExtrapolation, ScaledInterpolation,
-                   bounds, evaluate_debug, evaluate_direct, evaluate_from_host, evaluate_grid, evaluate_sorted, gradient_direct, extrapolate, gradient, gradient_sorted, hessian, interpolate, interpolate_inplace, lbounds, out_dtype,
+                   bounds, eachvalue, evaluate_debug, evaluate_direct, evaluate_from_host, evaluate_grid, evaluate_sorted, gradient_direct, extrapolate, gradient, gradient_sorted, hessian, interpolate, interpolate_inplace, lbounds, out_dtype,
                    prefilter_, scale, ubounds, value_and_gradient)
 from . import _lib, parallel
 
@@ -18,7 +18,7 @@ __all__ = [
     "constant_interpolation", "cubic_spline_interpolation", "differentiable", "linear_interpolation", "rrule",
     "InPlace", "InPlaceQ", "BSpline", "Constant", "Nearest", "Previous", "Next", "NoInterp", "Cubic", "Flat", "Free", "Line", "Linear", "Natural", "OnCell", "OnGrid", "Periodic", "Quadratic",
     "Reflect", "Throw", "FloatRange", "StepRange", "UnitRange", "jrange", "BoundsError", "BSplineInterpolation",
-    "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "evaluate_direct", "gradient_direct", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
+    "Extrapolation", "FilledExtrapolation", "ScaledInterpolation", "evaluate_direct", "gradient_direct", "eachvalue", "bounds", "evaluate_debug", "evaluate_from_host", "evaluate_grid",
     "evaluate_sorted",
     "extrapolate", "gradient", "gradient_sorted", "hessian", "interpolate", "interpolate_inplace", "lbounds", "out_dtype", "prefilter_", "scale", "ubounds",
     "value_and_gradient",

@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
         "b200itp_eval_sorted_set_min_queries": (None, [i64]),
         "b200itp_prefilter_set_segmentation": (C.c_int, [C.c_int]),
         "b200itp_prefilter_set_strict": (C.c_int, [C.c_int]),
+        "b200itp_eval_grid_set_separable": (C.c_int, [C.c_int]),
+        "b200itp_eval_grid_separable_calls": (C.c_uint64, []),
         "b200itp_eval_sorted_ordered_calls": (C.c_uint64, []),
     }
     for name, (res, args) in sigs.items():
@@ -127,7 +129,8 @@ EXPORTED_SYMBOLS = [
     "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_eval", "b200itp_eval_grid", "b200itp_eval_grid_scratch_bytes", "b200itp_hessian",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted", "b200itp_gradient_sorted",
     "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_prefilter_set_segmentation",
-    "b200itp_prefilter_set_strict", "b200itp_eval_sorted_ordered_calls",
+    "b200itp_prefilter_set_strict", "b200itp_eval_sorted_ordered_calls", "b200itp_eval_grid_set_separable",
+    "b200itp_eval_grid_separable_calls",
 ]
 
 

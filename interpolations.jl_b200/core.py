@@ -861,6 +861,21 @@ def evaluate_grid(itp, *vectors):
     return out.reshape(tuple(reversed(lens))).permute(*reversed(range(N)))
 
 
+def eachvalue(sitp):
+    """`collect(eachvalue(sitp))` (scaling.jl:174-256): the scaled interpolant at every integer point of its ranges,
+    `ceil(Int, first(r)):floor(Int, last(r))` per axis — one separable grid evaluation (each axis' weights computed once
+    per coordinate, each coefficient row reused across the axis-1 run, which is what the reference's ScaledIterator
+    caches by hand)."""
+    if not isinstance(sitp, ScaledInterpolation):
+        raise TypeError("eachvalue: a ScaledInterpolation is required")
+    vecs = []
+    for r in sitp.ranges:
+        lo, hi = int(np.ceil(float(r.first))), int(np.floor(float(r.last)))
+        dt = np.float32 if r.tag == TAG_F32 else np.float64
+        vecs.append(np.arange(lo, hi + 1).astype(dt))
+    return evaluate_grid(sitp, *vecs)
+
+
 def hessian(itp, *xs):
     """`Interpolations.hessian.(Ref(itp), xs...)`: trailing axes (N, N) hold the symmetric matrix of every query
     (indexing.jl:37-41, scaling.jl:150-160; extrapolated interpolants: in bounds only, extrapolation.jl:84-90)."""

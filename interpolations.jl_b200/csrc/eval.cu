@@ -341,6 +341,19 @@ extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coe
 namespace b200itp {
 // used by eval_sorted.cu: validated parameters for a values-only evaluation, plus whether the descriptor is
 // a bare Float32 B-spline interpolant (the ordered path's scope) and its uniform degree (0: mixed)
+// grid evaluation (eval_grid.cu): the per-axis parameters of the direct kernel with the coordinate VECTORS as `coords`
+int fill_eval_params_grid(const b200itp_desc *D, const void *coefs, const void *const *coords, EvalParams &P,
+                          bool *w_wide, bool *homogeneous) {
+  Chain c;
+  int rc = derive_chain(D, c);
+  if (rc) B200_FAIL(rc, "eval_grid: invalid descriptor");
+  rc = fill_params(D, c, coefs, coords, 0, nullptr, nullptr, nullptr, nullptr, nullptr, P);
+  if (rc) return rc;
+  *w_wide = c.w_wide != 0;
+  *homogeneous = c.homogeneous;
+  return 0;
+}
+
 int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void *const *coords, int64_t nq,
                             void *out_value, unsigned long long *first_oob_dev, EvalParams &P, int *uniform_degree,
                             bool *plain_f32) {

@@ -1462,6 +1462,21 @@ __global__ void __launch_bounds__(256) grid_expand_kernel(const T *a0, const T *
 }
 }  // namespace b200itp
 
+namespace b200itp {
+bool grid_separable_scope(const b200itp_desc *d);
+size_t grid_separable_scratch_bytes(const b200itp_desc *d, const int64_t *axis_len);
+int grid_separable(int dev, const b200itp_desc *D, const void *coefs, const void *const *axis_coords,
+                   const int64_t *axis_len, void *out_value, int64_t *first_oob, unsigned char *sp, size_t sbytes,
+                   cudaStream_t st, bool *done);
+std::atomic<int> g_grid_separable{1};
+std::atomic<uint64_t> g_grid_separable_calls{0};
+}  // namespace b200itp
+
+// verification switch: 0 forces the tuple-expansion path (every element through the pointwise kernels); returns the
+// previous setting
+extern "C" int b200itp_eval_grid_set_separable(int enable) { return b200itp::g_grid_separable.exchange(enable ? 1 : 0); }
+extern "C" uint64_t b200itp_eval_grid_separable_calls(void) { return b200itp::g_grid_separable_calls.load(); }
+
 static size_t grid_coord_bytes(const b200itp_desc *d, int64_t nq) {
   const size_t es = d->coord_dtype == B200ITP_F64 ? 8 : 4;
   return ((size_t)nq * es + 255) / 256 * 256;
@@ -1472,6 +1487,9 @@ extern "C" size_t b200itp_eval_grid_scratch_bytes(const b200itp_desc *d, const i
   int64_t nq = 1;
   for (int i = 0; i < d->ndims; ++i) nq *= axis_len[i] > 0 ? axis_len[i] : 0;
   if (nq <= 0) return 0;
+  // the separable path needs its axis tables and intermediates only; the expansion path the expanded tuples (+ the
+  // ordered pipeline's scratch)
+  if (b200itp::g_grid_separable.load() && grid_separable_scope(d)) return grid_separable_scratch_bytes(d, axis_len) + 512;
   return grid_coord_bytes(d, nq) * d->ndims + b200itp_eval_sorted_scratch_bytes(d, nq) + 512;
 }
 
@@ -1498,10 +1516,19 @@ extern "C" int b200itp_eval_grid(int dev, const b200itp_desc *d, const void *coe
     sp += mis;
     sbytes -= mis;
   }
-  if (!sp || sbytes < cb * d->ndims) B200_FAIL(B200ITP_E_SIZE, "eval_grid: scratch too small (b200itp_eval_grid_scratch_bytes)");
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval_grid: cannot select device %d", dev);
   cudaStream_t st = (cudaStream_t)stream;
+  if (sp && g_grid_separable.load()) {  // N one-dimensional resampling passes (eval_grid.cu), same bits as pointwise
+    bool done = false;
+    const int rc = grid_separable(dev, d, coefs, axis_coords, axis_len, out_value, first_oob, sp, sbytes, st, &done);
+    if (rc) return rc;
+    if (done) {
+      g_grid_separable_calls.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  if (!sp || sbytes < cb * d->ndims) B200_FAIL(B200ITP_E_SIZE, "eval_grid: scratch too small (b200itp_eval_grid_scratch_bytes)");
   const void *cptr[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   void *optr[B200ITP_MAX_DIMS] = {nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < d->ndims; ++i) {

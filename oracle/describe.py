@@ -14,8 +14,6 @@ from __future__ import annotations
 
 import os
 import sys
-from fractions import Fraction
-
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -103,16 +101,11 @@ def describe(itp, coord_dtype) -> "_pl.Desc":
         D.has_scale = 1
         for d in range(N):
             r = s.ranges[d]
-            rf, rs = Fraction(r.first), Fraction(r.step)
-            rl = rf + (len(r) - 1) * rs           # last(r)
+            # first(r), step(r), last(r): primitives of the range object, each already rounded once to the range's
+            # element type by Julia's range arithmetic (ranges.py); last(r) is NOT first + (n-1)*step(r) in floating point
             tag = r.tag
-            if tag == _T32:                       # range parameters are Float32 numbers
-                f32 = lambda v: float(np.float32(float(v)))
-                D.range_first[d], D.range_step[d] = f32(rf), f32(rs)
-                last_v = float(np.float32(float(rl)))
-            else:
-                D.range_first[d], D.range_step[d] = float(rf), float(rs)
-                last_v = float(rl)
+            D.range_first[d], D.range_step[d] = float(r.first), float(r.step)
+            last_v = float(r.last)
             D.range_tag[d] = tag
             lo, hi, btag = scaled_bounds(D.range_first[d], D.range_step[d], last_v, tag, b.its[d].degree.bc.gt.code,
                                          type(r).__name__ == "UnitRange", b.its[d].degree.code)

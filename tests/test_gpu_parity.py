@@ -9,11 +9,11 @@ Bars (BASELINE.json north_star):
       - STRICT build of the prefilter (reference operation order, no FMA, explicit Woodbury; b200itp_prefilter_set_strict)
         == oracle BIT FOR BIT given the same factors: rounding identical, nothing algorithmic differs;
       - fast kernels, Float64: the element-wise metric at 1e-12;
-      - fast kernels, Float32: |gpu - ref| <= 1e-5 * ||ref||_inf (`norm_err`) AND the element-wise metric at 2e-3.  An
-        element 1000x below the norm carries the absolute rounding error of its O(||ref||) neighbours (a three-axis
-        Float32 solve with condition number 3 per axis: ~1e-6 ||ref||, measured), so two correct Float32 solves with
-        different operation orders differ by up to ~1e-3 in the element-wise metric with its 1e-3 floor: the 1e-5
-        element-wise bar is attainable only by the operation-identical strict build (which meets it with 0).
+      - fast kernels, Float32: |gpu - ref| <= 1e-5 * ||ref||_inf (`norm_err`; measured 1-3e-7, tools/prefilter_err.py,
+        profiles/r2_prefilter_err.txt) AND the element-wise metric at 2e-4 (measured 1-9e-5).  An element 1000x below
+        the norm carries the absolute rounding error of its O(||ref||) neighbours (~1e-7 ||ref||), so two correct
+        Float32 solves with different operation orders differ by ~1e-4 in the element-wise metric with its 1e-3 floor:
+        the 1e-5 element-wise bar is attainable only by the operation-identical strict build (which meets it with 0).
 """
 import itertools
 import os
@@ -36,7 +36,7 @@ def specs(m):
     return out
 
 
-ELEM_TOL = {np.dtype(np.float32): 2e-3, np.dtype(np.float64): 1e-12}
+ELEM_TOL = {np.dtype(np.float32): 2e-4, np.dtype(np.float64): 1e-12}
 
 
 def norm_err(got, ref):
@@ -829,8 +829,8 @@ def test_inplace_boundary_conditions(pkg, orc, coef_dtype, coord_dtype):
                                              shape[d], 1500, coord_dtype)[:1200] for d in range(len(shape))]
                 coords = [np.clip(c, coord_dtype(itp.lbounds()[d]), coord_dtype(itp.ubounds()[d])) for d, c in enumerate(coords)]
                 check_eval(m, orc, itp, coords)
-    bad = m.interpolate(rng.standard_normal(30).astype(coef_dtype), m.BSpline(m.Cubic(m.InPlace(m.OnCell()))))
-    with pytest.raises(ValueError):  # the reference defines InPlace for Quadratic only (quadratic.jl:61-62,91-110)
+    with pytest.raises((TypeError, ValueError)):  # the reference defines InPlace for Quadratic only (quadratic.jl:61-62,91-110)
+        bad = m.interpolate(rng.standard_normal(30).astype(coef_dtype), m.BSpline(m.Cubic(m.InPlace(m.OnCell()))))
         bad(np.array([3.0], coord_dtype))
 
 
@@ -977,3 +977,102 @@ def test_grid_evaluation_equals_pointwise(pkg):
     itp = m.interpolate(rng.standard_normal((9, 9)).astype(np.float32), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))))
     with pytest.raises(m.BoundsError):
         m.evaluate_grid(itp, np.array([1.0, 2.0], np.float32), np.array([3.0, 9.5], np.float32))
+
+
+def _grid_specs(m):
+    return [m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Cubic(m.Flat(m.OnCell()))),
+            m.BSpline(m.Quadratic(m.Reflect(m.OnCell()))), m.BSpline(m.Quadratic(m.Periodic(m.OnGrid()))),
+            m.BSpline(m.Linear()), m.BSpline(m.Constant()), m.BSpline(m.Cubic(m.Line(m.OnGrid())))]
+
+
+@pytest.mark.parametrize("coef_dtype,coord_dtype", [(np.float32, np.float32), (np.float32, np.float64),
+                                                    (np.float64, np.float32), (np.float64, np.float64)])
+def test_grid_separable_bit_exact(pkg, orc, coef_dtype, coord_dtype):
+    """Separable grid evaluation (csrc/eval_grid.cu: one resampling pass per axis, last axis first) against
+      (1) the CPU oracle evaluated pointwise on the same coefficients (values `==`),
+      (2) the GPU tuple-expansion path (b200itp_eval_grid_set_separable(0)),
+    for 1-D .. 4-D, uniform and mixed degrees, bare / scaled / Flat, Periodic, Reflect-extrapolated interpolants, all
+    element-type combinations; and the BoundsError protocol (first throwing tuple in column-major order)."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(99)
+    specs = _grid_specs(m)
+    n_sep = 0
+    for shape in ((33,), (19, 23), (14, 11, 13), (7, 8, 6, 9)):
+        N = len(shape)
+        for trial in range(4):
+            its = tuple(specs[int(rng.integers(len(specs)))] for _ in range(N)) if trial else specs[trial % len(specs)]
+            A = rng.standard_normal(shape).astype(coef_dtype)
+            itp = m.interpolate(A, its)
+            rdt = [np.float32, np.float64][trial % 2]
+            rngs = [m.jrange(rdt(-1), rdt(2), length=n, dtype=rdt) for n in shape]
+            objs = [itp, m.scale(itp, *rngs), m.extrapolate(itp, m.Flat()), m.extrapolate(m.scale(itp, *rngs), m.Periodic()),
+                    m.extrapolate(itp, m.Reflect()), m.extrapolate(m.scale(itp, *rngs), (m.Flat(),) * N if N > 1 else m.Flat())]
+            for obj in objs:
+                ext = isinstance(obj, m.Extrapolation)
+                vecs = []
+                for (lb, ub) in obj.bounds():
+                    lb, ub = float(lb), float(ub)
+                    pad = 0.6 * (ub - lb) if ext else 0.0
+                    v = rng.uniform(lb - pad, ub + pad, int(rng.integers(2, 12))).astype(coord_dtype)
+                    v[0] = coord_dtype(lb) if coord_dtype(lb) >= lb else np.nextafter(coord_dtype(lb), coord_dtype(np.inf))
+                    v[-1] = coord_dtype(ub) if coord_dtype(ub) <= ub else np.nextafter(coord_dtype(ub), coord_dtype(-np.inf))
+                    if not ext:
+                        v = np.clip(v, v[0], v[-1])
+                    vecs.append(v)
+                c0 = L.b200itp_eval_grid_separable_calls()
+                got = m.evaluate_grid(obj, *vecs)
+                assert L.b200itp_eval_grid_separable_calls() == c0 + 1, "the separable kernels must serve this call"
+                n_sep += 1
+                prev = L.b200itp_eval_grid_set_separable(0)
+                try:
+                    exp = m.evaluate_grid(obj, *vecs)
+                finally:
+                    L.b200itp_eval_grid_set_separable(prev)
+                assert torch.equal(got, exp), (shape, its, type(obj).__name__)
+                host = orc.with_coefs(obj, obj.coefficients().cpu().numpy())
+                mesh = np.meshgrid(*vecs, indexing="ij")
+                ov = orc.evaluate(host, *mesh)[0]
+                assert np.array_equal(got.cpu().numpy().astype(np.float64), ov), (shape, its, type(obj).__name__)
+    assert n_sep > 50
+    # Line extrapolation / fill values are not separable: served by the expansion path, same answers as pointwise
+    itp = m.interpolate(rng.standard_normal((12, 9)).astype(coef_dtype), m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+    for obj in (m.extrapolate(itp, m.Line()), m.extrapolate(itp, 0.0)):
+        c0 = L.b200itp_eval_grid_separable_calls()
+        vecs = [rng.uniform(-3, 15, 7).astype(coord_dtype), rng.uniform(-3, 12, 5).astype(coord_dtype)]
+        got = m.evaluate_grid(obj, *vecs)
+        assert L.b200itp_eval_grid_separable_calls() == c0
+        ref = obj(*np.meshgrid(*vecs, indexing="ij"))
+        assert torch.equal(got.to(ref.dtype), ref)
+    # BoundsError: the first throwing tuple, first axis fastest
+    itp = m.interpolate(rng.standard_normal((9, 9, 9)).astype(coef_dtype), m.BSpline(m.Cubic(m.Flat(m.OnGrid()))))
+    with pytest.raises(m.BoundsError) as ei:
+        m.evaluate_grid(itp, np.array([1.0, 2.0, 3.0], coord_dtype), np.array([3.0, 9.5, 2.0], coord_dtype),
+                        np.array([4.0, 0.25], coord_dtype))
+    assert "(1.0, 9.5, 4.0)" in str(ei.value)
+
+
+def test_grid_resampling_full_size_and_eachvalue(pkg):
+    """Resampling the C3 volume (512^3 Float32) onto a 640^3 grid through the separable kernels: spot-checked against the
+    pointwise kernel on 10^6 random output elements, and `eachvalue(sitp)` of a scaled image equals the samples at the
+    knots (node reproduction, test/scaling/scaling.jl:45-50)."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    n, no = 512, 640
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = torch.randn((n, n, n), device="cuda", dtype=torch.float32, generator=g)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
+    vecs = [torch.linspace(1.0, float(n), no, device="cuda", dtype=torch.float32) for _ in range(3)]
+    c0 = L.b200itp_eval_grid_separable_calls()
+    out = m.evaluate_grid(itp, *vecs)
+    assert L.b200itp_eval_grid_separable_calls() == c0 + 1 and tuple(out.shape) == (no, no, no)
+    idx = torch.randint(0, no, (3, 1_000_000), device="cuda", generator=g)
+    ref = m.evaluate_direct(itp, *[vecs[d][idx[d]] for d in range(3)])
+    assert torch.equal(out[idx[0], idx[1], idx[2]], ref)
+    del out, A, itp
+    img = torch.rand((300, 200), device="cuda", dtype=torch.float64, generator=g)
+    sitp = m.scale(m.interpolate(img, m.BSpline(m.Cubic(m.Line(m.OnGrid())))), m.jrange(1, 300), m.jrange(1, 200))
+    ev = m.eachvalue(sitp)
+    assert tuple(ev.shape) == (300, 200) and (ev - img).abs().max().item() < 1e-12
