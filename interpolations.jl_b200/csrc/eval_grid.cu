@@ -93,44 +93,119 @@ __device__ __forceinline__ TO cast_out(TA v) {
   return (TO)v;
 }
 
+// 16-byte vectors of the element types (Float32 x 4, Float64 x 2) for the row passes
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  using type = float4;
+  static constexpr int N = 4;
+};
+template <>
+struct Vec16<double> {
+  using type = double2;
+  static constexpr int N = 2;
+};
+template <typename T, int V>
+struct Pack {
+  T v[V];
+};
+template <typename T, int V>
+__device__ __forceinline__ Pack<T, V> load_pack(const T *p) {
+  Pack<T, V> r;
+  if constexpr (V == 1) {
+    r.v[0] = __ldg(p);
+  } else if constexpr (sizeof(T) * V == 16) {
+    using V16 = typename Vec16<T>::type;
+    const V16 q = __ldg(reinterpret_cast<const V16 *>(p));
+    if constexpr (V == 4) {
+      r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    } else {
+      r.v[0] = q.x; r.v[1] = q.y;
+    }
+  } else {  // 4 doubles: two 16-byte loads
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  }
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_pack(T *p, const Pack<T, V> &r) {
+  if constexpr (V == 1) {
+    *p = r.v[0];
+  } else if constexpr (sizeof(T) * V == 16) {
+    using V16 = typename Vec16<T>::type;
+    V16 q;
+    if constexpr (V == 4) {
+      q.x = r.v[0]; q.y = r.v[1]; q.z = r.v[2]; q.w = r.v[3];
+    } else {
+      q.x = r.v[0]; q.y = r.v[1];
+    }
+    *reinterpret_cast<V16 *>(p) = q;
+  } else {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(r.v[0], r.v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(r.v[2], r.v[3]);
+  }
+}
+
 // One resampling pass along axis d >= 1: rows of R1 contiguous elements.
 //   in  [i + R1 * (p + Sd * h)]   i < R1, p < Sd, h < H
 //   out [i + R1 * (o + Od * h)]
-// blockIdx.y walks the rows (o, h); the row's taps and weights are uniform across the CTA.
-template <typename TI, typename TW, typename TA, typename TO, int L>
+// threadIdx.x walks the row in vectors of V elements (16-byte accesses when the row length and the pointers allow),
+// threadIdx.y / blockIdx.y walk the rows (o, h); a row's taps and weights are uniform across its threads.
+template <typename TI, typename TW, typename TA, typename TO, int L, int V>
 __global__ void __launch_bounds__(256) grid_pass_rows_kernel(const TI *__restrict__ in, TO *__restrict__ out, long long R1,
                                                              long long Sd, long long Od, long long H,
                                                              const int *__restrict__ pos, const TW *__restrict__ w) {
   const long long rows = Od * H;
-  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
-    const long long o = row % Od, h = row / Od;
+  const long long nvec = R1 / V;
+  const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+  const long long rstep = (long long)gridDim.y * blockDim.y;
+  long long o = row0 % Od, h = row0 / Od;
+  const long long ostep = rstep % Od, hstep = rstep / Od;
+  for (long long row = row0; row < rows; row += rstep) {
     int p[L];
     TA wk[L];
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-      p[k] = pos[o * kGridTaps + k];
-      wk[k] = (TA)w[o * kGridTaps + k];
+      p[k] = __ldg(pos + o * kGridTaps + k);
+      wk[k] = (TA)__ldg(w + o * kGridTaps + k);
     }
     const TI *src = in + R1 * Sd * h;
     TO *dst = out + R1 * (o + Od * h);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R1; i += (long long)gridDim.x * blockDim.x) {
-      TA acc = TA(0);
+    for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
+      Pack<TI, V> c[L];
 #pragma unroll
-      for (int k = 0; k < L; ++k) {
-        const TA t = wk[k] * (TA)__ldg(src + i + R1 * (long long)p[k]);
-        acc = k == 0 ? t : t + acc;
+      for (int k = 0; k < L; ++k) c[k] = load_pack<TI, V>(src + iv * V + R1 * (long long)p[k]);
+      Pack<TO, V> r;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        TA acc = TA(0);
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+          const TA t = wk[k] * (TA)c[k].v[e];
+          acc = k == 0 ? t : t + acc;
+        }
+        r.v[e] = cast_out<TO, TA>(acc);
       }
-      dst[i] = cast_out<TO, TA>(acc);
+      store_pack<TO, V>(dst + iv * V, r);
+    }
+    o += ostep;
+    h += hstep;
+    if (o >= Od) {
+      o -= Od;
+      ++h;
     }
   }
 }
 
 // The pass along axis 0 (contiguous): out[o + O0 * h] = sum_k w(o)[k] * in[pos(o)[k] + S0 * h].
-// Thread <-> output coordinate o (its taps and weights stay in registers), rows h walked by blockIdx.y.
+// Thread <-> output coordinate o (its taps and weights stay in registers), rows h walked by blockIdx.y, U rows in flight.
 template <typename TI, typename TW, typename TA, typename TO, int L>
 __global__ void __launch_bounds__(256) grid_pass_axis0_kernel(const TI *__restrict__ in, TO *__restrict__ out, long long S0,
                                                               long long O0, long long H, const int *__restrict__ pos,
                                                               const TW *__restrict__ w) {
+  constexpr int U = 4;
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= O0) return;
   int p[L];
@@ -140,16 +215,57 @@ __global__ void __launch_bounds__(256) grid_pass_axis0_kernel(const TI *__restri
     p[k] = pos[o * kGridTaps + k];
     wk[k] = (TA)w[o * kGridTaps + k];
   }
-  for (long long h = blockIdx.y; h < H; h += gridDim.y) {
-    const TI *src = in + S0 * h;
+  const long long hs = gridDim.y;
+  long long h = blockIdx.y;
+  for (; h + (U - 1) * hs < H; h += U * hs) {
+    TI c[U][L];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < L; ++k) c[u][k] = __ldg(in + S0 * (h + u * hs) + p[k]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      TA acc = TA(0);
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const TA t = wk[k] * (TA)c[u][k];
+        acc = k == 0 ? t : t + acc;
+      }
+      out[o + O0 * (h + u * hs)] = cast_out<TO, TA>(acc);
+    }
+  }
+  for (; h < H; h += hs) {
     TA acc = TA(0);
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-      const TA t = wk[k] * (TA)__ldg(src + p[k]);
+      const TA t = wk[k] * (TA)__ldg(in + S0 * h + p[k]);
       acc = k == 0 ? t : t + acc;
     }
     out[o + O0 * h] = cast_out<TO, TA>(acc);
   }
+}
+
+template <typename TI, typename TW, typename TA, typename TO, int L>
+static int launch_rows(const TI *in, TO *out, long long R1, long long Sd, long long Od, long long H, const int *pos,
+                       const TW *w, int sms, cudaStream_t st) {
+  // vector width: 16-byte accesses on the wider of the two element types when rows and pointers are aligned
+  constexpr int VMAX = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TO) : sizeof(TI));  // 4 for float, 2 for double (narrower type)
+  const bool aligned = ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0;
+  const long long rows = Od * H;
+  auto go = [&](auto vtag) -> int {
+    constexpr int V = decltype(vtag)::value;
+    const long long nvec = R1 / V;
+    unsigned tx = 32;
+    while (tx < 256 && tx < nvec) tx <<= 1;
+    const unsigned ty = 256 / tx;
+    const unsigned gx = (unsigned)std::min<long long>((nvec + tx - 1) / tx, 32);
+    const long long want = std::max<long long>(1, (long long)sms * 8 / gx);
+    const unsigned gy = (unsigned)std::min<long long>(std::min<long long>((rows + ty - 1) / ty, want), 65535LL);
+    grid_pass_rows_kernel<TI, TW, TA, TO, L, V><<<dim3(gx, gy), dim3(tx, ty), 0, st>>>(in, out, R1, Sd, Od, H, pos, w);
+    return 0;
+  };
+  if (aligned && R1 % VMAX == 0) return go(std::integral_constant<int, VMAX>{});
+  return go(std::integral_constant<int, 1>{});
 }
 
 template <typename TI, typename TW, typename TA, typename TO>
@@ -167,15 +283,11 @@ static int launch_pass(const TI *in, TO *out, int d, long long R1, long long Sd,
       default: grid_pass_axis0_kernel<TI, TW, TA, TO, 4><<<grid, 256, 0, st>>>(in, out, Sd, Od, H, pos, w); break;
     }
   } else {
-    const long long rows = Od * H;
-    const unsigned gx = (unsigned)std::min<long long>((R1 + 255) / 256, 64);
-    const unsigned gy = (unsigned)std::min<long long>(rows, std::max<long long>(1, (long long)sms * 16 / gx));
-    dim3 grid(gx, std::min<unsigned>(gy, 65535u));
     switch (L) {
-      case 1: grid_pass_rows_kernel<TI, TW, TA, TO, 1><<<grid, 256, 0, st>>>(in, out, R1, Sd, Od, H, pos, w); break;
-      case 2: grid_pass_rows_kernel<TI, TW, TA, TO, 2><<<grid, 256, 0, st>>>(in, out, R1, Sd, Od, H, pos, w); break;
-      case 3: grid_pass_rows_kernel<TI, TW, TA, TO, 3><<<grid, 256, 0, st>>>(in, out, R1, Sd, Od, H, pos, w); break;
-      default: grid_pass_rows_kernel<TI, TW, TA, TO, 4><<<grid, 256, 0, st>>>(in, out, R1, Sd, Od, H, pos, w); break;
+      case 1: launch_rows<TI, TW, TA, TO, 1>(in, out, R1, Sd, Od, H, pos, w, sms, st); break;
+      case 2: launch_rows<TI, TW, TA, TO, 2>(in, out, R1, Sd, Od, H, pos, w, sms, st); break;
+      case 3: launch_rows<TI, TW, TA, TO, 3>(in, out, R1, Sd, Od, H, pos, w, sms, st); break;
+      default: launch_rows<TI, TW, TA, TO, 4>(in, out, R1, Sd, Od, H, pos, w, sms, st); break;
     }
   }
   count_launch();

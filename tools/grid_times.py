@@ -16,3 +16,10 @@ print(f"grid {mo}^3 outputs: {ms:.2f} ms, {nq / ms / 1e6:.1f} Gevals/s, out writ
 k = 100
 ref = itp(vs[0][:k, None, None].expand(k, k, k), vs[1][None, :k, None].expand(k, k, k), vs[2][None, None, :k].expand(k, k, k))
 assert torch.equal(out[:k, :k, :k], ref)
+L.b200itp_profile_enable(1); out = m.evaluate_grid(itp, *vs); torch.cuda.synchronize(); L.b200itp_profile_enable(0)
+print({k_: round(min(v), 3) for k_, v in m._lib.profile_stages().items()})
+prev = L.b200itp_eval_grid_set_separable(0)
+del out
+a.record(); out2 = m.evaluate_grid(itp, *vs); b.record(); torch.cuda.synchronize()
+L.b200itp_eval_grid_set_separable(prev)
+print(f"expansion path: {a.elapsed_time(b):.2f} ms, {nq / a.elapsed_time(b) / 1e6:.1f} Gevals/s")
