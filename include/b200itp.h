@@ -215,6 +215,12 @@ B200ITP_API int b200itp_prefilter_axis(int dev, void *coefs, int dtype, int ndim
 B200ITP_API int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, const int64_t *size,
                       const int32_t *degree, const int32_t *bc, const int32_t *gridtype,
                       void *stream);
+/* `prefilter(TW, TC, A, it)` for an array that needs no padding (prefiltering.jl:32-38 with padded_axes == axes):
+ * the first axis pass reads the samples from `src` and writes `coefs` (same size and layout, must not overlap unless
+ * equal), the other passes run in place on `coefs`: the copy the reference makes first is folded into the first pass
+ * and the caller's array is left untouched. */
+B200ITP_API int b200itp_prefilter_from(int dev, const void *src, void *coefs, int dtype, int ndims, const int64_t *size,
+                           const int32_t *degree, const int32_t *bc, const int32_t *gridtype, void *stream);
 /* Long lines of arrays with few lines are cut into segments (one warm-up and one look-ahead block each) to fill the
  * machine; a segmented pass agrees with the unsegmented one to round-off (<= 1 ulp in ~1e-5 of the elements) but not
  * bit for bit.  Callers that need results independent of how an array is split into slabs (the slab-sharded prefilter:

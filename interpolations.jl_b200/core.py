@@ -383,8 +383,10 @@ def _stream_ptr(device_index):
     return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
 
 
-def prefilter_(coefs, size, its, device_index):
-    """`prefilter!(TW, ret, it)` on a padded device array (prefiltering.jl:49-59,108-122)."""
+def prefilter_(coefs, size, its, device_index, src=None):
+    """`prefilter!(TW, ret, it)` on a padded device array (prefiltering.jl:49-59,108-122).  With `src` (same size and
+    layout) the first axis pass reads the samples from `src` and writes `coefs`: `src` stays untouched and no copy
+    is made up front."""
     L = _lib.lib()
     N = len(size)
     sz = (C.c_int64 * N)(*size)
@@ -392,6 +394,11 @@ def prefilter_(coefs, size, its, device_index):
     bc = (C.c_int32 * N)(*[it.degree.bc.code for it in its])
     gt = (C.c_int32 * N)(*[it.degree.bc.gt.code for it in its])
     code = F32 if str(coefs.dtype).endswith("float32") else F64
+    if src is not None and src.data_ptr() != coefs.data_ptr():
+        rc = L.b200itp_prefilter_from(device_index, C.c_void_p(src.data_ptr()), C.c_void_p(coefs.data_ptr()), code, N, sz,
+                                      deg, bc, gt, _stream_ptr(device_index))
+        _lib.check(rc, "b200itp_prefilter_from")
+        return coefs
     rc = L.b200itp_prefilter(device_index, C.c_void_p(coefs.data_ptr()), code, N, sz, deg, bc, gt,
                              _stream_ptr(device_index))
     _lib.check(rc, "b200itp_prefilter")
@@ -426,7 +433,9 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
     torch = _torch()
     L = _lib.lib()
     dev = _device_index(device)
-    src, shape = _to_colmajor_device(A, dev)
+    # the caller's array is only READ: the padded copy, or the first axis pass, writes a new array
+    src, shape = _to_colmajor_device(A, dev, alias_ok=True)
+    aliased = isinstance(A, torch.Tensor) and src.data_ptr() == A.data_ptr()
     N = len(shape)
     if not 1 <= N <= MAX_DIMS:
         raise ValueError(f"1..{MAX_DIMS} dimensions are supported, got {N}")
@@ -447,9 +456,13 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
             rc = L.b200itp_copy_with_padding(dev, C.c_void_p(src.data_ptr()), C.c_void_p(coefs.data_ptr()), code, N,
                                              (C.c_int64 * N)(*shape), (C.c_int32 * N)(*pad), _stream_ptr(dev))
             _lib.check(rc, "b200itp_copy_with_padding")
+            prefilter_(coefs, psize, its, dev)
+        elif aliased:
+            coefs = torch.empty_like(src)
+            prefilter_(coefs, psize, its, dev, src=src)  # first pass reads A, writes coefs
         else:
-            coefs = src
-        prefilter_(coefs, psize, its, dev)
+            coefs = src  # already a private device copy (numpy / CPU / row-major input)
+            prefilter_(coefs, psize, its, dev)
     return BSplineInterpolation(coefs, psize, shape, its, dev)
 
 

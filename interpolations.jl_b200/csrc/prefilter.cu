@@ -1066,19 +1066,22 @@ int prefilter_strict_axis(int dev, T *coefs, int ndims, const int64_t *size, int
 // ping-pong between `coefs` and a scratch array; the result always ends in `coefs`.
 template <typename T>
 static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const AxisJob<T> *const *jobs,
-                      cudaStream_t st) {
+                      cudaStream_t st, const T *src0 = nullptr) {
+  // src0: the samples live in another array of the same layout (`interpolate` must not overwrite the caller's array):
+  // the first pass reads them and writes `coefs`, which saves the copy the reference makes up front
+  // (copy_with_padding, prefiltering.jl:17-28, also copies when nothing is padded)
   int64_t total = 1;
   for (int i = 0; i < ndims; ++i) total *= size[i];
   if (total == 0) return 0;
-  T *cur = coefs;
+  T *cur = src0 ? const_cast<T *>(src0) : coefs;
   T *other = nullptr;
   for (int ax = 0; ax < ndims; ++ax) {
     if (!jobs[ax]) continue;
     const int64_t n = size[ax];
     int nseg, seglen;
     choose_segments<T>(dev, total / n, n, jobs[ax]->fast_ok, ax, nseg, seglen);
-    T *dst = cur;
-    if (nseg > 1) {
+    T *dst = cur == src0 ? coefs : cur;
+    if (nseg > 1 && cur != src0) {
       if (!other) {
         void *tmp = nullptr;
         int rc = scratch_get(dev, 0, st, sizeof(T) * (size_t)total, &tmp);
@@ -1091,7 +1094,7 @@ static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const A
     if (rc) return rc;
     cur = dst;
   }
-  if (cur != coefs) {
+  if (cur != coefs) {  // a segmented last pass ended in the scratch array, or no axis was filtered at all (src0)
     B200_CUDA_OK(cudaMemcpyAsync(coefs, cur, sizeof(T) * (size_t)total, cudaMemcpyDeviceToDevice, st));
     count_launch();
   }
@@ -1176,8 +1179,13 @@ static int cached_job(int64_t n, int degree, int bc, int grid, std::shared_ptr<c
 
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
-                               const int32_t *bc, const int32_t *grid, cudaStream_t st) {
+                               const int32_t *bc, const int32_t *grid, cudaStream_t st, const void *src0 = nullptr) {
   if (g_prefilter_strict.load(std::memory_order_relaxed)) {
+    if (src0) {
+      int64_t total = 1;
+      for (int i = 0; i < ndims; ++i) total *= size[i];
+      B200_CUDA_OK(cudaMemcpyAsync(coefs, src0, sizeof(T) * (size_t)total, cudaMemcpyDeviceToDevice, st));
+    }
     for (int ax = 0; ax < ndims; ++ax) {
       if (degree[ax] != B200ITP_CUBIC && degree[ax] != B200ITP_QUADRATIC) continue;
       HostSystem<T> S;  // full-length system (no surrogate), the product's own assembly
@@ -1210,7 +1218,7 @@ static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *s
                 (long long)size[ax]);
     if (rc) return rc;
   }
-  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st);
+  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st, (const T *)src0);
 }
 
 }  // namespace b200itp
@@ -1273,6 +1281,19 @@ extern "C" int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, con
   if (dtype == B200ITP_F32) return prefilter_all_typed<float>(dev, coefs, ndims, size, degree, bc, gridtype, st);
   if (dtype == B200ITP_F64) return prefilter_all_typed<double>(dev, coefs, ndims, size, degree, bc, gridtype, st);
   B200_FAIL(B200ITP_E_DTYPE, "prefilter: dtype must be F32 or F64");
+}
+
+extern "C" int b200itp_prefilter_from(int dev, const void *src, void *coefs, int dtype, int ndims, const int64_t *size,
+                                      const int32_t *degree, const int32_t *bc, const int32_t *gridtype, void *stream) {
+  if (!src || !coefs || !size || !degree || !bc || !gridtype) B200_FAIL(B200ITP_E_BADARG, "prefilter_from: null pointer");
+  if (ndims < 1 || ndims > B200ITP_MAX_DIMS) B200_FAIL(B200ITP_E_BADARG, "prefilter_from: ndims must be 1..4");
+  if (src == coefs) return b200itp_prefilter(dev, coefs, dtype, ndims, size, degree, bc, gridtype, stream);
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "prefilter_from: cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200ITP_F32) return prefilter_all_typed<float>(dev, coefs, ndims, size, degree, bc, gridtype, st, src);
+  if (dtype == B200ITP_F64) return prefilter_all_typed<double>(dev, coefs, ndims, size, degree, bc, gridtype, st, src);
+  B200_FAIL(B200ITP_E_DTYPE, "prefilter_from: dtype must be F32 or F64");
 }
 
 extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,

@@ -1083,3 +1083,24 @@ def test_grid_resampling_full_size_and_eachvalue(pkg):
     sitp = m.scale(m.interpolate(img, m.BSpline(m.Cubic(m.Line(m.OnGrid())))), m.jrange(1, 300), m.jrange(1, 200))
     ev = m.eachvalue(sitp)
     assert tuple(ev.shape) == (300, 200) and (ev - img).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(100000,), (700, 520), (256, 128, 128), (60, 50, 40)])
+def test_interpolate_reads_column_major_input_without_copy_or_damage(pkg, shape):
+    """`interpolate(A, it)` on a CUDA tensor that already is column-major (a Julia array's memory): the first axis pass
+    (unpadded) or the padding copy (padded) reads A directly — A is left untouched and the coefficients are the bits of
+    the copy-then-solve-in-place path (numpy input)."""
+    import torch
+    m = pkg
+    g = torch.Generator(device="cuda").manual_seed(21)
+    base = torch.randn(tuple(reversed(shape)), device="cuda", dtype=torch.float32, generator=g)
+    A = base.permute(*reversed(range(len(shape)))) if len(shape) > 1 else base
+    keep = base.clone()
+    A_host = A.cpu().numpy()
+    for it in (m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Cubic(m.Flat(m.OnCell()))),
+               m.BSpline(m.Quadratic(m.Periodic(m.OnCell()))), m.BSpline(m.Linear())):
+        a = m.interpolate(A, it)
+        assert torch.equal(base, keep), "interpolate overwrote its input"
+        assert a.coefs.data_ptr() != base.data_ptr()
+        b = m.interpolate(A_host, it)
+        assert torch.equal(a.coefs, b.coefs), (shape, it)
