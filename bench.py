@@ -262,6 +262,38 @@ def run_config(ctx, name, workload, make_samples, it_of, wrap, coord_bounds, cdt
     return out
 
 
+def grid_config(ctx):
+    """Resampling: `itp(xvec, yvec, zvec)` of the C3 volume onto a 1000^3 grid: the separable kernels, one
+    pass per axis.  N > 1: the output z-range is sharded.  Algorithmic bytes: coefficients once + the output once."""
+    torch, m, L, dev = ctx.torch, ctx.m, ctx.L, ctx.dev
+    no = 1000
+    g = torch.Generator(device=dev).manual_seed(5)
+    A = torch.rand((N_GRID,) * 3, device=dev, dtype=torch.float32, generator=g).permute(2, 1, 0)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), device=dev)
+    lo, hi = shard(no, ctx.world, ctx.rank)
+    vecs = [torch.linspace(1.0, float(N_GRID), no, device=dev, dtype=torch.float32) for _ in range(3)]
+    vecs[2] = vecs[2][lo:hi].contiguous()
+    c0 = L.b200itp_eval_grid_separable_calls()
+    res = {}
+
+    def ev():
+        res["v"] = None
+        res["v"] = m.evaluate_grid(itp, *vecs)
+
+    ms = timed(ctx, ev, ctx.csteps, 3, flush=False)
+    nout = no ** 3
+    b = 4 * nout + 4 * N_GRID ** 3
+    out = {"workload": "grid: itp(xvec, yvec, zvec), 512^3 Float32 Cubic(Periodic(OnGrid())) resampled onto 1000^3",
+           "eval": {"ms": ms, "queries": nout, "gevals": nout / (ms * 1e-3) / 1e9,
+                    "path": "separable" if L.b200itp_eval_grid_separable_calls() > c0 else "expansion",
+                    "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9, "frac": b / (ms * 1e-3) / 1e9 / ctx.peak,
+                    "l2": "output 4 GB and intermediates 3 GB per call: larger than the L2",
+                    "checksum": float(res["v"].double().sum().item())}}
+    del res, itp, A, vecs
+    torch.cuda.empty_cache()
+    return out
+
+
 def other_configs(ctx):
     """C1, C2, C4, C5 of BASELINE.json (SURVEY §8 sizes and synthetic inputs; §8d algorithmic bytes)."""
     torch, dev = ctx.torch, ctx.dev
@@ -309,6 +341,7 @@ def other_configs(ctx):
         lambda: rnd((n5,) * 4, torch.float64), lambda m: m.BSpline(m.Linear()), lambda m, itp: itp,
         [(1.0, float(n5))] * 4, torch.float64, ctx.c5_queries, False,
         {"pre_bytes": 0, "eval_bytes": lambda q: q * (32 + 8) + 8 * n5**4})
+    out["grid"] = grid_config(ctx)
     return out
 
 

@@ -857,7 +857,7 @@ def evaluate_grid(itp, *vectors):
             ptrs = (C.c_void_p * N)(*[t.data_ptr() for t in ts])
             clens = (C.c_int64 * N)(*lens)
             nbytes = int(L.b200itp_eval_grid_scratch_bytes(C.byref(D), clens))
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=tdev)
+            scratch = _scratch_tensor(max(nbytes, 1), tdev)
             rc = L.b200itp_eval_grid(dev, C.byref(D), C.c_void_p(coefs.data_ptr()), ptrs, clens,
                                      C.c_void_p(out.data_ptr()), C.byref(foob), C.c_void_p(scratch.data_ptr()), nbytes,
                                      _stream_ptr(dev))

@@ -82,15 +82,17 @@ def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, de
 
 
 def _cuda_solver(device_index: int) -> Callable:
-    def solve(t, julia_size, its):
+    def solve(t, julia_size, its, src=None):
         # segmentation off: a line is then solved by the same arithmetic whatever slab it sits in, so the sharded
         # result has the bits of the single-GPU one at every world size (include/b200itp.h)
         L = core._lib.lib()
         prev = L.b200itp_prefilter_set_segmentation(0)
         try:
-            core.prefilter_(t.view(-1), tuple(julia_size), its, device_index)  # raises without the CUDA library
+            # raises without the CUDA library; with `src` the first pass reads the samples and writes `t`
+            core.prefilter_(t.view(-1), tuple(julia_size), its, device_index, src=None if src is None else src.reshape(-1))
         finally:
             L.b200itp_prefilter_set_segmentation(prev)
+    solve.reads_src = True
     return solve
 
 
@@ -102,6 +104,11 @@ def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
     Returns `(coefs_yshard, meta)`: the rank's y-shard of the padded coefficient array, shape (pz, py_local, px),
     and the metadata `allgather_coefficients` needs.  Pass order and systems are the reference's
     (prefiltering.jl:49-59): x, then y, then z.
+
+    Data movement: the x and y passes run in ONE library call on the slab (the first reads `A_slab`, so the samples are
+    never copied first); the all-to-all send buffer is one strided copy of the slab into peer-major order
+    (`view(pz_l, world, py_l, px).permute(1, 0, 2, 3)`); the blocks arrive in rank order == z order, so the receive
+    buffer IS the y-shard.  No zero-filled staging arrays unless the degree pads.
     """
     torch, dist = _torch(), _dist()
     world, rank = _world(group)
@@ -120,25 +127,38 @@ def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
         solve = _cuda_solver(A_slab.device.index)
     skip = BSpline(Linear())
 
-    # ---- local padded slab: copy_with_padding (prefiltering.jl:17-28); the zero z-planes belong to the end ranks
+    # ---- local slab: padded copy (copy_with_padding, prefiltering.jl:17-28; the zero z-planes belong to the end
+    #      ranks) only when some axis pads; otherwise the first pass reads the samples directly
     lead = pad[2] if rank == 0 else 0
     trail = pad[2] if rank == world - 1 else 0
     pzl = nzl + lead + trail
-    slab = torch.zeros((pzl, py, px), dtype=A_slab.dtype, device=A_slab.device)
-    slab[lead:lead + nzl, pad[1]:pad[1] + ny, pad[0]:pad[0] + nx] = A_slab
     pz_counts = [c + (pad[2] if r == 0 else 0) + (pad[2] if r == world - 1 else 0) for r, c in enumerate(counts)]
+    src = None
+    if any(pad):
+        slab = torch.zeros((pzl, py, px), dtype=A_slab.dtype, device=A_slab.device)
+        slab[lead:lead + nzl, pad[1]:pad[1] + ny, pad[0]:pad[0] + nx] = A_slab
+    elif getattr(solve, "reads_src", False) and A_slab.is_contiguous():
+        slab = torch.empty_like(A_slab)
+        src = A_slab
+    else:
+        slab = A_slab.clone()
 
-    # ---- passes along x and y: local
+    # ---- passes along x and y: local, one call
     if pzl > 0:
-        solve(slab, (px, py, pzl), (its[0], skip, skip))
-        solve(slab, (px, py, pzl), (skip, its[1], skip))
+        if src is not None:
+            solve(slab, (px, py, pzl), (its[0], its[1], skip), src=src)
+        else:
+            solve(slab, (px, py, pzl), (its[0], its[1], skip))
 
     # ---- one all-to-all: z-slabs -> y-slabs
     ybounds = [shard_bounds(py, world, r) for r in range(world)]
-    send = torch.cat([slab[:, lo:hi, :].reshape(-1) for lo, hi in ybounds]) if pzl > 0 else slab.reshape(-1)
-    in_splits = [pzl * (hi - lo) * px for lo, hi in ybounds]
     ylo, yhi = ybounds[rank]
     pyl = yhi - ylo
+    if py % world == 0 and pzl > 0:
+        send = slab.view(pzl, world, pyl, px).permute(1, 0, 2, 3).contiguous().view(-1)  # peer-major: one strided copy
+    else:
+        send = torch.cat([slab[:, lo:hi, :].reshape(-1) for lo, hi in ybounds]) if pzl > 0 else slab.reshape(-1)
+    in_splits = [pzl * (hi - lo) * px for lo, hi in ybounds]
     out_splits = [pz_counts[r] * pyl * px for r in range(world)]
     recv = torch.empty(int(sum(out_splits)), dtype=slab.dtype, device=slab.device)
     dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
@@ -152,11 +172,18 @@ def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
 
 
 def allgather_coefficients(yshard, meta, group=None):
-    """Replicate the y-sharded coefficient array on every rank (one broadcast per shard: uneven shards are fine on
-    both NCCL and gloo).  Returns the flat column-major coefficient tensor."""
+    """Replicate the y-sharded coefficient array on every rank.  Equal shards: ONE all-gather into a rank-major buffer
+    and one strided copy into the (z, y, x) layout; uneven shards: one broadcast per shard (fine on NCCL and gloo).
+    Returns the flat column-major coefficient tensor."""
     torch, dist = _torch(), _dist()
     world, rank = _world(group)
     px, py, pz = meta["size"]
+    sizes = [hi - lo for lo, hi in meta["ybounds"]]
+    if len(set(sizes)) == 1 and sizes[0] > 0:
+        pyl = sizes[0]
+        gath = torch.empty((world, pz, pyl, px), dtype=yshard.dtype, device=yshard.device)
+        dist.all_gather_into_tensor(gath.view(-1), yshard.contiguous().view(-1), group=group)
+        return gath.permute(1, 0, 2, 3).reshape(-1)  # (pz, world, pyl, px) -> (pz, py, px): the one copy
     full = torch.empty((pz, py, px), dtype=yshard.dtype, device=yshard.device)
     for r, (lo, hi) in enumerate(meta["ybounds"]):
         if hi == lo:
