@@ -313,6 +313,30 @@ B200ITP_API void b200itp_eval_sorted_set_min_queries(int64_t n);
  * forwarded to the direct kernel): lets tests and bench.py assert which path ran */
 B200ITP_API uint64_t b200itp_eval_sorted_ordered_calls(void);
 
+/* ---- multi-GPU on one box: one host process drives the devices, NCCL over NVLink / NVSwitch ------------
+ * libnccl.so.2 is loaded at run time by b200itp_comm_init (no link-time dependency).  Evaluation needs no collective of
+ * its own: queries are independent, so each device evaluates a contiguous chunk of the query arrays against its replica
+ * of the coefficient array (b200itp_eval* with that device's pointers). */
+typedef struct b200itp_comm b200itp_comm;
+/* ncclCommInitAll over `devs[0..ngpu)` plus one stream per device. */
+B200ITP_API int b200itp_comm_init(int ngpu, const int *devs, b200itp_comm **comm);
+B200ITP_API int b200itp_comm_size(const b200itp_comm *comm);
+B200ITP_API int b200itp_comm_destroy(b200itp_comm *comm);
+/* Replicate the coefficient array held by device `root` on every device: coefs_per_dev[i] is the buffer (device
+ * pointer, `bytes` bytes) on devs[i] (one ncclBroadcast; returns when the copies have landed). */
+B200ITP_API int b200itp_bcast_coefs(b200itp_comm *comm, int root, void *const *coefs_per_dev, size_t bytes);
+/* `interpolate(A, it)` for a large 3-D array, slab-sharded: samples_slab[i] is devs[i]'s z-slab of the samples
+ * (size[0] x size[1] x nz_i column-major, the z-planes split as evenly as possible in device order, sizes differing by at
+ * most one); coefs_full[i] receives the FULL coefficient array (size[0] x size[1] x size[2]) on every device, ready for
+ * query-sharded evaluation.  Passes x and y are local to the slabs, one all-to-all (ncclSend / ncclRecv) re-shards along
+ * y, the z pass is local, one all-gather replicates.  Same pass order and systems as the reference
+ * (prefiltering.jl:49-59), same bits as b200itp_prefilter on one device.  Unpadded specs (Periodic, InPlace, Linear
+ * axes); for padding boundary conditions pass slabs of the padded array.  ms_out (nullable, 2 doubles): device time up
+ * to the end of the z pass, and including the replication. */
+B200ITP_API int b200itp_prefilter_sharded(b200itp_comm *comm, const void *const *samples_slab, void *const *coefs_full,
+                              int dtype, const int64_t *size, const int32_t *degree, const int32_t *bc,
+                              const int32_t *gridtype, double *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

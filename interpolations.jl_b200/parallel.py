@@ -202,3 +202,67 @@ def interpolate_sharded(A_slab, it, group=None, solve: Optional[Callable] = None
     coefs = allgather_coefficients(yshard, meta, group=group)
     dev_index = coefs.device.index if coefs.device.type == "cuda" else None
     return core.BSplineInterpolation(coefs, meta["size"], meta["parent_len"], meta["its"], dev_index)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The C ABI's own multi-GPU entry points (include/b200itp.h: b200itp_comm_init, b200itp_bcast_coefs,
+# b200itp_prefilter_sharded): ONE host process drives several devices — what a Julia session does — NCCL inside the
+# library.  The torch.distributed functions above are the one-process-per-GPU form of the same sequence.
+class Comm:
+    """`b200itp_comm`: NCCL communicator over `devices` (CUDA device indices) owned by this process."""
+
+    def __init__(self, devices: Sequence[int]):
+        import ctypes as C
+        self._C = C
+        self.devices = [int(d) for d in devices]
+        self._L = core._lib.lib()
+        self._h = C.c_void_p(None)
+        devs = (C.c_int32 * len(self.devices))(*self.devices)
+        core._lib.check(self._L.b200itp_comm_init(len(self.devices), devs, C.byref(self._h)), "b200itp_comm_init")
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if self._h:
+            self._L.b200itp_comm_destroy(self._h)
+            self._h = self._C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bcast_coefs(self, buffers, root=0):
+        """Replicate `buffers[root]` (flat torch CUDA tensors, one per device, equal sizes) on every device."""
+        C = self._C
+        nbytes = buffers[root].numel() * buffers[root].element_size()
+        ptrs = (C.c_void_p * len(buffers))(*[b.data_ptr() for b in buffers])
+        _torch().cuda.synchronize()
+        core._lib.check(self._L.b200itp_bcast_coefs(self._h, root, ptrs, nbytes), "b200itp_bcast_coefs")
+
+    def interpolate_sharded(self, slabs, it):
+        """`interpolate(A, it)` with device i holding the z-slab `slabs[i]` (torch CUDA tensor of shape (nz_i, ny, nx):
+        the memory of the Julia array's slab).  Returns one replicated `BSplineInterpolation` per device and the device
+        times (ms) up to the end of the z pass and including the replication."""
+        C = self._C
+        torch = _torch()
+        its = core._its_tuple(it, 3)
+        nz = int(sum(int(s.shape[0]) for s in slabs))
+        ny, nx = int(slabs[0].shape[1]), int(slabs[0].shape[2])
+        code = core.F32 if slabs[0].dtype == torch.float32 else core.F64
+        outs = [torch.empty(nx * ny * nz, dtype=slabs[0].dtype, device=s.device) for s in slabs]
+        size = (C.c_int64 * 3)(nx, ny, nz)
+        deg = (C.c_int32 * 3)(*[i.degree.code for i in its])
+        bc = (C.c_int32 * 3)(*[i.degree.bc.code for i in its])
+        gt = (C.c_int32 * 3)(*[i.degree.bc.gt.code for i in its])
+        sp = (C.c_void_p * len(slabs))(*[s.contiguous().data_ptr() for s in slabs])
+        op = (C.c_void_p * len(slabs))(*[o.data_ptr() for o in outs])
+        ms = (C.c_double * 2)(0.0, 0.0)
+        for s in slabs:
+            torch.cuda.synchronize(s.device)
+        core._lib.check(self._L.b200itp_prefilter_sharded(self._h, sp, op, code, size, deg, bc, gt, ms),
+                        "b200itp_prefilter_sharded")
+        itps = [core.BSplineInterpolation(o, (nx, ny, nz), (nx, ny, nz), its, o.device.index) for o in outs]
+        return itps, (ms[0], ms[1])

@@ -1104,3 +1104,58 @@ def test_interpolate_reads_column_major_input_without_copy_or_damage(pkg, shape)
         assert a.coefs.data_ptr() != base.data_ptr()
         b = m.interpolate(A_host, it)
         assert torch.equal(a.coefs, b.coefs), (shape, it)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c_abi_multi_gpu_entry_points(pkg, dtype):
+    """b200itp_comm_init / b200itp_prefilter_sharded / b200itp_bcast_coefs: one process, every visible GPU
+    (one is enough: the NCCL group then has a single rank).  The sharded prefilter — z-slabs, local x/y passes, one
+    all-to-all, local z pass, all-gather — must return, on EVERY device, the bits of the single-device prefilter; the
+    replicas then serve query-sharded evaluation."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    ndev = min(torch.cuda.device_count(), 4)
+    comm = m.parallel.Comm(list(range(ndev)))
+    try:
+        tdt = torch.float32 if dtype == np.float32 else torch.float64
+        for (nx, ny, nz), it in (((128, 96, 80), m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))),
+                                 ((64, 50, 37), m.BSpline(m.Quadratic(m.Periodic(m.OnCell())))),
+                                 ((96, 40, 44), (m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))), m.BSpline(m.Linear()),
+                                                 m.BSpline(m.Quadratic(m.InPlace(m.OnCell())))))):
+            g = torch.Generator(device="cuda:0").manual_seed(3)
+            A = torch.randn((nz, ny, nx), device="cuda:0", dtype=tdt, generator=g)   # memory of the Julia array (nx, ny, nz)
+            prev = L.b200itp_prefilter_set_segmentation(0)
+            try:
+                ref = m.interpolate(A.permute(2, 1, 0), it, device="cuda:0")
+            finally:
+                L.b200itp_prefilter_set_segmentation(prev)
+            slabs = []
+            for r in range(ndev):
+                lo, hi = m.parallel.shard_bounds(nz, ndev, r)
+                slabs.append(A[lo:hi].to(f"cuda:{r}").contiguous())
+            itps, ms = comm.interpolate_sharded(slabs, it)
+            for r, itp in enumerate(itps):
+                assert itp.coefs.device.index == r
+                assert torch.equal(itp.coefs.to("cuda:0"), ref.coefs), ((nx, ny, nz), r)
+            # query-sharded evaluation on the replicas == evaluation on one device
+            q = [torch.rand(30000, device="cuda:0", dtype=torch.float32, generator=g) * (n - 1) + 1 for n in (nx, ny, nz)]
+            whole = ref(*q)
+            parts = []
+            for r, itp in enumerate(itps):
+                lo, hi = m.parallel.shard_bounds(30000, ndev, r)
+                with torch.cuda.device(r):
+                    parts.append(itp(*[c[lo:hi].to(f"cuda:{r}") for c in q]).to("cuda:0"))
+            assert torch.equal(torch.cat(parts), whole)
+        bufs = [torch.full((1 << 20,), float(r + 1), device=f"cuda:{r}", dtype=tdt) for r in range(ndev)]
+        comm.bcast_coefs(bufs, root=ndev - 1)
+        for b in bufs:
+            assert bool((b == float(ndev)).all())
+    finally:
+        comm.close()
+    with pytest.raises(Exception):  # padding boundary conditions are not sharded by the library
+        c2 = m.parallel.Comm([0])
+        try:
+            c2.interpolate_sharded([torch.zeros((8, 8, 8), device="cuda:0")], m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
+        finally:
+            c2.close()
