@@ -905,6 +905,38 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(const T *__restrict__ src
   }
 }
 
+// Row-wise variant: blockIdx.y walks the rows of the padded array (all axes but the first), the row's source offset is
+// found once per row (no per-element divisions), threads move the row with coalesced accesses.  The element-wise kernel
+// above spends its time in four 64-bit div/mod per element (measured 1.7 TB/s on 8194^2 Float32; this one streams).
+template <typename T>
+__global__ void __launch_bounds__(256) pad_copy_rows_kernel(const T *__restrict__ src, T *__restrict__ dst, int ndims,
+                                                            int64_t d0, int64_t d1, int64_t d2, int64_t d3, int p0, int p1,
+                                                            int p2, int p3, int64_t rows) {
+  const int64_t ds[4] = {d0, d1, d2, d3};
+  const int ps[4] = {p0, p1, p2, p3};
+  const int64_t s0 = d0 - 2 * p0;
+  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    int64_t rem = row, soff = 0, smul = s0;
+    bool inside = true;
+#pragma unroll
+    for (int d = 1; d < 4; ++d) {
+      if (d < ndims) {
+        const int64_t c = rem % ds[d];
+        rem /= ds[d];
+        const int64_t sc = c - ps[d];
+        const int64_t sd = ds[d] - 2 * ps[d];
+        inside = inside && sc >= 0 && sc < sd;
+        soff += sc * smul;
+        smul *= sd;
+      }
+    }
+    T *drow = dst + row * d0;
+    const T *srow = src + soff - p0;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < d0; x += (int64_t)gridDim.x * blockDim.x)
+      drow[x] = (inside && x >= p0 && x < d0 - p0) ? srow[x] : T(0);
+  }
+}
+
 // ================================================================== host drivers
 // Factor arrays longer than kSurrogate rows are represented by their first and last kSurrogate/2 rows:
 // the LU factors of the reference's systems are constant in between (checked by the caller), the
@@ -1315,14 +1347,24 @@ extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, in
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count(dev) * 16);
   StageScope sc("copy_with_padding", st);
-  if (dtype == B200ITP_F32)
+  if (dtype != B200ITP_F32 && dtype != B200ITP_F64) B200_FAIL(B200ITP_E_DTYPE, "copy_with_padding: dtype must be F32 or F64");
+  const int64_t rows = total / ds[0];
+  if (ds[0] >= 64) {  // rows long enough for coalesced row-wise copies
+    // few long rows (1-D arrays): spread the row over the machine instead
+    const unsigned gx = (unsigned)std::min<int64_t>((ds[0] + 255) / 256, std::max<int64_t>(8, (int64_t)sm_count(dev) * 16 / std::max<int64_t>(rows, 1)));
+    dim3 grid(gx, (unsigned)std::min<int64_t>(rows, std::max<int64_t>(1, (int64_t)sm_count(dev) * 16 / gx)));
+    if (dtype == B200ITP_F32)
+      pad_copy_rows_kernel<float><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, ndims, ds[0], ds[1], ds[2], ds[3],
+                                                        ps[0], ps[1], ps[2], ps[3], rows);
+    else
+      pad_copy_rows_kernel<double><<<grid, 256, 0, st>>>((const double *)src, (double *)dst, ndims, ds[0], ds[1], ds[2], ds[3],
+                                                         ps[0], ps[1], ps[2], ps[3], rows);
+  } else if (dtype == B200ITP_F32)
     pad_copy_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)src, (float *)dst, ndims, ds[0], ds[1],
                                                               ds[2], ds[3], ps[0], ps[1], ps[2], ps[3], total);
-  else if (dtype == B200ITP_F64)
+  else
     pad_copy_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)src, (double *)dst, ndims, ds[0], ds[1],
                                                                ds[2], ds[3], ps[0], ps[1], ps[2], ps[3], total);
-  else
-    B200_FAIL(B200ITP_E_DTYPE, "copy_with_padding: dtype must be F32 or F64");
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
   return 0;
