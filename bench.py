@@ -404,16 +404,28 @@ def main():
     A = synthetic_volume(torch, dev)
     ncoef = N_GRID**3
 
+    side = torch.cuda.Stream(device=dev)
+
     def make_step(coords):
         def step():
-            # rank 0 prefilters; the coefficient array is replicated over NVLink; every rank evaluates its shard
-            if rank == 0:
-                coefs = m.interpolate(A, it, device=dev).coefs
-            else:
-                coefs = torch.empty(ncoef, dtype=torch.float32, device=dev)
-            if world > 1:
-                dist.broadcast(coefs, src=0)
+            # rank 0 prefilters; the coefficient array is replicated over NVLink; every rank evaluates its shard.
+            # The coefficients are produced on a side stream: the ordered pipeline's count / split kernels only read the
+            # query coordinates, so they run meanwhile, and the gather kernel waits for `ready_event`
+            # (b200itp_eval_set_coefs_event).  Same work per step, the serial prologue is off the critical path.
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if rank == 0:
+                    coefs = m.interpolate(A, it, device=dev).coefs
+                else:
+                    coefs = torch.empty(ncoef, dtype=torch.float32, device=dev)
+                if world > 1:
+                    dist.broadcast(coefs, src=0)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            coefs.record_stream(main)
             itp = m.BSplineInterpolation(coefs, (N_GRID,) * 3, (N_GRID,) * 3, (it,) * 3, local_rank)
+            itp.ready_event = ready
             return itp(*coords)  # the drop-in call: takes the ordered pipeline for this size
         return step
 

@@ -252,6 +252,13 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
                  int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
                  int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
 
+/* Pipelining hook for multi-GPU hosts: `cuda_event` (a cudaEvent_t, or NULL to clear) marks the moment the coefficient
+ * array of the NEXT evaluation call (b200itp_eval / _eval_sorted / _gradient_sorted, any stream, taken once) becomes
+ * valid — e.g. the end of an NCCL broadcast or of the prefilter on another stream.  The call then waits for it only
+ * right before its first kernel that reads coefficients: the ordered pipeline's count / scan / split kernels, which
+ * only read the query coordinates, run while the coefficients are still on their way. */
+B200ITP_API int b200itp_eval_set_coefs_event(void *cuda_event);
+
 /* Tensor-product (grid) evaluation `itp(xvec, yvec, ...)` (src/b-splines/indexing.jl:16-23, src/scaling/scaling.jl:98-100,
  * src/extrapolation/extrapolation.jl:59-70): `axis_coords[d]` is a DEVICE vector of `axis_len[d]` coordinates of
  * d->coord_dtype; `out_value` receives prod(axis_len) elements of b200itp_out_dtype(d), first axis fastest (the Julia

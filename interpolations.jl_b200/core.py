@@ -683,6 +683,11 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
         def p(t):
             return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(None)
 
+        ev = getattr(itp._chain()[0], "ready_event", None)
+        if nq > 0 and ev is not None:
+            # coefficients still on their way on another stream (parallel.broadcast_interpolant(..., overlap=True)): the
+            # library waits for this event right before its first kernel that reads them
+            L.b200itp_eval_set_coefs_event(C.c_void_p(ev.cuda_event))
         if nq > 0:
             # scratch_bytes is 0 when the ordered pipeline would not serve this call (small / L2-resident / wrapped)
             nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq) if (

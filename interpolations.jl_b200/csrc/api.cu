@@ -56,6 +56,12 @@ int scratch_get(int dev, int slot, cudaStream_t stream, size_t bytes, void **out
   return 0;
 }
 
+// ---- coefficient-ready event: lets a host replicate / produce the coefficient array on another stream (NCCL
+//      broadcast, prefilter) while the ordered pipeline already counts and splits the queries, which needs no
+//      coefficients; only the kernels that gather coefficients wait.
+static std::atomic<cudaEvent_t> g_coefs_event{nullptr};
+cudaEvent_t take_coefs_event() { return g_coefs_event.exchange(nullptr); }
+
 // ---- per-stage timing
 namespace {
 struct StageRec {
@@ -128,6 +134,11 @@ extern "C" int b200itp_profile_get(int i, char *name, size_t namelen, double *ms
     memcpy(name, r.name.data(), c);
     name[c] = 0;
   }
+  return 0;
+}
+
+extern "C" int b200itp_eval_set_coefs_event(void *cuda_event) {
+  g_coefs_event.store((cudaEvent_t)cuda_event);
   return 0;
 }
 

@@ -70,6 +70,9 @@ struct StageScope {
   }
 };
 
+// "coefficients ready" event of the next evaluation call (b200itp_eval_set_coefs_event): taken (and cleared) by the
+// evaluation entry points, waited for on the caller's stream right before the first kernel that READS coefficients
+cudaEvent_t take_coefs_event();
 // per-device grow-only scratch buffer (guarded by a mutex; see api.cu)
 int scratch_get(int dev, int slot, cudaStream_t stream, size_t bytes, void **out);
 

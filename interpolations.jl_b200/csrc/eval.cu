@@ -247,6 +247,7 @@ static int eval_common(int dev, const b200itp_desc *D, const void *coefs, const 
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval: cannot select device %d", dev);
   if (first_oob) *first_oob = -1;
+  if (cudaEvent_t ev = take_coefs_event()) B200_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));  // coefficients produced elsewhere
   if (nq == 0 || (!out_value && !out_grad)) return 0;
 
   void *flag = nullptr;
@@ -316,6 +317,7 @@ extern "C" int b200itp_hessian(int dev, const b200itp_desc *Din, const void *coe
   if (first_oob) *first_oob = -1;
   if (nq == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (cudaEvent_t ev = take_coefs_event()) B200_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));  // coefficients produced elsewhere
   void *flag = nullptr;
   rc = scratch_get(dev, 2, st, 256, &flag);
   if (rc) return rc;

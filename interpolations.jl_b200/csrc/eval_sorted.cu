@@ -1272,6 +1272,9 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
     }
     count_launch();
   }
+  // the count / scan / split kernels above never touch the coefficient array: a host that replicates or prefilters it
+  // on another stream (b200itp_eval_set_coefs_event) overlaps that with them; the gather kernel waits here
+  if (cudaEvent_t ev = take_coefs_event()) B200_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));
   {
     StageScope sc(GRAD ? "ord_eval_gradient" : "ord_eval", st);
     ord_eval_kernel<N, DEG, GRAD><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
@@ -1519,6 +1522,7 @@ extern "C" int b200itp_eval_grid(int dev, const b200itp_desc *d, const void *coe
   DeviceGuard g(dev);
   if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "eval_grid: cannot select device %d", dev);
   cudaStream_t st = (cudaStream_t)stream;
+  if (cudaEvent_t ev = take_coefs_event()) B200_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));  // coefficients produced elsewhere
   if (sp && g_grid_separable.load()) {  // N one-dimensional resampling passes (eval_grid.cu), same bits as pointwise
     bool done = false;
     const int rc = grid_separable(dev, d, coefs, axis_coords, axis_len, out_value, first_oob, sp, sbytes, st, &done);

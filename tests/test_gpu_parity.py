@@ -1159,3 +1159,41 @@ def test_c_abi_multi_gpu_entry_points(pkg, dtype):
             c2.interpolate_sharded([torch.zeros((8, 8, 8), device="cuda:0")], m.BSpline(m.Cubic(m.Line(m.OnGrid()))))
         finally:
             c2.close()
+
+
+def test_coefficients_ready_event_orders_the_gather_after_a_side_stream(pkg):
+    """b200itp_eval_set_coefs_event: the coefficient array is produced on ANOTHER stream (here: a delay, then the prefilter)
+    while the evaluation call is already enqueued; the ordered pipeline's count / split kernels run meanwhile and its
+    gather kernel waits for the event, and so does the direct kernel.  Results equal the synchronous ones."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    A = torch.randn((96, 80, 72), device="cuda", dtype=torch.float32, generator=g).permute(2, 1, 0)
+    it = m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))
+    q = [(torch.rand(400_000, device="cuda", generator=g) * (n - 1) + 1) for n in A.shape]
+    ref_itp = m.interpolate(A, it)
+    ref = m.evaluate_direct(ref_itp, *q)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    prev = L.b200itp_eval_sorted_min_queries()
+    for ordered in (True, False):
+        L.b200itp_eval_sorted_set_min_queries(1 if ordered else 1 << 40)
+        try:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                torch.cuda._sleep(200_000_000)          # ~0.1 s: the evaluation call below is enqueued long before
+                coefs = m.interpolate(A, it).coefs
+                ready = torch.cuda.Event()
+                ready.record(side)
+            coefs.record_stream(main)
+            itp = m.BSplineInterpolation(coefs, ref_itp.size, ref_itp.parent_len, ref_itp.its, ref_itp.device_index)
+            itp.ready_event = ready
+            n0 = L.b200itp_eval_sorted_ordered_calls()
+            out = itp(*q)
+            assert (L.b200itp_eval_sorted_ordered_calls() == n0 + 1) == ordered
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), ordered
+        finally:
+            L.b200itp_eval_sorted_set_min_queries(prev)
