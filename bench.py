@@ -53,6 +53,32 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's CPU threads (and therefore its pinned host buffers, first-touch) to the NUMA node the GPU's PCIe
+    slot hangs off: host<->device copies of 8 ranks otherwise cross the socket interconnect.  Best effort; returns a
+    short description for the JSON line."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                                      text=True, timeout=10).strip().lower()
+        # sysfs uses a 4-digit PCI domain, nvidia-smi prints 8
+        parts = bus.split(":")
+        sysbus = ":".join([parts[0][-4:]] + parts[1:])
+        node = int(open(f"/sys/bus/pci/devices/{sysbus}/numa_node").read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa node {node} ({len(allowed)} cpus)"
+        return f"numa node {node}: no allowed cpus, unchanged"
+    except Exception as e:  # no sysfs / no permission: leave the affinity alone
+        return f"numa: unchanged ({type(e).__name__})"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -370,6 +396,7 @@ def main():
     import b200_loader
     m = b200_loader.load()
     L = m._lib.lib()  # raises if the CUDA library is missing: there is no fallback
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: not bound (single rank)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -594,7 +621,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": args.queries / (te.item() / e_steps * 1e-3) / 1e9, "unit": "Gevals/s",
                "h2d_bytes_per_step": 12 * args.queries + 4 * ncoef, "d2h_bytes_per_step": 4 * args.queries,
-               "queries_per_step": args.queries, "queries_per_gpu_per_step": nq, "ms_per_step": te.item() / e_steps}
+               "queries_per_step": args.queries, "queries_per_gpu_per_step": nq, "ms_per_step": te.item() / e_steps,
+               "host": numa}
         del host_coords, host_A, host_out
     if sampler:
         sampler.stop_flag.set()
