@@ -252,6 +252,10 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
                  int64_t nq, void *out_value, void *out_grad, int64_t *first_oob,
                  int32_t *dbg_index, uint32_t *dbg_branch, void *stream);
 
+/* cudaLimitMaxL2FetchGranularity of the device's context (32, 64 or 128 bytes; 0 = only query).  Returns the previous
+ * value (negative: CUDA error). */
+B200ITP_API int b200itp_set_l2_fetch_granularity(int dev, int bytes);
+
 /* Pipelining hook for multi-GPU hosts: `cuda_event` (a cudaEvent_t, or NULL to clear) marks the moment the coefficient
  * array of the NEXT evaluation call (b200itp_eval / _eval_sorted / _gradient_sorted, any stream, taken once) becomes
  * valid — e.g. the end of an NCCL broadcast or of the prefilter on another stream.  The call then waits for it only

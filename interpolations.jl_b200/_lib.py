@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "b200itp_prefilter_set_strict": (C.c_int, [C.c_int]),
         "b200itp_eval_grid_set_separable": (C.c_int, [C.c_int]),
         "b200itp_eval_set_coefs_event": (C.c_int, [vp]),
+        "b200itp_set_l2_fetch_granularity": (C.c_int, [i32, i32]),
         "b200itp_comm_init": (C.c_int, [i32, pi32, C.POINTER(vp)]),
         "b200itp_comm_size": (C.c_int, [vp]),
         "b200itp_comm_destroy": (C.c_int, [vp]),
@@ -138,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted", "b200itp_gradient_sorted",
     "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_prefilter_set_segmentation",
     "b200itp_prefilter_set_strict", "b200itp_eval_sorted_ordered_calls", "b200itp_eval_grid_set_separable",
-    "b200itp_eval_grid_separable_calls", "b200itp_eval_set_coefs_event", "b200itp_comm_init", "b200itp_comm_size", "b200itp_comm_destroy",
+    "b200itp_eval_grid_separable_calls", "b200itp_eval_set_coefs_event", "b200itp_set_l2_fetch_granularity", "b200itp_comm_init", "b200itp_comm_size", "b200itp_comm_destroy",
     "b200itp_bcast_coefs", "b200itp_prefilter_sharded",
 ]
 

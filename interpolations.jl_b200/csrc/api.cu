@@ -137,6 +137,18 @@ extern "C" int b200itp_profile_get(int i, char *name, size_t namelen, double *ms
   return 0;
 }
 
+extern "C" int b200itp_set_l2_fetch_granularity(int dev, int bytes) {
+  // cudaLimitMaxL2FetchGranularity (32 / 64 / 128): how much the L2 fetches from HBM around a missing sector.  The
+  // scattered-gather kernels want 32 (a 16-byte tap row otherwise drags in a 128-byte line: measured 1070 B of DRAM
+  // reads per 4-D linear query), the streaming kernels do not care.  A context-wide hint; returns the previous value.
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "set_l2_fetch_granularity: cannot select device %d", dev);
+  size_t prev = 0;
+  B200_CUDA_OK(cudaDeviceGetLimit(&prev, cudaLimitMaxL2FetchGranularity));
+  if (bytes > 0) B200_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return (int)prev;
+}
+
 extern "C" int b200itp_eval_set_coefs_event(void *cuda_event) {
   g_coefs_event.store((cudaEvent_t)cuda_event);
   return 0;
