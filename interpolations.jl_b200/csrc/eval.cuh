@@ -65,6 +65,31 @@ struct EvalParams {
   int clamp_taps[4]; // Quadratic(InPlace/InPlaceQ): outer taps clamped to the axis (quadratic.jl:61-62)
 };
 
+// Scattered coefficient gathers.  B200ITP_GATHER_VOLATILE=1 issues them as `ld.volatile.global` (no L1 allocation):
+// measured on B200 (tools/ubench_gather.cu, profiles/r2_ubench_gather.txt), random 16-byte gathers over 2 GiB run at
+// 32 G/s through `ld.global.nc` and 39 G/s volatile — the HBM-missing gather is bound by the ACCESS RATE (every miss
+// fills a 128-byte line: 124 B of DRAM reads per 16-byte gather), not by bytes.
+#ifndef B200ITP_GATHER_VOLATILE
+#define B200ITP_GATHER_VOLATILE 0
+#endif
+template <typename T>
+__device__ __forceinline__ T gather_ld(const T *p) {
+#if B200ITP_GATHER_VOLATILE
+  return *reinterpret_cast<const volatile T *>(p);
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float4 gather_ld4(const float4 *p) {
+#if B200ITP_GATHER_VOLATILE
+  float4 r;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <typename A, typename B>
 struct Promote {
   using type = double;
@@ -350,7 +375,7 @@ struct Reduce {
         TA gk[N];
         const TC *b = base + (long long)A.pos[k] * P.stride[D];
         if constexpr (D == N - 1) {
-          vk = (TA)__ldg(b);
+          vk = (TA)gather_ld(b);
         } else {
           Reduce<N, DEG, TC, TW, GRAD, D + 1>::run(P, ax, b, vk, gk);
         }
@@ -398,7 +423,7 @@ struct ReduceSel {
         const TC *b = base + (long long)A.pos[k] * P.stride[D];
         TA vk;
         if constexpr (D == N - 1) {
-          vk = (TA)__ldg(b);
+          vk = (TA)gather_ld(b);
         } else {
           vk = ReduceSel<N, DEG, TC, TW, D + 1>::run(P, ax, sel, b);
         }
@@ -419,7 +444,7 @@ __device__ __forceinline__ void load_row4(const float *coefs, long long lin, lon
   const int sft = (int)(lin - a);
   float4 q0;
   if (a + 4 <= total) {
-    q0 = __ldg(reinterpret_cast<const float4 *>(coefs + a));
+    q0 = gather_ld4(reinterpret_cast<const float4 *>(coefs + a));
   } else {  // the aligned quad would extend past the allocation (total % 4 != 0, Quadratic: 3 taps end at total - 1)
     q0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < total) q0.x = __ldg(coefs + a);
@@ -429,7 +454,7 @@ __device__ __forceinline__ void load_row4(const float *coefs, long long lin, lon
   float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (sft != 0) {
     if (a + 8 <= total) {
-      q1 = __ldg(reinterpret_cast<const float4 *>(coefs + a + 4));
+      q1 = gather_ld4(reinterpret_cast<const float4 *>(coefs + a + 4));
     } else {  // last few elements of the array: stay inside the allocation
       if (a + 4 < total) q1.x = __ldg(coefs + a + 4);
       if (a + 5 < total) q1.y = __ldg(coefs + a + 5);
