@@ -571,7 +571,7 @@ def main():
             barrier()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            ysh, meta = par.prefilter_sharded(slab, it)
+            ysh, meta = par.prefilter_sharded(slab, it, counts=[b - a for a, b in (par.shard_bounds(N_GRID, world, r) for r in range(world))])
             e1.record()
             full = par.allgather_coefficients(ysh, meta)
             e2.record()

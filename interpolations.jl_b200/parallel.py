@@ -96,7 +96,7 @@ def _cuda_solver(device_index: int) -> Callable:
     return solve
 
 
-def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
+def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None, counts=None):
     """Slab-sharded `interpolate(A, it)` for a 3-D array.
 
     `A_slab`: this rank's z-slab of the samples, torch tensor of shape (nz_local, ny, nx) (z-planes
@@ -117,8 +117,14 @@ def prefilter_sharded(A_slab, it, group=None, solve: Optional[Callable] = None):
     its = core._its_tuple(it, 3)
     pad = [1 if needs_padding(i) else 0 for i in its]
     nzl, ny, nx = (int(s) for s in A_slab.shape)
-    counts = [None] * world
-    dist.all_gather_object(counts, nzl, group=group)
+    if counts is None:
+        # slab sizes of the other ranks: one small tensor all-gather (an object all-gather pickles on the CPU and costs
+        # milliseconds); callers that split with `shard_bounds` can pass `counts` and skip it
+        mine = torch.tensor([nzl], dtype=torch.int64, device=A_slab.device)
+        allc = torch.empty(world, dtype=torch.int64, device=A_slab.device)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        counts = [int(v) for v in allc.tolist()]
+    counts = [int(c) for c in counts]
     nz = int(sum(counts))
     px, py, pz = nx + 2 * pad[0], ny + 2 * pad[1], nz + 2 * pad[2]
     if solve is None:
