@@ -586,7 +586,34 @@ def main():
                    "prefilter_gbs": pre_bytes / (t2[0].item() * 1e-3) / 1e9, "matches_single_gpu": ok,
                    "single_gpu_prefilter_ms": pre_ms,
                    "note": "z-slabs, local x/y passes, one all-to-all, local z pass; then all-gather for evaluation"}
-        del full, ysh, slab, itp_check
+        del full, ysh, slab
+        # the same sequence through the C ABI's own entry points (b200itp_comm_init / b200itp_prefilter_sharded): ONE
+        # process — rank 0 — drives all N devices, the other ranks wait with idle GPUs
+        barrier()
+        if rank == 0:
+            try:
+                comm = par.Comm(list(range(world)))
+                base = A.permute(2, 1, 0)
+                slabs = []
+                for r in range(world):
+                    a, b = par.shard_bounds(N_GRID, world, r)
+                    slabs.append(base[a:b].to(f"cuda:{r}").contiguous())
+                best = None
+                for _ in range(4):
+                    itps, ms2 = comm.interpolate_sharded(slabs, it)
+                    best = ms2 if best is None else (min(best[0], ms2[0]), min(best[1], ms2[1]))
+                same = all(bool(torch.equal(i.coefs.to(dev), itp_check.coefs)) for i in itps)
+                sharded["c_abi"] = {"prefilter_ms": best[0], "prefilter_plus_allgather_ms": best[1],
+                                    "prefilter_gbs": pre_bytes / (best[0] * 1e-3) / 1e9, "matches_single_gpu": same,
+                                    "note": "b200itp_prefilter_sharded: one process drives the N devices (ncclSend/Recv "
+                                            "all-to-all, ncclAllGather), strided pack kernels, no torch in the path"}
+                del itps, slabs
+                comm.close()
+            except Exception as e:  # reported, never fatal for the headline
+                sharded["c_abi"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.set_device(local_rank)
+        barrier()
+        del itp_check
 
     # ---- end to end through the public API with host buffers (pinned): H2D samples + coords, D2H results, per step
     e2e = None
