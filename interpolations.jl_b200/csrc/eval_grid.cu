@@ -153,10 +153,23 @@ __device__ __forceinline__ void store_pack(T *p, const Pack<T, V> &r) {
 //   out [i + R1 * (o + Od * h)]
 // threadIdx.x walks the row in vectors of V elements (16-byte accesses when the row length and the pointers allow),
 // threadIdx.y / blockIdx.y walk the rows (o, h); a row's taps and weights are uniform across its threads.
-template <typename TI, typename TW, typename TA, typename TO, int L, int V>
+template <typename TI, typename TW, typename TA, typename TO, int L, int V, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(256) grid_pass_rows_kernel(const TI *__restrict__ in, TO *__restrict__ out, long long R1,
                                                              long long Sd, long long Od, long long H,
                                                              const int *__restrict__ pos, const TW *__restrict__ w) {
+  // the axis' tap table in shared memory when it fits (a row's taps are then an LDS away instead of a dependent global
+  // load in front of every row: with short rows — one vector per thread — that latency was the bound)
+  extern __shared__ unsigned char grid_smem[];
+  int *spos = reinterpret_cast<int *>(grid_smem);
+  TW *sw = reinterpret_cast<TW *>(grid_smem + (size_t)Od * kGridTaps * sizeof(int));
+  if (TABLE_IN_SMEM) {
+    const int nt = blockDim.x * blockDim.y, t = threadIdx.y * blockDim.x + threadIdx.x;
+    for (long long i = t; i < Od * kGridTaps; i += nt) {
+      spos[i] = pos[i];
+      sw[i] = w[i];
+    }
+    __syncthreads();
+  }
   const long long rows = Od * H;
   const long long nvec = R1 / V;
   const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
@@ -168,8 +181,8 @@ __global__ void __launch_bounds__(256) grid_pass_rows_kernel(const TI *__restric
     TA wk[L];
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-      p[k] = __ldg(pos + o * kGridTaps + k);
-      wk[k] = (TA)__ldg(w + o * kGridTaps + k);
+      p[k] = TABLE_IN_SMEM ? spos[o * kGridTaps + k] : __ldg(pos + o * kGridTaps + k);
+      wk[k] = (TA)(TABLE_IN_SMEM ? sw[o * kGridTaps + k] : __ldg(w + o * kGridTaps + k));
     }
     const TI *src = in + R1 * Sd * h;
     TO *dst = out + R1 * (o + Od * h);
@@ -261,7 +274,11 @@ static int launch_rows(const TI *in, TO *out, long long R1, long long Sd, long l
     const unsigned gx = (unsigned)std::min<long long>((nvec + tx - 1) / tx, 32);
     const long long want = std::max<long long>(1, (long long)sms * 8 / gx);
     const unsigned gy = (unsigned)std::min<long long>(std::min<long long>((rows + ty - 1) / ty, want), 65535LL);
-    grid_pass_rows_kernel<TI, TW, TA, TO, L, V><<<dim3(gx, gy), dim3(tx, ty), 0, st>>>(in, out, R1, Sd, Od, H, pos, w);
+    const size_t tab = (size_t)Od * kGridTaps * (sizeof(int) + sizeof(TW));
+    if (tab <= 40 * 1024)
+      grid_pass_rows_kernel<TI, TW, TA, TO, L, V, true><<<dim3(gx, gy), dim3(tx, ty), tab, st>>>(in, out, R1, Sd, Od, H, pos, w);
+    else
+      grid_pass_rows_kernel<TI, TW, TA, TO, L, V, false><<<dim3(gx, gy), dim3(tx, ty), 0, st>>>(in, out, R1, Sd, Od, H, pos, w);
     return 0;
   };
   if (aligned && R1 % VMAX == 0) return go(std::integral_constant<int, VMAX>{});
