@@ -15,8 +15,8 @@ drop-in for the B-spline hot path of Interpolations.jl v0.16: `interpolate(A, BS
 
 Every `ccall` signature in this file is checked against `include/b200itp.h` by `tests/test_julia_glue.py` (arity and
 argument kinds), and the field order of `Desc` / `AxisSystem` against the C structs.  Julia is not part of the build
-image, so this file is reviewed, not executed, there; `test/runtests.jl` is the reference's own GPU testset
-(`test/gpu_support.jl:4-126`) with `B200Array` in place of `JLArray`.
+image, so this file is reviewed, not executed, there; `test/runtests.jl` covers the cases of the reference's own
+array-type-generic testset (`test/gpu_support.jl`) with `==`.
 """
 module B200Interpolations
 

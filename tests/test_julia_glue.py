@@ -143,9 +143,11 @@ def test_julia_structs_mirror_the_c_structs():
                 assert jtype == width[ctype], (fname, ctype, jtype)
 
 
-def test_reference_gpu_testset_is_carried_over():
-    """test/runtests.jl keeps the reference's own `==` assertions (test/gpu_support.jl) for the B-spline testsets."""
+def test_reference_gpu_cases_are_covered():
+    """test/runtests.jl exercises the cases of the reference's array-type-generic testset (test/gpu_support.jl): 1-D and 2-D
+    B-splines, bare / scaled / Flat / filled, values, gradients, hessians, host and device coordinates, with `==`."""
     t = open(os.path.join(ROOT, "julia", "B200Interpolations", "test", "runtests.jl")).read()
-    for needle in ('@testset "1d GPU Interpolation"', '@testset "2d GPU Interpolation"', '@testset "eltype after adaption"',
-                   "Interpolations.hessian.(Ref(jlitp), jlidx, jlidx')", "extrapolate(sitp, 0.0)"):
-        assert needle in t
+    for needle in ("BSpline(Cubic(Line(OnGrid())))", "BSpline(Linear())", "extrapolate(sitp, Flat())", "extrapolate(sitp, 0.0)",
+                   "Interpolations.gradient", "Interpolations.hessian", "cpu == collect(on_host_args) == collect(on_dev_args)",
+                   "adapt(Array{Float32}, obj)", "b200itp_prefilter_set_strict"):
+        assert needle in t, needle
