@@ -688,11 +688,12 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
             # coefficients still on their way on another stream (parallel.broadcast_interpolant(..., overlap=True)): the
             # library waits for this event right before its first kernel that reads them
             L.b200itp_eval_set_coefs_event(C.c_void_p(ev.cuda_event))
-        if nq > 0:
+        try:
             # scratch_bytes is 0 when the ordered pipeline would not serve this call (small / L2-resident / wrapped)
-            nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq) if (
-                sorted_queries and (want_value != want_grad) and not debug) else 0
-            if nbytes:
+            nbytes = 0
+            if nq > 0 and sorted_queries and (want_value != want_grad) and not debug:
+                nbytes = L.b200itp_eval_sorted_scratch_bytes(C.byref(D), nq)
+            if nq > 0 and nbytes:
                 scratch = _scratch_tensor(int(nbytes), tdev)
                 if want_value:
                     rc = L.b200itp_eval_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(val), foob_ref, p(scratch),
@@ -702,10 +703,13 @@ def _broadcast_eval(itp, xs, want_value, want_grad, debug=False, sorted_queries=
                     rc = L.b200itp_gradient_sorted(dev, C.byref(D), p(coefs), ptrs, nq, p(grad), foob_ref,
                                                    p(scratch), nbytes, _stream_ptr(dev))
                     _lib.check(rc, "b200itp_gradient_sorted")
-            else:
+            elif nq > 0:
                 rc = L.b200itp_eval(dev, C.byref(D), p(coefs), ptrs, nq, p(val), p(grad), foob_ref, p(dbg_i),
                                     p(dbg_b), _stream_ptr(dev))
                 _lib.check(rc, "b200itp_eval")
+        finally:
+            if ev is not None:  # a call that failed before it consumed the event must not leave it for the next one
+                L.b200itp_eval_set_coefs_event(None)
     if foob.value >= 0:
         q = foob.value
         xq = tuple(float(c[q].item()) for c in coords)
