@@ -935,6 +935,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
   const unsigned it_lo = first_item(blockIdx.x);
   const unsigned it_hi = first_item(blockIdx.x + 1);
   int cur_brick = -1;
+  int walk_brick = -1;  // thread 0: brick of the previous item
   int o[3] = {0, 0, 0};
 #ifdef B200ITP_EVAL_TRACE
   const long long t_begin = clock64();
@@ -944,11 +945,20 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
   for (unsigned item = it_lo; item < it_hi; ++item) {
     __syncthreads();  // previous item fully consumed (cbeg/ccnt, tile)
     if (tid == 0) {
-      int lo = 0, hi = G.nbricks - 1;  // last brick with item_start <= item (skips empty bricks)
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+      // last brick with item_start <= item (skips empty bricks): a binary search (13 dependent global loads) for the
+      // CTA's first item only, a short forward walk afterwards (the CTA's items are consecutive)
+      int lo = walk_brick;
+      if (lo < 0) {
+        lo = 0;
+        int hi = G.nbricks - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+        }
+      } else {
+        while (lo + 1 < G.nbricks && item_start[lo + 1] <= item) ++lo;
       }
+      walk_brick = lo;
       sm.item_brick = lo;
       sm.item_part = (int)(item - item_start[lo]);
       sm.item_parts = (int)(item_start[lo + 1] - item_start[lo]);
