@@ -257,7 +257,8 @@ B200ITP_API int b200itp_eval(int dev, const b200itp_desc *d, const void *coefs, 
 B200ITP_API int b200itp_set_l2_fetch_granularity(int dev, int bytes);
 
 /* Pipelining hook for multi-GPU hosts: `cuda_event` (a cudaEvent_t, or NULL to clear) marks the moment the coefficient
- * array of the NEXT evaluation call (b200itp_eval / _eval_sorted / _gradient_sorted, any stream, taken once) becomes
+ * array of the NEXT evaluation call of the CALLING THREAD (b200itp_eval / _eval_sorted / _gradient_sorted / _hessian /
+ * _eval_grid, any stream, taken once) becomes
  * valid — e.g. the end of an NCCL broadcast or of the prefilter on another stream.  The call then waits for it only
  * right before its first kernel that reads coefficients: the ordered pipeline's count / scan / split kernels, which
  * only read the query coordinates, run while the coefficients are still on their way. */

@@ -59,8 +59,14 @@ int scratch_get(int dev, int slot, cudaStream_t stream, size_t bytes, void **out
 // ---- coefficient-ready event: lets a host replicate / produce the coefficient array on another stream (NCCL
 //      broadcast, prefilter) while the ordered pipeline already counts and splits the queries, which needs no
 //      coefficients; only the kernels that gather coefficients wait.
-static std::atomic<cudaEvent_t> g_coefs_event{nullptr};
-cudaEvent_t take_coefs_event() { return g_coefs_event.exchange(nullptr); }
+// (thread-local: the event belongs to the NEXT evaluation call of the thread that set it, so concurrent host threads
+//  driving different streams cannot take each other's event)
+static thread_local cudaEvent_t g_coefs_event = nullptr;
+cudaEvent_t take_coefs_event() {
+  cudaEvent_t e = g_coefs_event;
+  g_coefs_event = nullptr;
+  return e;
+}
 
 // ---- per-stage timing
 namespace {
@@ -150,7 +156,7 @@ extern "C" int b200itp_set_l2_fetch_granularity(int dev, int bytes) {
 }
 
 extern "C" int b200itp_eval_set_coefs_event(void *cuda_event) {
-  g_coefs_event.store((cudaEvent_t)cuda_event);
+  g_coefs_event = (cudaEvent_t)cuda_event;
   return 0;
 }
 
