@@ -221,6 +221,14 @@ B200ITP_API int b200itp_prefilter(int dev, void *coefs, int dtype, int ndims, co
  * and the caller's array is left untouched. */
 B200ITP_API int b200itp_prefilter_from(int dev, const void *src, void *coefs, int dtype, int ndims, const int64_t *size,
                            const int32_t *degree, const int32_t *bc, const int32_t *gridtype, void *stream);
+/* `prefilter(TW, TC, A, it)` for an array that DOES need padding: `src` is the unpadded sample array (src_size), `coefs`
+ * receives the padded (src_size + 2*pad per axis), prefiltered coefficient array.  `copy_with_padding`
+ * (prefiltering.jl:17-28) is folded into the first axis pass where possible (the contiguous-axis streaming kernel reads
+ * the samples and treats the line ends and the border lines as zeros), otherwise the two steps run one after the other;
+ * same results either way. */
+B200ITP_API int b200itp_prefilter_padded_from(int dev, const void *src, void *coefs, int dtype, int ndims,
+                                  const int64_t *src_size, const int32_t *pad, const int32_t *degree,
+                                  const int32_t *bc, const int32_t *gridtype, void *stream);
 /* Long lines of arrays with few lines are cut into segments (one warm-up and one look-ahead block each) to fill the
  * machine; a segmented pass agrees with the unsegmented one to round-off (<= 1 ulp in ~1e-5 of the elements) but not
  * bit for bit.  Callers that need results independent of how an array is split into slabs (the slab-sharded prefilter:

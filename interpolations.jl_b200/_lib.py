@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "b200itp_prefilter_axis": (C.c_int, [i32, vp, i32, i32, pi64, i32, C.POINTER(AxisSystem), vp]),
         "b200itp_prefilter": (C.c_int, [i32, vp, i32, i32, pi64, pi32, pi32, pi32, vp]),
         "b200itp_prefilter_from": (C.c_int, [i32, vp, vp, i32, i32, pi64, pi32, pi32, pi32, vp]),
+        "b200itp_prefilter_padded_from": (C.c_int, [i32, vp, vp, i32, i32, pi64, pi32, pi32, pi32, pi32, vp]),
         "b200itp_eval": (C.c_int, [i32, C.POINTER(Desc), vp, C.POINTER(vp), i64, vp, vp, pi64, vp, vp, vp]),
         "b200itp_eval_grid_scratch_bytes": (sz, [C.POINTER(Desc), pi64]),
         "b200itp_eval_grid": (C.c_int, [i32, C.POINTER(Desc), vp, C.POINTER(vp), pi64, vp, pi64, vp, sz, vp]),
@@ -135,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "b200itp_version", "b200itp_last_error", "b200itp_launch_count", "b200itp_profile_enable",
     "b200itp_profile_count", "b200itp_profile_get", "b200itp_malloc", "b200itp_free",
     "b200itp_memcpy_h2d", "b200itp_memcpy_d2h", "b200itp_sync", "b200itp_copy_with_padding",
-    "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_prefilter_from", "b200itp_eval", "b200itp_eval_grid", "b200itp_eval_grid_scratch_bytes", "b200itp_hessian",
+    "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_prefilter_from", "b200itp_prefilter_padded_from", "b200itp_eval", "b200itp_eval_grid", "b200itp_eval_grid_scratch_bytes", "b200itp_hessian",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted", "b200itp_gradient_sorted",
     "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_prefilter_set_segmentation",
     "b200itp_prefilter_set_strict", "b200itp_eval_sorted_ordered_calls", "b200itp_eval_grid_set_separable",

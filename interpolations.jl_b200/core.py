@@ -452,11 +452,14 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
     code = F32 if src.dtype == torch.float32 else F64
     with torch.cuda.device(dev):
         if any(pad):
+            # copy_with_padding + prefilter! in one library call: the padding is folded into the first axis pass
             coefs = torch.empty(int(np.prod(psize)), dtype=src.dtype, device=src.device)
-            rc = L.b200itp_copy_with_padding(dev, C.c_void_p(src.data_ptr()), C.c_void_p(coefs.data_ptr()), code, N,
-                                             (C.c_int64 * N)(*shape), (C.c_int32 * N)(*pad), _stream_ptr(dev))
-            _lib.check(rc, "b200itp_copy_with_padding")
-            prefilter_(coefs, psize, its, dev)
+            rc = L.b200itp_prefilter_padded_from(
+                dev, C.c_void_p(src.data_ptr()), C.c_void_p(coefs.data_ptr()), code, N, (C.c_int64 * N)(*shape),
+                (C.c_int32 * N)(*pad), (C.c_int32 * N)(*[i.degree.code for i in its]),
+                (C.c_int32 * N)(*[i.degree.bc.code for i in its]), (C.c_int32 * N)(*[i.degree.bc.gt.code for i in its]),
+                _stream_ptr(dev))
+            _lib.check(rc, "b200itp_prefilter_padded_from")
         elif aliased:
             coefs = torch.empty_like(src)
             prefilter_(coefs, psize, its, dev, src=src)  # first pass reads A, writes coefs

@@ -487,26 +487,43 @@ struct ContigCfg {
 #define PF_CONTIG_STAGES 2  // 2 input stages: 55 KB per CTA, 4 CTAs per SM (measured best of 2..4)
 #endif
   static constexpr int STAGES = PF_CONTIG_STAGES;
-  static constexpr size_t smem_bytes = (size_t)(STAGES + 1) * ITEMS * PITCH * 16 + (size_t)ITEMS * 16;
+  static constexpr size_t smem_bytes = (size_t)(STAGES + 1) * ITEMS * PITCH * 16 + (size_t)ITEMS * 24;
 };
 
 #ifndef PF_CONTIG_MINB
 #define PF_CONTIG_MINB 1
 #endif
-template <typename T, int VW>
+// copy_with_padding folded into the first (contiguous-axis) pass: the kernel reads the UNPADDED samples and produces the
+// padded, solved lines.  Line `l` of the padded array (all axes but the first flattened) is a border line (all zero: it
+// stays zero) or the padded image of one source line; inside a line, rows [p0, p0 + s0) come from the source, the ends
+// are zero on input (the solve writes the extrapolated coefficients there).
+struct PadInfo {
+  int ndims;
+  int p[4];         // padding per axis (0 or 1)
+  long long d[4];   // padded sizes
+  long long s[4];   // source sizes
+};
+
+template <typename T, int VW, bool PAD>
 __global__ void __launch_bounds__(Tune<T>::ITEMS, sizeof(T) == 4 ? PF_CONTIG_MINB : 1) prefilter_contig_kernel(const T *src, T *dst,
                                                                            const __grid_constant__ AxisPlan<T> p,
-                                                                           int64_t nitems, int nseg, int seglen) {
+                                                                           int64_t nitems, int nseg, int seglen,
+                                                                           const __grid_constant__ PadInfo pad) {
   using Cfg = ContigCfg<T>;
   constexpr int B = Cfg::B, ITEMS = Cfg::ITEMS, CH = Cfg::CH, K = Cfg::K, EPV = Cfg::EPV, VPI = Cfg::VPI;
   constexpr int PITCH = Cfg::PITCH, VPB = Cfg::VPB, S = Cfg::STAGES;
   constexpr int PPI = CH * (int)sizeof(T) / VW;  // pieces per item per chunk
   constexpr int EPP = VW / (int)sizeof(T);       // elements per piece
+  // loads of the fused-padding variant: the source rows are one element off the padded rows, so element-wise pieces
+  constexpr int VWL = PAD ? (int)sizeof(T) : VW;
+  constexpr int PPIL = CH * (int)sizeof(T) / VWL;
+  constexpr int EPPL = VWL / (int)sizeof(T);
   extern __shared__ uint4 smem_dyn[];
   uint4 *tin = smem_dyn;                          // S tiles
   uint4 *tout = smem_dyn + S * ITEMS * PITCH;     // 1 tile
   long long *s_base = reinterpret_cast<long long *>(tout + ITEMS * PITCH);  // element offset of row 1 of the item's line
   int *s_ci0 = reinterpret_cast<int *>(s_base + ITEMS);                      // global chunk index of the item's chunk 0
+  long long *s_sbase = reinterpret_cast<long long *>(s_ci0 + ITEMS);         // PAD: element offset of the SOURCE line (-1: border)
 
   const int tid = threadIdx.x;
   const int n = p.n;
@@ -517,14 +534,39 @@ __global__ void __launch_bounds__(Tune<T>::ITEMS, sizeof(T) == 4 ? PF_CONTIG_MIN
   const int seg = active ? (int)(item % nseg) : 0;
   s_base[tid] = active ? line * (int64_t)n : -1;
   s_ci0[tid] = seg * cps - 1;
+  long long my_sbase = -1;
+  if (PAD && active) {  // padded line index -> source line offset
+    long long rem = line, soff = 0, smul = pad.s[0];
+    bool inside = true;
+#pragma unroll
+    for (int d = 1; d < 4; ++d)
+      if (d < pad.ndims) {
+        const long long c = rem % pad.d[d];
+        rem /= pad.d[d];
+        const long long sc = c - pad.p[d];
+        inside = inside && sc >= 0 && sc < pad.s[d];
+        soff += sc * smul;
+        smul *= pad.s[d];
+      }
+    my_sbase = inside ? soff : -1;
+  }
+  if (PAD) s_sbase[tid] = my_sbase;
   __syncthreads();
 
   const int s = 1 + seg * seglen;
   const int e = min(n, s + seglen - 1);
   T c1 = T(0), cn = T(0);
   if (active && p.nv > 0 && (s <= p.Hz || e > n - p.Hz)) {
-    const T *in = src + line * (int64_t)n;
-    woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[r - 1]; }, c1, cn);
+    if constexpr (PAD) {
+      const T *in = src + (my_sbase >= 0 ? my_sbase : 0);
+      const int p0 = pad.p[0];
+      const long long s0 = pad.s[0];
+      woodbury_coeffs<T, Tune<T>::TP>(
+          p, [&](int r) { return (my_sbase >= 0 && r - 1 >= p0 && r - 1 < p0 + s0) ? in[r - 1 - p0] : T(0); }, c1, cn);
+    } else {
+      const T *in = src + line * (int64_t)n;
+      woodbury_coeffs<T, Tune<T>::TP>(p, [&](int r) { return in[r - 1]; }, c1, cn);
+    }
   }
   const int bs = (s - 1) / B, be = (e - 1) / B;
   const int bfirst = bs > 0 ? bs - 1 : bs;
@@ -534,15 +576,23 @@ __global__ void __launch_bounds__(Tune<T>::ITEMS, sizeof(T) == 4 ? PF_CONTIG_MIN
     if (lc < nlc) {
       unsigned char *tile = reinterpret_cast<unsigned char *>(tin + (lc % S) * ITEMS * PITCH);
 #pragma unroll
-      for (int it = 0; it < PPI; ++it) {
+      for (int it = 0; it < PPIL; ++it) {
         const int idx = it * ITEMS + tid;
-        const int im = idx / PPI, pc = idx % PPI;
-        const long long base = s_base[im];
+        const int im = idx / PPIL, pc = idx % PPIL;
         const int ci = s_ci0[im] + lc;
-        const int row = 1 + ci * CH + pc * EPP;
-        const bool valid = base >= 0 && ci >= 0 && row <= n;
-        const T *g = valid ? src + base + (row - 1) : src;
-        cp_async_zfill(tile + (size_t)im * PITCH * 16 + (size_t)pc * VW, g, VW, valid);
+        const int row = 1 + ci * CH + pc * EPPL;
+        if constexpr (PAD) {
+          const long long sb = s_sbase[im];
+          const long long col = (long long)row - 1 - pad.p[0];   // source row of this padded row
+          const bool valid = sb >= 0 && ci >= 0 && col >= 0 && col < pad.s[0];
+          const T *g = valid ? src + sb + col : src;
+          cp_async_zfill(tile + (size_t)im * PITCH * 16 + (size_t)pc * VWL, g, VWL, valid);
+        } else {
+          const long long base = s_base[im];
+          const bool valid = base >= 0 && ci >= 0 && row <= n;
+          const T *g = valid ? src + base + (row - 1) : src;
+          cp_async_zfill(tile + (size_t)im * PITCH * 16 + (size_t)pc * VW, g, VW, valid);
+        }
       }
     }
     cp_async_commit();
@@ -969,7 +1019,8 @@ static int make_job(int64_t n, int64_t ns, const T *dl, const T *d, const T *du,
 // one axis pass: src -> dst (dst may equal src when the pass is not segmented); *segmented tells the caller
 template <typename T>
 static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *size, int axis, const AxisJob<T> &job,
-                       int nseg, int seglen, cudaStream_t st) {
+                       int nseg, int seglen, cudaStream_t st, const PadInfo *pad = nullptr) {
+  // pad != nullptr: `src` is the UNPADDED sample array and this (contiguous-axis, streaming) pass pads while it loads
   const int64_t n = size[axis];
   int64_t R1 = 1, R2 = 1;
   for (int i = 0; i < axis; ++i) R1 *= size[i];
@@ -999,7 +1050,7 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
   if constexpr (sizeof(T) == 4) {
     // Float32 lines along the contiguous axis that fit a warp's registers: one warp per line, warp-scan recurrences
     const bool aligned = ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
-    if (nseg == 1 && aligned && warpline_shape_ok<T>(dev, axis, n, lines) && job.plan.P <= 128 && job.plan.Hz <= 128) {
+    if (!pad && nseg == 1 && aligned && warpline_shape_ok<T>(dev, axis, n, lines) && job.plan.P <= 128 && job.plan.Hz <= 128) {
       StageScope sc("prefilter_axis0_warpline", st);
       auto go = [&](auto kern) -> int {
         int per_sm = 0;
@@ -1033,20 +1084,29 @@ static int launch_axis(int dev, const T *src, T *dst, int ndims, const int64_t *
     const int64_t blocks = (nitems + Cfg::ITEMS - 1) / Cfg::ITEMS;
     if (blocks > 0x7fffffff) B200_FAIL(B200ITP_E_SIZE, "prefilter: grid too large");
     const size_t lb = (size_t)n * sizeof(T);
-    const uintptr_t al = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)lb;
+    // (fused padding loads the source element-wise: only the stores' alignment matters)
+    const uintptr_t al = (pad ? (uintptr_t)0 : (uintptr_t)src) | (uintptr_t)dst | (uintptr_t)lb;
     const int vw = (al % 16 == 0) ? 16 : ((al % 8 == 0) ? 8 : 4);
+    const PadInfo pi = pad ? *pad : PadInfo{};
     auto go = [&](auto kern) -> int {
       B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-      kern<<<(unsigned)blocks, Cfg::ITEMS, Cfg::smem_bytes, st>>>(src, dst, job.plan, nitems, nseg, seglen);
+      kern<<<(unsigned)blocks, Cfg::ITEMS, Cfg::smem_bytes, st>>>(src, dst, job.plan, nitems, nseg, seglen, pi);
       return 0;
     };
     int rc;
-    if (vw == 16)
-      rc = go(prefilter_contig_kernel<T, 16>);
+    if (pad) {
+      if (vw == 16)
+        rc = go(prefilter_contig_kernel<T, 16, true>);
+      else if (vw == 8)
+        rc = go(prefilter_contig_kernel<T, 8, true>);
+      else
+        rc = go(prefilter_contig_kernel<T, (sizeof(T) == 8 ? 8 : 4), true>);
+    } else if (vw == 16)
+      rc = go(prefilter_contig_kernel<T, 16, false>);
     else if (vw == 8)
-      rc = go(prefilter_contig_kernel<T, 8>);
+      rc = go(prefilter_contig_kernel<T, 8, false>);
     else
-      rc = go(prefilter_contig_kernel<T, (sizeof(T) == 8 ? 8 : 4)>);
+      rc = go(prefilter_contig_kernel<T, (sizeof(T) == 8 ? 8 : 4), false>);
     if (rc) return rc;
   } else if (use_bulk) {
     if constexpr (sizeof(T) == 4) {
@@ -1098,7 +1158,9 @@ int prefilter_strict_axis(int dev, T *coefs, int ndims, const int64_t *size, int
 // ping-pong between `coefs` and a scratch array; the result always ends in `coefs`.
 template <typename T>
 static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const AxisJob<T> *const *jobs,
-                      cudaStream_t st, const T *src0 = nullptr) {
+                      cudaStream_t st, const T *src0 = nullptr, const PadInfo *pad0 = nullptr) {
+  // pad0 (with src0): src0 is the UNPADDED sample array; the first pass — which the caller has checked to be the
+  // streaming contiguous-axis kernel — pads while it loads (copy_with_padding folded into it)
   // src0: the samples live in another array of the same layout (`interpolate` must not overwrite the caller's array):
   // the first pass reads them and writes `coefs`, which saves the copy the reference makes up front
   // (copy_with_padding, prefiltering.jl:17-28, also copies when nothing is padded)
@@ -1107,22 +1169,49 @@ static int run_passes(int dev, T *coefs, int ndims, const int64_t *size, const A
   if (total == 0) return 0;
   T *cur = src0 ? const_cast<T *>(src0) : coefs;
   T *other = nullptr;
+  auto need_other = [&]() -> int {
+    if (!other) {
+      void *tmp = nullptr;
+      int rc = scratch_get(dev, 0, st, sizeof(T) * (size_t)total, &tmp);
+      if (rc) return rc;
+      other = (T *)tmp;
+    }
+    return 0;
+  };
+  // The first pass of the src0 form may write either array: pick the one that makes the chain of segmented
+  // (out-of-place) passes END in `coefs`, so that no copy back is needed.
+  bool first_to_other = false;
+  if (src0) {
+    int toggles = 0;
+    bool first = true;
+    for (int ax = 0; ax < ndims; ++ax) {
+      if (!jobs[ax]) continue;
+      int nseg, seglen;
+      choose_segments<T>(dev, total / size[ax], size[ax], jobs[ax]->fast_ok, ax, nseg, seglen);
+      if (!first && nseg > 1) ++toggles;
+      first = false;
+    }
+    first_to_other = (toggles & 1) != 0;
+  }
   for (int ax = 0; ax < ndims; ++ax) {
     if (!jobs[ax]) continue;
     const int64_t n = size[ax];
     int nseg, seglen;
     choose_segments<T>(dev, total / n, n, jobs[ax]->fast_ok, ax, nseg, seglen);
-    T *dst = cur == src0 ? coefs : cur;
-    if (nseg > 1 && cur != src0) {
-      if (!other) {
-        void *tmp = nullptr;
-        int rc = scratch_get(dev, 0, st, sizeof(T) * (size_t)total, &tmp);
+    T *dst = cur;
+    if (cur == src0) {
+      dst = coefs;
+      if (first_to_other) {
+        int rc = need_other();
         if (rc) return rc;
-        other = (T *)tmp;
+        dst = other;
       }
+    } else if (nseg > 1) {
+      int rc = need_other();
+      if (rc) return rc;
       dst = cur == coefs ? other : coefs;
     }
-    int rc = launch_axis<T>(dev, cur, dst, ndims, size, ax, *jobs[ax], nseg, seglen, st);
+    int rc = launch_axis<T>(dev, cur, dst, ndims, size, ax, *jobs[ax], nseg, seglen, st, cur == src0 ? pad0 : nullptr);
     if (rc) return rc;
     cur = dst;
   }
@@ -1211,8 +1300,14 @@ static int cached_job(int64_t n, int degree, int bc, int grid, std::shared_ptr<c
 
 template <typename T>
 static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *size, const int32_t *degree,
-                               const int32_t *bc, const int32_t *grid, cudaStream_t st, const void *src0 = nullptr) {
+                               const int32_t *bc, const int32_t *grid, cudaStream_t st, const void *src0 = nullptr,
+                               const PadInfo *pad = nullptr, bool *pad_fused = nullptr) {
+  // pad != nullptr: src0 is the UNPADDED sample array (sizes pad->s), `size` the padded sizes.  *pad_fused tells the
+  // caller whether the padding was folded into the first pass; if not (strict mode, first filtered axis not the
+  // contiguous one, a system whose factors do not settle) the caller pads first and calls again without `pad`.
+  if (pad_fused) *pad_fused = false;
   if (g_prefilter_strict.load(std::memory_order_relaxed)) {
+    if (pad) return 0;
     if (src0) {
       int64_t total = 1;
       for (int i = 0; i < ndims; ++i) total *= size[i];
@@ -1250,7 +1345,14 @@ static int prefilter_all_typed(int dev, void *coefs, int ndims, const int64_t *s
                 (long long)size[ax]);
     if (rc) return rc;
   }
-  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st, (const T *)src0);
+  if (pad) {
+    // Fusable: the first pass is the streaming contiguous-axis kernel.  Worth it for 8-byte elements only: the source
+    // rows sit one element off the padded rows, so the fused loads are element-wise cp.async — measured (8194^2):
+    // Float64 0.39 ms fused against 0.20 + 0.30 ms for copy + pass, Float32 (4-byte copies) 0.30 against 0.13 + 0.17.
+    if (!(jobs[0] && jobs[0]->fast_ok) || sizeof(T) != 8) return 0;  // *pad_fused stays false: the caller pads first
+    *pad_fused = true;
+  }
+  return run_passes<T>(dev, (T *)coefs, ndims, size, jobs, st, (const T *)src0, pad);
 }
 
 }  // namespace b200itp
@@ -1326,6 +1428,47 @@ extern "C" int b200itp_prefilter_from(int dev, const void *src, void *coefs, int
   if (dtype == B200ITP_F32) return prefilter_all_typed<float>(dev, coefs, ndims, size, degree, bc, gridtype, st, src);
   if (dtype == B200ITP_F64) return prefilter_all_typed<double>(dev, coefs, ndims, size, degree, bc, gridtype, st, src);
   B200_FAIL(B200ITP_E_DTYPE, "prefilter_from: dtype must be F32 or F64");
+}
+
+extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
+                                         const int64_t *src_size, const int32_t *pad, void *stream);
+
+extern "C" int b200itp_prefilter_padded_from(int dev, const void *src, void *coefs, int dtype, int ndims,
+                                             const int64_t *src_size, const int32_t *pad, const int32_t *degree,
+                                             const int32_t *bc, const int32_t *gridtype, void *stream) {
+  if (!src || !coefs || !src_size || !pad || !degree || !bc || !gridtype)
+    B200_FAIL(B200ITP_E_BADARG, "prefilter_padded_from: null pointer");
+  if (ndims < 1 || ndims > B200ITP_MAX_DIMS) B200_FAIL(B200ITP_E_BADARG, "prefilter_padded_from: ndims must be 1..4");
+  if (dtype != B200ITP_F32 && dtype != B200ITP_F64) B200_FAIL(B200ITP_E_DTYPE, "prefilter_padded_from: dtype must be F32 or F64");
+  PadInfo pi{};
+  int64_t psize[B200ITP_MAX_DIMS] = {1, 1, 1, 1};
+  bool any = false;
+  pi.ndims = ndims;
+  for (int i = 0; i < 4; ++i) {
+    pi.p[i] = 0;
+    pi.d[i] = 1;
+    pi.s[i] = 1;
+  }
+  for (int i = 0; i < ndims; ++i) {
+    if (pad[i] < 0 || pad[i] > 1 || src_size[i] < 1) B200_FAIL(B200ITP_E_BADARG, "prefilter_padded_from: bad size or padding");
+    pi.p[i] = pad[i];
+    pi.s[i] = src_size[i];
+    pi.d[i] = psize[i] = src_size[i] + 2 * pad[i];
+    any = any || pad[i];
+  }
+  if (!any) return b200itp_prefilter_from(dev, src, coefs, dtype, ndims, psize, degree, bc, gridtype, stream);
+  DeviceGuard g(dev);
+  if (!g.ok) B200_FAIL(-(int)cudaErrorInvalidDevice, "prefilter_padded_from: cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool fused = false;
+  int rc = dtype == B200ITP_F32
+               ? prefilter_all_typed<float>(dev, coefs, ndims, psize, degree, bc, gridtype, st, src, &pi, &fused)
+               : prefilter_all_typed<double>(dev, coefs, ndims, psize, degree, bc, gridtype, st, src, &pi, &fused);
+  if (rc || fused) return rc;
+  // not fusable: the reference's two steps
+  rc = b200itp_copy_with_padding(dev, src, coefs, dtype, ndims, src_size, pad, stream);
+  if (rc) return rc;
+  return b200itp_prefilter(dev, coefs, dtype, ndims, psize, degree, bc, gridtype, stream);
 }
 
 extern "C" int b200itp_copy_with_padding(int dev, const void *src, void *dst, int dtype, int ndims,
