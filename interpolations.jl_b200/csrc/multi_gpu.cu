@@ -153,6 +153,62 @@ int box_copy(int dev, const void *src, void *dst, int es, int64_t nx, int64_t ny
   return 0;
 }
 
+// All peers' blocks in ONE launch per device (the host thread drives every device: a launch per peer made the
+// 8-GPU prefilter launch-bound).  y-ranges y0[h] .. y0[h+1] tile [0, ny); block h of the peer-major / rank-major buffer
+// starts at element off[h] and is the dense box (nx, yl_h, nzb).
+constexpr int kMaxPeers = 16;
+struct PeerSplit {
+  int n;
+  long long y0[kMaxPeers + 1];
+  long long off[kMaxPeers + 1];
+};
+
+// PACK:   slab (nx, ny, nzb) -> peer-major buffer;   UNPACK: rank-major buffer -> array (nx, ny, nzb)
+template <typename V, bool PACK>
+__global__ void __launch_bounds__(256) slab_pack_kernel(const V *__restrict__ src, V *__restrict__ dst, long long nxv,
+                                                        long long ny, long long nzb, const PeerSplit ps) {
+  const long long rows = ny * nzb;
+  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
+    const long long y = row % ny, z = row / ny;
+    int h = 0;
+    while (h + 1 < ps.n && y >= ps.y0[h + 1]) ++h;
+    const long long yl = ps.y0[h + 1] - ps.y0[h];
+    const long long dense = ps.off[h] + nxv * ((y - ps.y0[h]) + yl * z);  // position in the blocked buffer
+    const long long full = nxv * (y + ny * z);                             // position in the (x, y, z) array
+    const V *s = src + (PACK ? full : dense);
+    V *d = dst + (PACK ? dense : full);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxv; i += (long long)gridDim.x * blockDim.x)
+      d[i] = s[i];
+  }
+}
+
+template <bool PACK>
+int slab_pack(int dev, const void *src, void *dst, int es, int64_t nx, int64_t ny, int64_t nzb, const int64_t *y0, int G,
+              cudaStream_t st) {
+  if (nx == 0 || ny == 0 || nzb == 0) return 0;
+  const bool v16 = ((nx * es) % 16 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+  const long long k = v16 ? 16 / es : 1;
+  PeerSplit ps;
+  ps.n = G;
+  long long off = 0;
+  for (int h = 0; h <= G; ++h) {
+    ps.y0[h] = y0[h];
+    ps.off[h] = off;
+    if (h < G) off += (nx / k) * (y0[h + 1] - y0[h]) * nzb;
+  }
+  const long long nxv = nx / k, rows = ny * nzb;
+  dim3 grid((unsigned)std::min<long long>((nxv + 255) / 256, 8), (unsigned)std::min<long long>(rows, (long long)sm_count(dev) * 16));
+  if (v16)
+    slab_pack_kernel<float4, PACK><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, nxv, ny, nzb, ps);
+  else if (es == 4)
+    slab_pack_kernel<float, PACK><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, nxv, ny, nzb, ps);
+  else
+    slab_pack_kernel<double, PACK><<<grid, 256, 0, st>>>((const double *)src, (double *)dst, nxv, ny, nzb, ps);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 }  // namespace b200itp
 
@@ -250,10 +306,13 @@ extern "C" int b200itp_prefilter_sharded(b200itp_comm *c, const void *const *sam
   const ncclDataType_t nt = dtype == B200ITP_F32 ? ncclFloat : ncclDouble;
   const int32_t lin = B200ITP_LINEAR;  // "skip this axis" (prefiltering.jl:30)
   const int32_t deg_xy[3] = {degree[0], degree[1], lin}, deg_z[3] = {lin, lin, degree[2]};
-  std::vector<int64_t> z0(G), z1(G), y0(G), y1(G);
+  if (G > kMaxPeers) B200_FAIL(B200ITP_E_UNSUPPORTED, "prefilter_sharded: at most %d devices", kMaxPeers);
+  std::vector<int64_t> z0(G), z1(G), y0(G), y1(G), ybound(G + 1);
   for (int g = 0; g < G; ++g) {
     split(nz, G, g, z0[g], z1[g]);
     split(ny, G, g, y0[g], y1[g]);
+    ybound[g] = y0[g];
+    ybound[g + 1] = y1[g];
     if (!samples_slab[g] || !coefs_full[g]) B200_FAIL(B200ITP_E_BADARG, "prefilter_sharded: null buffer for device %d", c->dev[g]);
   }
   const int prev_seg = b200itp_prefilter_set_segmentation(0);  // same bits whatever the slab sizes
@@ -283,14 +342,9 @@ extern "C" int b200itp_prefilter_sharded(b200itp_comm *c, const void *const *sam
     rc = b200itp_prefilter_from(c->dev[g], samples_slab[g], c->work[g].p, dtype, 3, ssz, deg_xy, bc, gridtype, c->stream[g]);
     if (rc) return fail(rc);
     if (G == 1) continue;
-    size_t off = 0;
-    for (int h = 0; h < G; ++h) {  // block h of the send buffer: box (nx, yl_h, nzl), dense
-      const int64_t yl = y1[h] - y0[h];
-      rc = box_copy(c->dev[g], (const char *)c->work[g].p + (size_t)nx * y0[h] * es, (char *)c->send[g].p + off, es, nx, yl, nzl,
-                    nx, nx * ny, nx, nx * yl, c->stream[g]);
-      if (rc) return fail(rc);
-      off += (size_t)nx * yl * nzl * es;
-    }
+    // the slab in peer-major order (block h = the box (nx, yl_h, nzl), dense): one launch
+    rc = slab_pack<true>(c->dev[g], c->work[g].p, c->send[g].p, es, nx, ny, nzl, ybound.data(), G, c->stream[g]);
+    if (rc) return fail(rc);
   }
   // ---- one all-to-all: z-slabs -> y-slabs.  Device g receives from h the box (nx, yl_g, nzl_h), which is the z-range of
   //      h inside g's y-slab (nx, yl_g, nz): blocks land in rank order == z order, the receive buffer IS the y-slab.
@@ -346,14 +400,10 @@ extern "C" int b200itp_prefilter_sharded(b200itp_comm *c, const void *const *sam
       }
     }
     B200_NCCL_OK(g_nccl.GroupEnd());
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G; ++g) {  // rank-major y-slabs -> the (x, y, z) array: one launch per device
       DeviceGuard dg(c->dev[g]);
-      for (int h = 0; h < G; ++h) {
-        const int64_t yl = y1[h] - y0[h];
-        rc = box_copy(c->dev[g], (const char *)c->gath[g].p + goff[h], (char *)coefs_full[g] + (size_t)nx * y0[h] * es, es, nx, yl, nz,
-                      nx, nx * yl, nx, nx * ny, c->stream[g]);
-        if (rc) return rc;
-      }
+      rc = slab_pack<false>(c->dev[g], c->gath[g].p, coefs_full[g], es, nx, ny, nz, ybound.data(), G, c->stream[g]);
+      if (rc) return rc;
     }
   } else {
     DeviceGuard dg(c->dev[0]);
