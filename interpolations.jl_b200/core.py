@@ -760,7 +760,7 @@ def evaluate_sorted(itp, *xs):
     return _broadcast_eval(itp, xs, want_value=True, want_grad=False, sorted_queries=True)[0]
 
 
-def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
+def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True, copy_streams=1):
     """`itp.(xs...)` for coordinate arrays that live in (pinned) HOST memory: the queries are cut into chunks and the
     host->device copy of chunk i+1, the evaluation of chunk i and the device->host copy of chunk i-1 run on three
     CUDA streams, so the call is bound by the PCIe transfer of the coordinates instead of the sum of the three.
@@ -789,6 +789,10 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
         main = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         s_in.wait_stream(main)
+        # optionally one upload stream per coordinate array (copy_streams > 1): concurrent copies on several copy engines
+        s_ins = [s_in] + [torch.cuda.Stream() for _ in range(max(0, min(int(copy_streams), N) - 1))]
+        for s_extra in s_ins[1:]:
+            s_extra.wait_stream(main)
         nbuf = min(3, nchunks)
         bufs = [[torch.empty(min(chunk, nq), dtype=dt, device=dev) for _ in range(N)] for _ in range(nbuf)]
         free_ev = [None] * nbuf   # buffer may be refilled once its evaluation has finished
@@ -799,11 +803,19 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
         def upload(c):
             lo, hi = c * chunk, min(nq, (c + 1) * chunk)
             b = c % nbuf
+            for k, s_k in enumerate(s_ins[1:], start=1):  # extra upload streams: their arrays first
+                with torch.cuda.stream(s_k):
+                    if free_ev[b] is not None:
+                        s_k.wait_event(free_ev[b])
+                    for d in range(k, N, len(s_ins)):
+                        bufs[b][d][: hi - lo].copy_(host_xs[d][lo:hi], non_blocking=True)
             with torch.cuda.stream(s_in):
                 if free_ev[b] is not None:
                     s_in.wait_event(free_ev[b])
-                for d in range(N):
+                for d in range(0, N, len(s_ins)):
                     bufs[b][d][: hi - lo].copy_(host_xs[d][lo:hi], non_blocking=True)
+                for s_k in s_ins[1:]:
+                    s_in.wait_stream(s_k)
                 ready[b] = torch.cuda.Event()
                 ready[b].record(s_in)
 
@@ -827,7 +839,8 @@ def evaluate_from_host(itp, *host_xs, out=None, chunk=1 << 26, ordered=True):
                 done_ev[b] = torch.cuda.Event()
                 done_ev[b].record(s_out)
         main.wait_stream(s_out)
-        main.wait_stream(s_in)
+        for s_k in s_ins:
+            main.wait_stream(s_k)
         # `out` lives in host memory: the caller may read it as soon as this returns, so the last device->host copies
         # must have LANDED (stream ordering alone does not block the CPU)
         s_out.synchronize()
