@@ -371,9 +371,16 @@ int fill_eval_params_public(const b200itp_desc *D, const void *coefs, const void
   for (int d = 1; d < D->ndims; ++d)
     if (D->degree[d] != deg) deg = 0;
   *uniform_degree = deg;
-  *plain_f32 = c.homogeneous && D->etp_kind == B200ITP_ETP_NONE && !D->has_scale && D->coef_dtype == B200ITP_F32 &&
-               D->coord_dtype == B200ITP_F32 && !c.w_wide && !(P.xshift[0] | P.xshift[1] | P.xshift[2] | P.xshift[3] |
-                                                              P.clamp_taps[0] | P.clamp_taps[1] | P.clamp_taps[2] | P.clamp_taps[3]);
+  // Float32 throughout: coefficients, coordinates, and — for scaled / extrapolated objects — every stage of the
+  // coordinate chain (no Float64 bound or range widens it: c.w_wide covers the extrapolation and coordlookup stages, which
+  // only ever widen).  Line extrapolation (value + gradient * dx) and fill values stay with the direct kernel.
+  bool etp_ok = D->etp_kind == B200ITP_ETP_NONE;
+  if (D->etp_kind == B200ITP_ETP_FLAGS) {
+    etp_ok = !P.any_line;
+  }
+  *plain_f32 = c.homogeneous && etp_ok && D->coef_dtype == B200ITP_F32 && D->coord_dtype == B200ITP_F32 && !c.w_wide &&
+               !(P.xshift[0] | P.xshift[1] | P.xshift[2] | P.xshift[3] | P.clamp_taps[0] | P.clamp_taps[1] |
+                 P.clamp_taps[2] | P.clamp_taps[3]);
   return 0;
 }
 }  // namespace b200itp

@@ -21,8 +21,10 @@
 // The per-query arithmetic is the device code of the direct kernel (axis_setup + the reference's reduction
 // order, -fmad=false), so both paths return bit-identical values.
 //
-// Scope: BSplineInterpolation without wrappers, Float32 coefficients and coordinates, 2-D / 3-D, uniform
-// Quadratic or Cubic degree, at least 2^20 queries.  Everything else is forwarded to the direct kernel.
+// Scope: Float32 coefficients and coordinates, 2-D / 3-D, uniform Quadratic or Cubic degree, at least 2^20 queries; bare
+// BSplineInterpolation (values and gradients), and — values only — scale / extrapolate wrappers whose coordinate chain
+// stays Float32 (Int or Float32 ranges, OnGrid bounds, flags Throw / Flat / Periodic / Reflect): their per-axis maps are
+// applied when the records are made.  Everything else is forwarded to the direct kernel.
 #include "eval.cuh"
 
 #include <algorithm>
@@ -107,6 +109,7 @@ struct OrdGeom {
   int ngroups;   // groups of kGroupBricks bricks (split 1 bins)
   int nsuper;    // super-groups of kMaxBins groups: > 1 adds a split level in front (arrays beyond 8192 bricks)
   int nfinal;    // nbricks * kClasses
+  int wrapped;   // scale / extrapolation maps are applied when the records are made (check_query)
 };
 
 // First tap index of one axis: the `first` of axis_setup (eval.cuh; cubic.jl:40-57, quadratic.jl:39-43,
@@ -148,10 +151,34 @@ __device__ __forceinline__ void locate(const EvalParams &P, const OrdGeom &G, co
 // A query outside the bounds (or NaN) is a BoundsError (indexing.jl:6): it travels through the pipeline as
 // an all-NaN record (brick 0, class 0, NaN result) so that every q appears exactly once in the unsort.
 template <int N>
-__device__ __forceinline__ void check_query(const OrdGeom &G, float (&x)[3], bool &valid) {
+__device__ __forceinline__ void check_query(const EvalParams &P, const OrdGeom &G, float (&x)[3], bool &valid) {
   valid = true;
+  if (G.wrapped) {
+    // extrapolate(scale(itp, ranges...), flags) whose whole coordinate chain stays Float32 (Int / Float32 ranges, OnGrid
+    // bounds, no Line): the per-axis maps of the direct kernel (eval.cuh: etp_inbounds, coordlookup + clamp;
+    // extrapolation.jl:106-163, scaling.jl:102-115) are applied HERE, once, and the record carries the coordinate in
+    // the B-spline's own index space — from then on the pipeline is the bare interpolant's
 #pragma unroll
-  for (int d = 0; d < N; ++d) valid = valid && (G.lbf[d] <= x[d]) && (x[d] <= G.ubf[d]);  // false for NaN
+    for (int d = 0; d < N; ++d) {
+      float xs = x[d];
+      if (P.etp_kind == B200ITP_ETP_FLAGS) {
+        float y;
+        if (etp_inbounds<float>(P, d, x[d], y)) valid = false;
+        xs = y;
+      } else {
+        valid = valid && (G.lbf[d] <= x[d]) && (x[d] <= G.ubf[d]);
+      }
+      if (P.has_scale) {
+        xs = (xs - (float)P.rfirst[d]) / (float)P.rstep[d] + 1.f;
+        const float lo = (float)P.inner_lb[d], hi = (float)P.inner_ub[d];
+        xs = xs > hi ? hi : (xs < lo ? lo : xs);
+      }
+      x[d] = xs;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < N; ++d) valid = valid && (G.lbf[d] <= x[d]) && (x[d] <= G.ubf[d]);  // false for NaN
+  }
   if (!valid) {
     const float nn = __int_as_float(0x7fc00000);
     x[0] = nn;
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
       const long long q = q0 + u * stride;
       if (q < P.nq) {
         bool valid;
-        check_query<N>(G, x[u], valid);
+        check_query<N>(P, G, x[u], valid);
         if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
         int brick, cls;
         locate<N, DEG>(P, G, x[u], brick, cls);
@@ -627,7 +654,7 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
       if (FULL || q < nq) {
         float x[3] = {nx[j][0], nx[j][1], nx[j][2]};
         bool valid;
-        check_query<N>(G, x, valid);
+        check_query<N>(P, G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
         key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
@@ -1182,7 +1209,7 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
   for (int d = 0; d < N; ++d) {
     // first-tap indices: periodic cubic on OnCell grids -1..n-1 (floor(x) - 1 with x in [0.5, n + 0.5]), other periodic
     // axes 0..n-1, otherwise 0..size-1-DEG
-    G.fmin[d] = (P.periodic[d] && DEG == B200ITP_CUBIC && P.lb[d] < 1.0) ? -1 : 0;  // OnGrid: x >= 1, first >= 0
+    G.fmin[d] = (P.periodic[d] && DEG == B200ITP_CUBIC && P.inner_lb[d] < 1.0) ? -1 : 0;  // OnGrid: x >= 1, first >= 0
     G.cells[d] = P.periodic[d] ? P.n[d] - G.fmin[d] : (int)D->size[d] - DEG;
     if (G.cells[d] < 1) return false;
     G.nb[d] = (G.cells[d] + bdim[d] - 1) / bdim[d];
@@ -1196,6 +1223,7 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
   G.ngroups = (int)((bricks + kGroupBricks - 1) / kGroupBricks);
   G.nsuper = G.ngroups <= kMaxBins ? 1 : (G.ngroups + kMaxBins - 1) / kMaxBins;
   G.nfinal = (int)bricks * kClasses;
+  G.wrapped = (P.has_scale || P.etp_kind == B200ITP_ETP_FLAGS) ? 1 : 0;
   return true;
 }
 
@@ -1338,7 +1366,16 @@ extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
 static bool ordered_candidate(const b200itp_desc *d, int64_t nq) {
   if (d->ndims != 2 && d->ndims != 3) return false;
   if (d->coef_dtype != B200ITP_F32 || d->coord_dtype != B200ITP_F32) return false;
-  if (d->has_scale || d->etp_kind != B200ITP_ETP_NONE) return false;
+  // wrappers: only chains that stay Float32 (no Float64 bound or range), no Line extrapolation, no fill value
+  if (d->etp_kind == B200ITP_ETP_FILL) return false;
+  for (int i = 0; i < d->ndims; ++i) {
+    if (d->has_scale && (d->range_tag[i] == B200ITP_TAG_F64 || d->outer_tag[i] == B200ITP_TAG_F64 || d->inner_tag[i] == B200ITP_TAG_F64))
+      return false;
+    if (d->etp_kind == B200ITP_ETP_FLAGS) {
+      if (d->etp_lo[i] == B200ITP_BC_LINE || d->etp_hi[i] == B200ITP_BC_LINE) return false;
+      if ((d->has_scale ? d->outer_tag[i] : d->inner_tag[i]) == B200ITP_TAG_F64) return false;
+    }
+  }
   const int deg = d->degree[0];
   if (deg != B200ITP_CUBIC && deg != B200ITP_QUADRATIC) return false;
   long long coef_bytes = 4;
@@ -1391,6 +1428,9 @@ static int eval_sorted_common(int dev, const b200itp_desc *d, const void *coefs,
   for (int i = 0; i < d->ndims && i < B200ITP_MAX_DIMS; ++i) coef_bytes *= d->size[i];
   // (3-D: the direct tricubic kernel stays at 2-4 Gevals/s even from the L2 — 128^3: 4.0 vs 16.3, 256^3: 3.1 vs 20.5 — so
   // every 3-D array takes the ordered path; the size condition applies to 2-D arrays only)
+  // (gradients of wrapped objects — rescale_gradient, the in-bounds / Flat rules of extrapolation.jl:71-82 — stay with the
+  //  direct kernel; values of all-Float32 scaled / extrapolated objects take the ordered pipeline)
+  if (grad && (d->has_scale || d->etp_kind != B200ITP_ETP_NONE)) plain = false;
   if (plain && nq >= g_sorted_min_queries && (d->ndims == 3 || coef_bytes >= g_sorted_min_coef_bytes) &&
       (deg == B200ITP_CUBIC || deg == B200ITP_QUADRATIC) && (d->ndims == 2 || d->ndims == 3)) {
     B200_CUDA_OK(cudaMemsetAsync(flag, 0xFF, sizeof(unsigned long long), st));

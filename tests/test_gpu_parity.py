@@ -1197,3 +1197,67 @@ def test_coefficients_ready_event_orders_the_gather_after_a_side_stream(pkg):
             assert torch.equal(out, ref), ordered
         finally:
             L.b200itp_eval_sorted_set_min_queries(prev)
+
+
+def test_ordered_pipeline_serves_float32_wrapped_interpolants(pkg, orc):
+    """scale / extrapolate objects whose coordinate chain stays Float32 (Int or Float32 ranges, OnGrid bounds, flags
+    Throw / Flat / Periodic / Reflect): the ordered pipeline applies the per-axis maps (extrapolation.jl:106-163,
+    scaling.jl:102-115) when it builds the records and must return the direct kernel's bits — and the oracle's; chains
+    that widen to Float64 (Float64 ranges, OnCell bounds), Line extrapolation, fill values and gradients of wrapped
+    objects are served by the direct kernel."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(17)
+    prev = L.b200itp_eval_sorted_min_queries()
+    L.b200itp_eval_sorted_set_min_queries(1)
+    try:
+        for shape, it in (((70, 66, 40), m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))),
+                          ((300, 260), m.BSpline(m.Quadratic(m.Flat(m.OnGrid())))),
+                          ((40, 36, 50), m.BSpline(m.Cubic(m.Line(m.OnGrid()))))):
+            N = len(shape)
+            A = rng.standard_normal(shape).astype(np.float32)
+            itp = m.interpolate(A, it)
+            f32r = [m.jrange(np.float32(-1), np.float32(2), length=n, dtype=np.float32) for n in shape]
+            intr = [m.jrange(3, 3 + n - 1) for n in shape]
+            served = [m.scale(itp, *f32r), m.scale(itp, *intr), m.extrapolate(itp, m.Flat()), m.extrapolate(itp, m.Periodic()),
+                      m.extrapolate(m.scale(itp, *f32r), m.Reflect()), m.extrapolate(m.scale(itp, *intr), m.Throw()),
+                      m.extrapolate(m.scale(itp, *f32r), tuple([m.Flat()] + [m.Periodic()] * (N - 1)))]
+            f64r = [m.jrange(-1.0, 2.0, length=n) for n in shape]
+            not_served = [m.scale(itp, *f64r), m.extrapolate(itp, m.Line()), m.extrapolate(m.scale(itp, *f32r), 0.0)]
+            nq = 200_000
+            for obj in served + not_served:
+                ext = isinstance(obj, m.Extrapolation) and not any(
+                    (f.code if not isinstance(f, tuple) else 0) == 0 for f in obj.flags)
+                coords = []
+                for (lb, ub) in obj.bounds():
+                    lb, ub = float(lb), float(ub)
+                    pad = 0.5 * (ub - lb) if ext else 0.0
+                    x = rng.uniform(lb - pad, ub + pad, nq).astype(np.float32)
+                    x[:3] = [lb, ub, (lb + ub) / 2]
+                    if not ext:
+                        x = np.clip(x, np.float32(lb), np.float32(ub))
+                    coords.append(x)
+                a = m.evaluate_direct(obj, *coords).cpu().numpy()
+                n0 = L.b200itp_eval_sorted_ordered_calls()
+                b = obj(*coords).cpu().numpy()
+                took = L.b200itp_eval_sorted_ordered_calls() - n0
+                assert took == (1 if obj in served else 0), (shape, repr(obj)[:80], took)
+                assert np.array_equal(a, b, equal_nan=True), (shape, repr(obj)[:80])
+                k = 3000
+                host = orc.with_coefs(obj, obj.coefficients().cpu().numpy())
+                ov = orc.evaluate(host, *[c[:k] for c in coords])[0]
+                assert np.array_equal(b[:k], ov.astype(b.dtype)), (shape, repr(obj)[:80])
+                if obj in served:  # gradients of wrapped objects: direct kernel, same answers as before
+                    n1 = L.b200itp_eval_sorted_ordered_calls()
+                    g = m.gradient(obj, *[c[:k] for c in coords])
+                    assert L.b200itp_eval_sorted_ordered_calls() == n1
+                    assert torch.equal(g, m.gradient_direct(obj, *[c[:k] for c in coords]))
+            # BoundsError protocol through the ordered pipeline for a scaled object
+            sobj = m.scale(itp, *f32r)
+            bad = [np.full(5000, 0.5, np.float32) for _ in range(N)]
+            bad[0][1234] = np.float32(2.5)
+            with pytest.raises(m.BoundsError):
+                sobj(*bad)
+    finally:
+        L.b200itp_eval_sorted_set_min_queries(prev)
