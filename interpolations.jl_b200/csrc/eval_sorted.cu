@@ -57,7 +57,11 @@ struct TileCfg {
   static constexpr int TX = Bk::BX + DEG;
   static constexpr int TY = Bk::BY + DEG;
   static constexpr int TZ = N == 3 ? Bk::BZ + DEG : 1;
-  static constexpr int PX = TX | 1;  // odd row pitch
+  // row pitch: a multiple of 4 floats with room for a shift of up to 3, so that the tile columns whose global addresses
+  // are 16-byte aligned sit on 16-byte aligned shared-memory addresses (OrdGeom::tshift) and rows are staged with
+  // 16-byte asynchronous copies.  Any pitch keeps the gathers conflict-free: lane c's 64 taps sit at fixed offsets from
+  // a base whose bank is c.
+  static constexpr int PX = (TX + 3 + 3) / 4 * 4;
   static constexpr int FLOATS = PX * TY * TZ;
   static constexpr int MAXT = TX > TY ? (TX > TZ ? TX : TZ) : (TY > TZ ? TY : TZ);
 };
@@ -93,7 +97,18 @@ struct Uns {
 //  arithmetic all land at 11.7-12.2 ms per 1e9 tricubic queries — 64 LDS at half issue rate + 263 other instructions
 //  per record put the floor at ~3.1 SM cycles per record, the kernel runs at 3.3)
 constexpr int kEvalThreads = ORD_EVAL_THREADS;
+#ifndef ORD_TILE_PREFETCH
+#define ORD_TILE_PREFETCH 0  // measured: no gain (ord_eval 2.13 -> 2.18 ms at 1.25e8 queries), see DESIGN 4.3
+#endif
 constexpr int kRB = 8;              // rows (records per class) a warp stages and evaluates at a time
+#ifndef ORD_TAIL_RB
+#define ORD_TAIL_RB 8
+#endif
+#ifndef ORD_TAIL_ROWS
+#define ORD_TAIL_ROWS 0
+#endif
+constexpr int kTailRB = ORD_TAIL_RB;      // rows per block at the end of an item (8 == no finer tail)
+constexpr int kTailRows = ORD_TAIL_ROWS;  // rows of an item handed out in tail blocks
 constexpr int kRBP = kRB + 1;       // pitch in records: lane c reads slot c * 9 + r -> conflict-free 128-bit accesses
 // Evaluation work items: a brick's records are cut into parts of at most `item target` records.  Large items keep the
 // per-item overhead and the end-of-item tail small (measured: 32 Ki -> 128 Ki records per item = -10 % evaluation time);
@@ -110,6 +125,7 @@ struct OrdGeom {
   int nsuper;    // super-groups of kMaxBins groups: > 1 adds a split level in front (arrays beyond 8192 bricks)
   int nfinal;    // nbricks * kClasses
   int wrapped;   // scale / extrapolation maps are applied when the records are made (check_query)
+  int tshift;    // shared-memory column of tile coordinate 0 on axis 1 (0..3), see TileCfg::PX
 };
 
 // First tap index of one axis: the `first` of axis_setup (eval.cuh; cubic.jl:40-57, quadratic.jl:39-43,
@@ -150,10 +166,10 @@ __device__ __forceinline__ void locate(const EvalParams &P, const OrdGeom &G, co
 
 // A query outside the bounds (or NaN) is a BoundsError (indexing.jl:6): it travels through the pipeline as
 // an all-NaN record (brick 0, class 0, NaN result) so that every q appears exactly once in the unsort.
-template <int N>
+template <int N, bool WRAP>
 __device__ __forceinline__ void check_query(const EvalParams &P, const OrdGeom &G, float (&x)[3], bool &valid) {
   valid = true;
-  if (G.wrapped) {
+  if constexpr (WRAP) {  // compile-time: the bare interpolant's count / split kernels carry none of this
     // extrapolate(scale(itp, ranges...), flags) whose whole coordinate chain stays Float32 (Int / Float32 ranges, OnGrid
     // bounds, no Line): the per-axis maps of the direct kernel (eval.cuh: etp_inbounds, coordlookup + clamp;
     // extrapolation.jl:106-163, scaling.jl:102-115) are applied HERE, once, and the record carries the coordinate in
@@ -187,7 +203,7 @@ __device__ __forceinline__ void check_query(const EvalParams &P, const OrdGeom &
   }
 }
 // ------------------------------------------------------------------------------------------ count
-template <int N, int DEG>
+template <int N, int DEG, bool WRAP>
 __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
                                                         unsigned *__restrict__ hist) {
   constexpr int U = 4;  // queries per thread per iteration: their loads are in flight together
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
       const long long q = q0 + u * stride;
       if (q < P.nq) {
         bool valid;
-        check_query<N>(P, G, x[u], valid);
+        check_query<N, WRAP>(P, G, x[u], valid);
         if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
         int brick, cls;
         locate<N, DEG>(P, G, x[u], brick, cls);
@@ -606,7 +622,7 @@ __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
 
 // split 1: coordinates -> {x,y,z,q} records grouped by brick group
 // SUPER: three-level geometry, the first pass splits by super-group (kMaxBins groups)
-template <int N, int DEG, bool SUPER>
+template <int N, int DEG, bool SUPER, bool WRAP>
 __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G, unsigned *__restrict__ cursor1,
                                                                    float4 *__restrict__ rec1) {
@@ -654,7 +670,7 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
       if (FULL || q < nq) {
         float x[3] = {nx[j][0], nx[j][1], nx[j][2]};
         bool valid;
-        check_query<N>(P, G, x, valid);
+        check_query<N, WRAP>(P, G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
         key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
@@ -907,6 +923,12 @@ struct TileReduce {
   }
 };
 
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
 __device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int sz = valid ? 4 : 0;
@@ -918,9 +940,13 @@ struct EvalSmem {
   float tile[TileCfg<N, DEG>::FLOATS];
   float4 wstage[kEvalThreads / 32][kClasses * kRBP];  // per-warp staging: kRB rows of every class
   long long axoff[3][TileCfg<N, DEG>::MAXT];  // element offset of tile coordinate l on each axis, -1: outside
-  unsigned cbeg[kClasses];  // first record of the item's share of each class stream
-  unsigned ccnt[kClasses];
-  int item_brick, item_part, item_parts, max_cnt, next_blk;
+  // work-item descriptors, double buffered: warp 0 fetches the next item's while the current one is evaluated
+  struct Item {
+    unsigned cbeg[kClasses];  // first record of the item's share of each class stream
+    unsigned ccnt[kClasses];
+    int brick, max_cnt;
+  } meta[2];
+  int next_blk;
 };
 
 template <int N, int DEG, bool GRAD>
@@ -962,47 +988,58 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
   const unsigned it_lo = first_item(blockIdx.x);
   const unsigned it_hi = first_item(blockIdx.x + 1);
   int cur_brick = -1;
-  int walk_brick = -1;  // thread 0: brick of the previous item
+  int walk_brick = -1;  // warp 0: brick of the previous item
   int o[3] = {0, 0, 0};
 #ifdef B200ITP_EVAL_TRACE
   const long long t_begin = clock64();
   unsigned long long n_rec = 0, n_rounds = 0, n_tiles = 0;
+  long long c_tile = 0, c_setup = 0, c_loop = 0, c_mark = t_begin, c_axoff = 0, c_issue = 0, c_tail = 0;
 #endif
+  // Descriptor of one work item (warp 0, all lanes): its brick — the last brick with item_start <= item (skips empty
+  // bricks): a binary search (13 dependent global loads) for the CTA's first item only, a short forward walk afterwards
+  // (the CTA's items are consecutive) — and its share of each of the brick's 32 class streams.
+  auto load_meta = [&](unsigned item, int slot) {
+    int lo = walk_brick;
+    if (lo < 0) {
+      lo = 0;
+      int hi = G.nbricks - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+      }
+    } else {
+      while (lo + 1 < G.nbricks && item_start[lo + 1] <= item) ++lo;
+    }
+    walk_brick = lo;
+    const unsigned is0 = item_start[lo];
+    const unsigned part = item - is0, parts = item_start[lo + 1] - is0;
+    const unsigned s0 = start[(long long)lo * kClasses + lane];
+    const unsigned long long n = start[(long long)lo * kClasses + lane + 1] - s0;
+    const unsigned a = (unsigned)(n * part / parts);
+    const unsigned b = (unsigned)(n * (part + 1) / parts);
+    auto &M = sm.meta[slot];
+    M.cbeg[lane] = s0 + a;
+    M.ccnt[lane] = b - a;
+    const unsigned mx = __reduce_max_sync(0xffffffffu, b - a);
+    if (lane == 0) {
+      M.brick = lo;
+      M.max_cnt = (int)mx;
+    }
+  };
+  if (warp == 0 && it_lo < it_hi) load_meta(it_lo, 0);
 
   for (unsigned item = it_lo; item < it_hi; ++item) {
-    __syncthreads();  // previous item fully consumed (cbeg/ccnt, tile)
-    if (tid == 0) {
-      // last brick with item_start <= item (skips empty bricks): a binary search (13 dependent global loads) for the
-      // CTA's first item only, a short forward walk afterwards (the CTA's items are consecutive)
-      int lo = walk_brick;
-      if (lo < 0) {
-        lo = 0;
-        int hi = G.nbricks - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
-        }
-      } else {
-        while (lo + 1 < G.nbricks && item_start[lo + 1] <= item) ++lo;
-      }
-      walk_brick = lo;
-      sm.item_brick = lo;
-      sm.item_part = (int)(item - item_start[lo]);
-      sm.item_parts = (int)(item_start[lo + 1] - item_start[lo]);
-      sm.max_cnt = 0;
-      sm.next_blk = 0;
-    }
-    __syncthreads();
-    const int brick = sm.item_brick;
-    if (tid < kClasses) {
-      const unsigned s = start[(long long)brick * kClasses + tid];
-      const unsigned long long n = start[(long long)brick * kClasses + tid + 1] - s;
-      const unsigned a = (unsigned)(n * (unsigned)sm.item_part / (unsigned)sm.item_parts);
-      const unsigned b = (unsigned)(n * (unsigned)(sm.item_part + 1) / (unsigned)sm.item_parts);
-      sm.cbeg[tid] = s + a;
-      sm.ccnt[tid] = b - a;
-      atomicMax(&sm.max_cnt, (int)(b - a));
-    }
+    const int slot = (int)((item - it_lo) & 1u);
+    __syncthreads();  // previous item fully consumed (tile, block counter); this item's descriptor is visible
+#ifdef B200ITP_EVAL_TRACE
+    { const long long now = clock64(); c_tail += now - c_mark; c_mark = now; }
+#endif
+    if (tid == 0) sm.next_blk = 0;
+    const auto &M = sm.meta[slot];
+    const int brick = M.brick;
+#ifdef B200ITP_EVAL_TRACE
+    { const long long now = clock64(); c_setup += now - c_mark; c_mark = now; }
+#endif
     if (brick != cur_brick) {  // stage the brick + halo; tile element l <-> parent index o + l on each axis
       cur_brick = brick;
 #ifdef B200ITP_EVAL_TRACE
@@ -1036,23 +1073,88 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
         }
       }
       __syncthreads();
-      for (int t = tid; t < TC::TX * TC::TY * TC::TZ; t += kEvalThreads) {
-        const int lx = t % TC::TX;
-        const int ly = (t / TC::TX) % TC::TY;
-        const int lz = t / (TC::TX * TC::TY);
-        const long long ox = sm.axoff[0][lx], oy = sm.axoff[1][ly], oz = N == 3 ? sm.axoff[2][lz] : 0;
-        const bool ok = ox >= 0 && oy >= 0 && oz >= 0;
-        // asynchronous 4-byte copies (zero fill outside the array): ~30 per thread in flight, no register round trip
-        cp_async4_zfill(&sm.tile[(lz * TC::TY + ly) * TC::PX + lx], coefs + (ok ? ox + oy + oz : 0), ok);
+#ifdef B200ITP_EVAL_TRACE
+      const long long t_ax = clock64();
+      c_axoff += t_ax - c_mark;
+#endif
+      // asynchronous copies (zero fill outside the array), no register round trip: a row is staged in groups of four
+      // shared-memory columns; a group whose four tile columns are consecutive array elements at a 16-byte aligned
+      // address is one 16-byte copy (8 of the 10 groups of a 35-wide row), the rest goes element by element (row ends,
+      // periodic wrap inside a group, rows of padded arrays that start off alignment)
+      constexpr int NG = TC::PX / 4;
+      const float *coefs16 = reinterpret_cast<const float *>(reinterpret_cast<uintptr_t>(coefs) & ~(uintptr_t)15);
+      const bool base16 = coefs16 == coefs;
+      for (int t = tid; t < NG * TC::TY * TC::TZ; t += kEvalThreads) {
+        const int gx = t % NG;
+        const int ly = (t / NG) % TC::TY;
+        const int lz = t / (NG * TC::TY);
+        const long long oy = sm.axoff[1][ly], oz = N == 3 ? sm.axoff[2][lz] : 0;
+        const bool rowok = oy >= 0 && oz >= 0;
+        const int l0 = 4 * gx - G.tshift;  // tile coordinate of the group's first column
+        float *dst = &sm.tile[(lz * TC::TY + ly) * TC::PX + 4 * gx];
+        bool whole = base16 && l0 >= 0 && l0 + 3 < TC::TX;
+        long long src = 0;
+        if (whole) {
+          const long long ox0 = sm.axoff[0][l0];
+          src = ox0 + oy + oz;
+          whole = !rowok || (ox0 >= 0 && sm.axoff[0][l0 + 3] == ox0 + 3 && (src & 3) == 0);
+        }
+        if (whole) {
+          cp_async16_zfill(dst, rowok ? coefs + src : coefs16, rowok);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int l = l0 + e;
+            if (l >= 0 && l < TC::TX) {
+              const long long ox = sm.axoff[0][l];
+              const bool ok = rowok && ox >= 0;
+              cp_async4_zfill(dst + e, coefs + (ok ? ox + oy + oz : 0), ok);
+            }
+          }
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+#ifdef B200ITP_EVAL_TRACE
+      c_issue += clock64() - t_ax;
+#endif
+#if ORD_TILE_PREFETCH
+      // Staging a tile is ~1300 scattered 128-byte lines (a 140-byte row every 2 KB): latency-bound, 15 000 cycles from
+      // DRAM.  While this tile is consumed, ask the L2 for the lines of the next brick (the CTA's bricks are consecutive;
+      // a hint only: an empty or foreign next brick costs nothing but the requests).
+      if (brick + 1 < G.nbricks) {
+        const int nbk = brick + 1;
+        const int no[3] = {(nbk % G.nb[0]) * Bk::BX, ((nbk / G.nb[0]) % G.nb[1]) * Bk::BY, (nbk / (G.nb[0] * G.nb[1])) * Bk::BZ};
+        auto aoff = [&](int d, int l) -> long long {
+          int idx = no[d] + l + G.fmin[d];
+          if (P.periodic[d]) {
+            const int n = P.n[d];
+            idx = (idx - 1) % n;
+            if (idx < 0) idx += n;
+            return (long long)idx * P.stride[d];
+          }
+          const int size_d = P.n[d] + (P.coef_first[d] == 0 ? 2 : 0);
+          const int pos = min(max(idx - P.coef_first[d], 0), size_d - 1);
+          return (long long)pos * P.stride[d];
+        };
+        for (int r = tid; r < TC::TY * TC::TZ; r += kEvalThreads) {
+          const long long row = aoff(1, r % TC::TY) + (N == 3 ? aoff(2, r / TC::TY) : 0);
+#pragma unroll
+          for (int l = 0; l < TC::TX + 31; l += 32) {  // one request per 128 bytes of the row (and its end)
+            const float *a = coefs + row + aoff(0, min(l, TC::TX - 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
+      }
+#endif
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int rounds = (sm.max_cnt + kRB - 1) / kRB;
+    if (warp == 0 && item + 1 < it_hi) load_meta(item + 1, slot ^ 1);  // its latency hides behind the other warps' blocks
+    const int rounds = (M.max_cnt + kRB - 1) / kRB;
 #ifdef B200ITP_EVAL_TRACE
+    { const long long now = clock64(); c_tile += now - c_mark; c_mark = now; }
     if (tid == 0) {
-      for (int c = 0; c < kClasses; ++c) n_rec += sm.ccnt[c];
+      for (int c = 0; c < kClasses; ++c) n_rec += M.ccnt[c];
       n_rounds += rounds;
     }
 #endif
@@ -1062,26 +1164,29 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     // instruction), evaluates them with lane c on class c, and stores the {q, value} results with the same mapping.
     // Only __syncwarp() is needed: no CTA-wide barrier inside an item.
     float4 *wst = sm.wstage[warp];
-    const unsigned mycnt = sm.ccnt[lane];
-    const int nblk = (sm.max_cnt + kRB - 1) / kRB;
+    const unsigned mycnt = M.ccnt[lane];
     // blocks are handed out dynamically (one shared counter per item): warps finish an item within one block of
-    // each other whatever their pace
+    // each other whatever their pace; the last kTailRows rows go out in blocks of kTailRB rows
+    const int rows_all = M.max_cnt;
+    const int nbig = rows_all > kTailRows ? (rows_all - kTailRows) / kRB : 0;
+    const int nblk = nbig + (rows_all - nbig * kRB + kTailRB - 1) / kTailRB;
     for (;;) {
       int blk = 0;
       if (lane == 0) blk = atomicAdd(&sm.next_blk, 1);
       blk = __shfl_sync(0xffffffffu, blk, 0);
       if (blk >= nblk) break;
-      const unsigned r0 = (unsigned)blk * kRB;
+      const unsigned r0 = blk < nbig ? (unsigned)blk * kRB : (unsigned)(nbig * kRB + (blk - nbig) * kTailRB);
+      const int rows = blk < nbig ? kRB : kTailRB;
 #pragma unroll
       for (int j = 0; j < kClasses / 4; ++j) {
         const int c = 4 * j + (lane >> 3), r = lane & 7;
-        if (r0 + r < sm.ccnt[c]) cp_async16(&wst[c * kRBP + r], rec + sm.cbeg[c] + r0 + r);
+        if (r < rows && r0 + r < M.ccnt[c]) cp_async16(&wst[c * kRBP + r], rec + M.cbeg[c] + r0 + r);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
 #pragma unroll 1
-      for (int r = 0; r < kRB; ++r) {
+      for (int r = 0; r < rows; ++r) {
         if (r0 + r < mycnt) {
           const float4 q4 = wst[lane * kRBP + r];
           const float x[3] = {q4.x, q4.y, q4.z};
@@ -1092,7 +1197,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
             axis_setup<DEG, float, GRAD>(P, d, x[d], ax[d]);
             lpos[d] = min(max(ax[d].first - G.fmin[d], 0), G.cells[d] - 1) - o[d];
           }
-          const float *tb = sm.tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0];
+          const float *tb = sm.tile + (lpos[2] * TC::TY + lpos[1]) * TC::PX + lpos[0] + G.tshift;
           if constexpr (GRAD) {
             float val = 0.f, g[N];
             TileReduce<N, DEG, 0>::run(ax, tb, val, g);
@@ -1130,26 +1235,29 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < kClasses / 4; ++j) {
         const int c = 4 * j + (lane >> 3), r = lane & 7;
-        if (r0 + r < sm.ccnt[c]) {
+        if (r < rows && r0 + r < M.ccnt[c]) {
           if constexpr (GRAD) {
             const float4 v = wst[c * kRBP + r];
-            res[sm.cbeg[c] + r0 + r] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+            res[M.cbeg[c] + r0 + r] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
                                                   __float_as_uint(v.w));
           } else {
             const float2 v = *reinterpret_cast<const float2 *>(&wst[c * kRBP + r]);
-            res[sm.cbeg[c] + r0 + r] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+            res[M.cbeg[c] + r0 + r] = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
           }
         }
       }
       __syncwarp();
     }
+#ifdef B200ITP_EVAL_TRACE
+    { const long long now = clock64(); c_loop += now - c_mark; c_mark = now; }
+#endif
   }
 #ifdef B200ITP_EVAL_TRACE
   if (tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    printf("evaltrace cta %d sm %u items %u records %llu rounds %llu tiles %llu cycles %lld\n", blockIdx.x, smid,
-           it_hi - it_lo, n_rec, n_rounds, n_tiles, clock64() - t_begin);
+    printf("evaltrace cta %d sm %u items %u records %llu rounds %llu tiles %llu cycles %lld setup %lld tile %lld loop(warp0) %lld axoff %lld issue %lld tail %lld\n",
+           blockIdx.x, smid, it_hi - it_lo, n_rec, n_rounds, n_tiles, clock64() - t_begin, c_setup, c_tile, c_loop, c_axoff, c_issue, c_tail);
   }
 #endif
 }
@@ -1224,6 +1332,9 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
   G.nsuper = G.ngroups <= kMaxBins ? 1 : (G.ngroups + kMaxBins - 1) / kMaxBins;
   G.nfinal = (int)bricks * kClasses;
   G.wrapped = (P.has_scale || P.etp_kind == B200ITP_ETP_FLAGS) ? 1 : 0;
+  // array column (0-based) of tile coordinate 0 on axis 1, modulo 4 (brick origins are multiples of 4)
+  const int c0 = G.fmin[0] - (P.periodic[0] ? 1 : P.coef_first[0]);
+  G.tshift = ((c0 % 4) + 4) % 4;
   return true;
 }
 
@@ -1266,8 +1377,10 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   constexpr int smem_place = (4 << U::SB) * (GRAD ? N : 1);
   static_assert(smem_eval <= 227 * 1024, "evaluation tile does not fit shared memory");
   static_assert(smem_place <= 227 * 1024, "placement window does not fit shared memory");
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
   B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
@@ -1279,7 +1392,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   const int cblocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sms * 16);
   {
     StageScope sc("ord_count", st);
-    ord_count_kernel<N, DEG><<<cblocks, 256, 0, st>>>(P, G, hist);
+    if (G.wrapped) ord_count_kernel<N, DEG, true><<<cblocks, 256, 0, st>>>(P, G, hist);
+    else ord_count_kernel<N, DEG, false><<<cblocks, 256, 0, st>>>(P, G, hist);
   }
   {
     StageScope sc("ord_scan_plan", st);
@@ -1292,7 +1406,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   if (G.nsuper == 1) {
     {
       StageScope sc("ord_split1", st);
-      ord_split1_kernel<N, DEG, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+      if (G.wrapped) ord_split1_kernel<N, DEG, false, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+      else ord_split1_kernel<N, DEG, false, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
     }
     {
       StageScope sc("ord_split2", st);
@@ -1301,7 +1416,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   } else {  // arrays beyond 8192 bricks: super-groups -> groups -> (brick, class) streams; the records end in rec2 again
     {
       StageScope sc("ord_split0", st);
-      ord_split1_kernel<N, DEG, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
+      if (G.wrapped) ord_split1_kernel<N, DEG, true, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
+      else ord_split1_kernel<N, DEG, true, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
     }
     {
       StageScope sc("ord_split1", st);
