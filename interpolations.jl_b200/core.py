@@ -597,6 +597,11 @@ def _prepare_coords(itp, xs):
     if len(xs) != N:
         raise ValueError(f"expected {N} coordinate arguments, got {len(xs)}")
     dev = torch.device("cuda", itp.device_index)
+    x0 = xs[0] if xs else None
+    if isinstance(x0, torch.Tensor) and x0.dim() == 1 and x0.dtype in (torch.float32, torch.float64) and all(
+            isinstance(x, torch.Tensor) and x.device == dev and x.dtype == x0.dtype and x.shape == x0.shape
+            and x.is_contiguous() for x in xs):
+        return list(xs), tuple(x0.shape), x0.dtype  # the hot path: SoA device arrays of one type, nothing to do
     ts = []
     for x in xs:
         if isinstance(x, torch.Tensor):

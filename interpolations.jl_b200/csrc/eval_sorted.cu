@@ -232,6 +232,54 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
   }
 }
 
+// Two-level geometry (at most kMaxBins groups): the first split only needs the group sizes, and a group histogram fits
+// shared memory, so this pass runs at the HBM rate (12 bytes per query) instead of the L2's atomic rate (one global
+// reduction per query: 6.2 ms per 1e9).  The (brick, class) histogram is accumulated by the first split itself
+// (ord_split1_kernel<.., COUNT = true>), whose shared-memory-bound chunks hide the reductions.
+#ifndef ORD_CG_U
+#define ORD_CG_U 4
+#endif
+#ifndef ORD_CG_THREADS
+#define ORD_CG_THREADS 256
+#endif
+#ifndef ORD_CG_MULT
+#define ORD_CG_MULT 16
+#endif
+template <int N, int DEG, bool WRAP>
+__global__ void __launch_bounds__(ORD_CG_THREADS) ord_count_groups_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
+                                                               unsigned *__restrict__ ghist) {
+  __shared__ unsigned sh[kMaxBins];
+  for (int i = threadIdx.x; i < kMaxBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  constexpr int U = ORD_CG_U;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < P.nq; q0 += U * stride) {
+    float x[U][3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        x[u][d] = (d < N && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < P.nq) {
+        bool valid;
+        check_query<N, WRAP>(P, G, x[u], valid);
+        if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
+        int brick, cls;
+        locate<N, DEG>(P, G, x[u], brick, cls);
+        atomicAdd(&sh[brick / kGroupBricks], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G.ngroups; i += blockDim.x)
+    if (sh[i]) atomicAdd(ghist + i, sh[i]);
+}
+
 // ------------------------------------------------------------------------------------------ scan (3 kernels)
 constexpr int kScanBlock = 1024;
 constexpr int kScanPer = 4;
@@ -337,22 +385,53 @@ struct OrdPlan {
   unsigned *cursorB;      // ceil(nq / 2^SB)
 };
 
-__global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restrict__ start, const OrdGeom G,
-                                                        long long nq, int ctas, int shiftA, int shiftB, OrdPlan pl) {
+// Two-level geometry, before the first split: group cursors and the split-2 chunk table from the group histogram
+// (ngroups <= kMaxBins <= 1024: one tile), plus the unsort cursors.
+__global__ void __launch_bounds__(1024) ord_plan_groups_kernel(const unsigned *__restrict__ ghist, const OrdGeom G,
+                                                               long long nq, int shiftA, int shiftB, OrdPlan pl) {
   __shared__ unsigned buf[1024];
-  __shared__ unsigned carry;
   const int t = threadIdx.x;
-  // unsort cursors
   const long long na = (nq + (1LL << shiftA) - 1) >> shiftA, nbw = (nq + (1LL << shiftB) - 1) >> shiftB;
   for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << shiftA);
   for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << shiftB);
-  // split cursors: first record of every group / super-group
+  const unsigned cnt = t < G.ngroups ? ghist[t] : 0u;
+  for (int pass = 0; pass < 2; ++pass) {
+    const unsigned v = pass == 0 ? cnt : (cnt + kChunk16 - 1) / kChunk16;
+    __syncthreads();
+    buf[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const unsigned u = t >= o ? buf[t - o] : 0u;
+      __syncthreads();
+      buf[t] += u;
+      __syncthreads();
+    }
+    unsigned *dst = pass == 0 ? pl.cursor1 : pl.chunk_start;
+    if (t < G.ngroups) dst[t] = buf[t] - v;
+    if (pass == 1 && t == 1023) dst[G.ngroups] = buf[t];
+  }
+}
+
+// items_only: the two-level path calls this after the first split, for the work-item table alone
+__global__ void __launch_bounds__(1024) ord_plan_kernel(const unsigned *__restrict__ start, const OrdGeom G,
+                                                        long long nq, int ctas, int shiftA, int shiftB, OrdPlan pl,
+                                                        bool items_only) {
+  __shared__ unsigned buf[1024];
+  __shared__ unsigned carry;
+  const int t = threadIdx.x;
   constexpr long long FPG = (long long)kGroupBricks * kClasses;  // final bins per group
-  for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[min((long long)g * FPG, (long long)G.nfinal)];
-  if (G.nsuper > 1)
-    for (int sg = t; sg < G.nsuper; sg += 1024) pl.cursor0[sg] = start[min((long long)sg * kMaxBins * FPG, (long long)G.nfinal)];
+  if (!items_only) {
+    // unsort cursors
+    const long long na = (nq + (1LL << shiftA) - 1) >> shiftA, nbw = (nq + (1LL << shiftB) - 1) >> shiftB;
+    for (long long i = t; i < na; i += 1024) pl.cursorA[i] = (unsigned)(i << shiftA);
+    for (long long i = t; i < nbw; i += 1024) pl.cursorB[i] = (unsigned)(i << shiftB);
+    // split cursors: first record of every group / super-group
+    for (int g = t; g < G.ngroups; g += 1024) pl.cursor1[g] = start[min((long long)g * FPG, (long long)G.nfinal)];
+    if (G.nsuper > 1)
+      for (int sg = t; sg < G.nsuper; sg += 1024) pl.cursor0[sg] = start[min((long long)sg * kMaxBins * FPG, (long long)G.nfinal)];
+  }
   // exclusive scans: chunks per group, items per brick, chunks per super-group
-  for (int pass = 0; pass < (G.nsuper > 1 ? 3 : 2); ++pass) {
+  for (int pass = items_only ? 1 : 0; pass < (items_only ? 2 : (G.nsuper > 1 ? 3 : 2)); ++pass) {
     const int n = pass == 0 ? G.ngroups : (pass == 1 ? G.nbricks : G.nsuper);
     unsigned *dst = pass == 0 ? pl.chunk_start : (pass == 1 ? pl.item_start : pl.chunk_mid);
     if (t == 0) carry = 0;
@@ -622,10 +701,12 @@ __device__ __forceinline__ void split_init(SplitSmem<Rec, S> &sm) {
 
 // split 1: coordinates -> {x,y,z,q} records grouped by brick group
 // SUPER: three-level geometry, the first pass splits by super-group (kMaxBins groups)
-template <int N, int DEG, bool SUPER, bool WRAP>
+// COUNT: also accumulate the (brick, class) histogram (two-level geometry, see ord_count_groups_kernel)
+template <int N, int DEG, bool SUPER, bool WRAP, bool COUNT>
 __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kernel(const __grid_constant__ EvalParams P,
                                                                    const OrdGeom G, unsigned *__restrict__ cursor1,
-                                                                   float4 *__restrict__ rec1) {
+                                                                   float4 *__restrict__ rec1,
+                                                                   unsigned *__restrict__ fine_hist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<SplitSmem<float4, kChunk16> *>(smem_raw);
   split_init(sm);
@@ -673,6 +754,7 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
         check_query<N, WRAP>(P, G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
+        if constexpr (COUNT) atomicAdd(fine_hist + (brick * kClasses + cls), 1u);  // result unused: RED
         key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float(q));
       }
@@ -1377,47 +1459,75 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   constexpr int smem_place = (4 << U::SB) * (GRAD ? N : 1);
   static_assert(smem_eval <= 227 * 1024, "evaluation tile does not fit shared memory");
   static_assert(smem_place <= 227 * 1024, "placement window does not fit shared memory");
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
-  B200_CUDA_OK(cudaFuncSetAttribute(ord_place_kernel<GRAD, GRAD ? N : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_place));
+  // once per device and instantiation (the attribute belongs to the function in that device's context)
+  static std::atomic<unsigned long long> attr_done{0};
+  if (dev >= 64 || !(attr_done.load(std::memory_order_acquire) >> dev & 1ULL)) {
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split1_kernel<N, DEG, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_split2_kernel<N, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<0, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_unsort_kernel<1, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemU));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_eval_kernel<N, DEG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval));
+    B200_CUDA_OK(cudaFuncSetAttribute(ord_place_kernel<GRAD, GRAD ? N : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_place));
+    if (dev < 64) attr_done.fetch_or(1ULL << dev, std::memory_order_release);
+  }
 
   B200_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)(G.nfinal + 1) * 4, st));
   const int cblocks = (int)std::min<long long>((P.nq + 255) / 256, (long long)sms * 16);
-  {
-    StageScope sc("ord_count", st);
-    if (G.wrapped) ord_count_kernel<N, DEG, true><<<cblocks, 256, 0, st>>>(P, G, hist);
-    else ord_count_kernel<N, DEG, false><<<cblocks, 256, 0, st>>>(P, G, hist);
-  }
-  {
-    StageScope sc("ord_scan_plan", st);
+  const int sblocks = sms * 2;
+  auto scan_fine = [&]() {
     scan_partial_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)nsb);
     scan_final_kernel<<<(unsigned)nsb, kScanBlock, 0, st>>>(hist, G.nfinal, sums, start);
-    ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, U::SA, U::SB, pl);
-  }
-  const int sblocks = sms * 2;
+  };
   if (G.nsuper == 1) {
+    // two-level geometry: group histogram (HBM rate) -> group cursors -> first split, which also accumulates the
+    // (brick, class) histogram -> scan, work items -> second split
+    unsigned *ghist = pl.chunk_mid;  // unused by this geometry otherwise (kMaxBins + 2 entries)
+    B200_CUDA_OK(cudaMemsetAsync(ghist, 0, (size_t)(kMaxBins + 2) * 4, st));
+    {
+      StageScope sc("ord_count", st);
+      const int gblocks = (int)std::min<long long>((P.nq + ORD_CG_THREADS - 1) / ORD_CG_THREADS, (long long)sms * ORD_CG_MULT);
+      if (G.wrapped) ord_count_groups_kernel<N, DEG, true><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist);
+      else ord_count_groups_kernel<N, DEG, false><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist);
+    }
+    {
+      StageScope sc("ord_scan_plan", st);
+      ord_plan_groups_kernel<<<1, 1024, 0, st>>>(ghist, G, P.nq, U::SA, U::SB, pl);
+    }
     {
       StageScope sc("ord_split1", st);
-      if (G.wrapped) ord_split1_kernel<N, DEG, false, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
-      else ord_split1_kernel<N, DEG, false, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1);
+      if (G.wrapped) ord_split1_kernel<N, DEG, false, true, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1, hist);
+      else ord_split1_kernel<N, DEG, false, false, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor1, rec1, hist);
+    }
+    {
+      StageScope sc("ord_scan_plan", st);
+      scan_fine();
+      ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, U::SA, U::SB, pl, true);
     }
     {
       StageScope sc("ord_split2", st);
       ord_split2_kernel<N, DEG, 2><<<sblocks, kSplitThreads, smem16, st>>>(P, G, start, pl.chunk_start, hist, rec1, rec2);
     }
+    count_launch();
   } else {  // arrays beyond 8192 bricks: super-groups -> groups -> (brick, class) streams; the records end in rec2 again
     {
+      StageScope sc("ord_count", st);
+      if (G.wrapped) ord_count_kernel<N, DEG, true><<<cblocks, 256, 0, st>>>(P, G, hist);
+      else ord_count_kernel<N, DEG, false><<<cblocks, 256, 0, st>>>(P, G, hist);
+    }
+    {
+      StageScope sc("ord_scan_plan", st);
+      scan_fine();
+      ord_plan_kernel<<<1, 1024, 0, st>>>(start, G, P.nq, sms, U::SA, U::SB, pl, false);
+    }
+    {
       StageScope sc("ord_split0", st);
-      if (G.wrapped) ord_split1_kernel<N, DEG, true, true><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
-      else ord_split1_kernel<N, DEG, true, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2);
+      if (G.wrapped) ord_split1_kernel<N, DEG, true, true, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2, nullptr);
+      else ord_split1_kernel<N, DEG, true, false, false><<<sblocks, kSplitThreads, smem16, st>>>(P, G, pl.cursor0, rec2, nullptr);
     }
     {
       StageScope sc("ord_split1", st);
