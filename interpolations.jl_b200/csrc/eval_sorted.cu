@@ -237,13 +237,13 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
 // reduction per query: 6.2 ms per 1e9).  The (brick, class) histogram is accumulated by the first split itself
 // (ord_split1_kernel<.., COUNT = true>), whose shared-memory-bound chunks hide the reductions.
 #ifndef ORD_CG_U
-#define ORD_CG_U 4
+#define ORD_CG_U 1
 #endif
 #ifndef ORD_CG_THREADS
 #define ORD_CG_THREADS 256
 #endif
 #ifndef ORD_CG_MULT
-#define ORD_CG_MULT 16
+#define ORD_CG_MULT 32
 #endif
 template <int N, int DEG, bool WRAP>
 __global__ void __launch_bounds__(ORD_CG_THREADS) ord_count_groups_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
@@ -251,30 +251,46 @@ __global__ void __launch_bounds__(ORD_CG_THREADS) ord_count_groups_kernel(const 
   __shared__ unsigned sh[kMaxBins];
   for (int i = threadIdx.x; i < kMaxBins; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  constexpr int U = ORD_CG_U;
+  auto one = [&](float x0, float x1, float x2, long long q) {
+    float x[3] = {x0, x1, x2};
+    bool valid;
+    check_query<N, WRAP>(P, G, x, valid);
+    if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
+    int brick, cls;
+    locate<N, DEG>(P, G, x, brick, cls);
+    atomicAdd(&sh[brick / kGroupBricks], 1u);
+  };
+  const float *c0 = reinterpret_cast<const float *>(P.coords[0]);
+  const float *c1 = reinterpret_cast<const float *>(P.coords[1]);
+  const float *c2 = N == 3 ? reinterpret_cast<const float *>(P.coords[2]) : c0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) == 0;
+  const long long nvec = vec ? P.nq / 4 : 0;  // four consecutive queries per thread: 128-bit loads
+  constexpr int U = ORD_CG_U;                 // vectors in flight per thread
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < P.nq; q0 += U * stride) {
-    float x[U][3];
+  for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += U * stride) {
+    float4 a[U], b[U], c[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long q = q0 + u * stride;
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        x[u][d] = (d < N && q < P.nq) ? reinterpret_cast<const float *>(P.coords[d])[q] : 0.f;
+      const long long v = v0 + u * stride;
+      if (v < nvec) {
+        a[u] = reinterpret_cast<const float4 *>(c0)[v];
+        b[u] = reinterpret_cast<const float4 *>(c1)[v];
+        c[u] = N == 3 ? reinterpret_cast<const float4 *>(c2)[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long q = q0 + u * stride;
-      if (q < P.nq) {
-        bool valid;
-        check_query<N, WRAP>(P, G, x[u], valid);
-        if (!valid) atomicMin(P.first_oob, (unsigned long long)q);
-        int brick, cls;
-        locate<N, DEG>(P, G, x[u], brick, cls);
-        atomicAdd(&sh[brick / kGroupBricks], 1u);
+      const long long v = v0 + u * stride;
+      if (v < nvec) {
+        one(a[u].x, b[u].x, c[u].x, 4 * v);
+        one(a[u].y, b[u].y, c[u].y, 4 * v + 1);
+        one(a[u].z, b[u].z, c[u].z, 4 * v + 2);
+        one(a[u].w, b[u].w, c[u].w, 4 * v + 3);
       }
     }
   }
+  for (long long q = 4 * nvec + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P.nq; q += stride)
+    one(c0[q], c1[q], N == 3 ? c2[q] : 0.f, q);
   __syncthreads();
   for (int i = threadIdx.x; i < G.ngroups; i += blockDim.x)
     if (sh[i]) atomicAdd(ghist + i, sh[i]);

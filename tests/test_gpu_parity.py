@@ -1261,3 +1261,27 @@ def test_ordered_pipeline_serves_float32_wrapped_interpolants(pkg, orc):
                 sobj(*bad)
     finally:
         L.b200itp_eval_sorted_set_min_queries(prev)
+
+
+def test_ordered_pipeline_unaligned_coordinate_arrays_and_odd_counts(pkg):
+    """The group-count pass reads the coordinate arrays with 128-bit loads when it can: views that start off a 16-byte
+    boundary and query counts that are not multiples of four must give the direct kernel's bits."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(23)
+    A = rng.standard_normal((70, 66, 40)).astype(np.float32)
+    itp = m.interpolate(A, m.BSpline(m.Cubic(m.Periodic(m.OnGrid()))))
+    prev = L.b200itp_eval_sorted_min_queries()
+    L.b200itp_eval_sorted_set_min_queries(1)
+    try:
+        for nq, off in ((100_003, 0), (65_537, 1), (4_099, 3), (3, 0), (40_000, 2)):
+            base = [torch.from_numpy(rng.uniform(1, n, nq + 4).astype(np.float32)).cuda() for n in A.shape]
+            coords = [b[off:off + nq] for b in base]
+            assert all(c.is_contiguous() for c in coords)
+            n0 = L.b200itp_eval_sorted_ordered_calls()
+            got = itp(*coords)
+            assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1
+            assert torch.equal(got, m.evaluate_direct(itp, *coords)), (nq, off)
+    finally:
+        L.b200itp_eval_sorted_set_min_queries(prev)
