@@ -406,7 +406,11 @@ def main():
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            # the coefficient broadcast runs beside the evaluation's persistent count / split kernels (one CTA per SM,
+            # nearly all registers): on a normal-priority stream NCCL's CTAs only get an SM when such a kernel ends
+            # and then queue behind the next one; high priority puts them first at those boundaries
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -431,7 +435,7 @@ def main():
     A = synthetic_volume(torch, dev)
     ncoef = N_GRID**3
 
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=-1)  # prefilter + broadcast: ahead of the queued split kernels
 
     def make_step(coords):
         def step():
@@ -618,6 +622,13 @@ def main():
             except Exception as e:  # reported, never fatal for the headline
                 sharded["c_abi"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.set_device(local_rank)
+        # the other ranks wait on the HOST (store key), not inside a NCCL barrier kernel that would spin on the very
+        # devices rank 0 is timing
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("b200itp_c_abi_done", "1")
+        else:
+            store.wait(["b200itp_c_abi_done"])
         barrier()
         del itp_check
 

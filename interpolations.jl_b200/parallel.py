@@ -57,9 +57,28 @@ def _world(group):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
-def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, device=None, group=None):
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One high-priority stream per device for coefficient traffic that overlaps an evaluation: the ordered pipeline's
+    count / split kernels are persistent (one CTA per SM, nearly all registers), so work queued at normal priority only
+    gets an SM when such a kernel ends and then waits behind the next one.  (For the NCCL kernels themselves create the
+    process group with `ProcessGroupNCCL.Options(is_high_priority_stream=True)`, as bench.py does.)"""
+    torch = _torch()
+    key = device.index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _side_streams[key]
+
+
+def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, device=None, group=None, overlap=False):
     """Replicate `itp` (held by rank `src` OF THE GROUP) on every rank: metadata by object broadcast, the coefficient
-    array by one `broadcast` (NCCL: 512 MiB cross NVLink once)."""
+    array by one `broadcast` (NCCL: 512 MiB cross NVLink once).
+
+    `overlap=True` (CUDA tensors): the broadcast is issued on a high-priority side stream and the returned object
+    carries `ready_event`; the next evaluation hands it to the library (`b200itp_eval_set_coefs_event`), whose count /
+    split kernels — they read only the coordinates — run meanwhile, and whose gather kernel waits for it."""
     torch, dist = _torch(), _dist()
     world, rank = _world(group)
     gsrc = dist.get_global_rank(group, src) if group is not None else src  # the collectives take GLOBAL ranks
@@ -74,11 +93,26 @@ def broadcast_interpolant(itp: Optional[core.BSplineInterpolation], src: int, de
     else:
         dev = torch.device("cuda", core._device_index(device)) if device is not None else torch.device("cpu")
         coefs = torch.empty(int(np.prod(size)), dtype=tdtype, device=dev)
-    dist.broadcast(coefs, src=gsrc, group=group)
+    ready = None
+    if overlap and coefs.device.type == "cuda":
+        main = torch.cuda.current_stream(coefs.device)
+        side = _side_stream(coefs.device)
+        side.wait_stream(main)  # the coefficients were produced on the caller's stream
+        with torch.cuda.stream(side):
+            dist.broadcast(coefs, src=gsrc, group=group)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        coefs.record_stream(side)
+    else:
+        dist.broadcast(coefs, src=gsrc, group=group)
     if rank == src:
-        return itp
-    dev_index = coefs.device.index if coefs.device.type == "cuda" else None
-    return core.BSplineInterpolation(coefs, size, parent_len, its, dev_index, parent_first=parent_first)
+        out = itp
+    else:
+        dev_index = coefs.device.index if coefs.device.type == "cuda" else None
+        out = core.BSplineInterpolation(coefs, size, parent_len, its, dev_index, parent_first=parent_first)
+    if ready is not None:
+        out.ready_event = ready
+    return out
 
 
 def _cuda_solver(device_index: int) -> Callable:
