@@ -329,6 +329,13 @@ B200ITP_API int b200itp_gradient_sorted(int dev, const b200itp_desc *d, const vo
  * threshold to 1 (tests) also lifts the array-size condition. */
 B200ITP_API int64_t b200itp_eval_sorted_min_queries(void);
 B200ITP_API void b200itp_eval_sorted_set_min_queries(int64_t n);
+/* 1 (default): the evaluation kernel of the ordered pipeline fetches a brick + halo tile with one tensor-map bulk copy
+ * (cp.async.bulk.tensor) whenever no axis of the tile wraps around a periodic boundary and the array qualifies
+ * (16-byte aligned base and rows); 0: every tile is staged with cp.async.  Identical results; returns the previous
+ * setting. */
+B200ITP_API int b200itp_eval_sorted_set_tma(int on);
+/* number of ordered-pipeline calls of this process whose evaluation kernel used the tensor-map tile copy */
+B200ITP_API uint64_t b200itp_eval_sorted_tma_calls(void);
 /* number of b200itp_eval_sorted calls of this process that were served by the ordered pipeline (the others were
  * forwarded to the direct kernel): lets tests and bench.py assert which path ran */
 B200ITP_API uint64_t b200itp_eval_sorted_ordered_calls(void);

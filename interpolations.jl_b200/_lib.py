@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
         "b200itp_gradient_sorted": (C.c_int, [i32, C.POINTER(Desc), vp, C.POINTER(vp), i64, vp, pi64, vp, sz, vp]),
         "b200itp_eval_sorted_min_queries": (i64, []),
         "b200itp_eval_sorted_set_min_queries": (None, [i64]),
+        "b200itp_eval_sorted_set_tma": (C.c_int, [C.c_int]),
+        "b200itp_eval_sorted_tma_calls": (C.c_uint64, []),
         "b200itp_prefilter_set_segmentation": (C.c_int, [C.c_int]),
         "b200itp_prefilter_set_strict": (C.c_int, [C.c_int]),
         "b200itp_eval_grid_set_separable": (C.c_int, [C.c_int]),
@@ -138,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "b200itp_memcpy_h2d", "b200itp_memcpy_d2h", "b200itp_sync", "b200itp_copy_with_padding",
     "b200itp_prefiltering_system", "b200itp_prefilter_axis", "b200itp_prefilter", "b200itp_prefilter_from", "b200itp_prefilter_padded_from", "b200itp_eval", "b200itp_eval_grid", "b200itp_eval_grid_scratch_bytes", "b200itp_hessian",
     "b200itp_out_dtype", "b200itp_eval_sorted_scratch_bytes", "b200itp_eval_sorted", "b200itp_gradient_sorted",
-    "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_prefilter_set_segmentation",
+    "b200itp_eval_sorted_min_queries", "b200itp_eval_sorted_set_min_queries", "b200itp_eval_sorted_set_tma", "b200itp_eval_sorted_tma_calls", "b200itp_prefilter_set_segmentation",
     "b200itp_prefilter_set_strict", "b200itp_eval_sorted_ordered_calls", "b200itp_eval_grid_set_separable",
     "b200itp_eval_grid_separable_calls", "b200itp_eval_set_coefs_event", "b200itp_set_l2_fetch_granularity", "b200itp_comm_init", "b200itp_comm_size", "b200itp_comm_destroy",
     "b200itp_bcast_coefs", "b200itp_prefilter_sharded",

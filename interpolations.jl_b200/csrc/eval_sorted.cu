@@ -27,6 +27,7 @@
 // applied when the records are made.  Everything else is forwarded to the direct kernel.
 #include "eval.cuh"
 
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is resolved at run time, libcuda is not linked
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -126,6 +127,7 @@ struct OrdGeom {
   int nfinal;    // nbricks * kClasses
   int wrapped;   // scale / extrapolation maps are applied when the records are made (check_query)
   int tshift;    // shared-memory column of tile coordinate 0 on axis 1 (0..3), see TileCfg::PX
+  int tma;       // brick tiles that need no periodic wrap are fetched by ONE tensor-map bulk copy (run_ordered)
 };
 
 // First tap index of one axis: the `first` of axis_setup (eval.cuh; cubic.jl:40-57, quadratic.jl:39-43,
@@ -1033,6 +1035,42 @@ __device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gsrc
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 
+// ---- tensor-map (TMA) tile copy: one instruction moves the brick + halo box, rows outside the array arrive as zeros
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tile_bar_init(unsigned long long *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tile_bar_expect(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tile_bar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+template <int N>
+__device__ __forceinline__ void tile_tma_load(void *dst, const CUtensorMap *map, int x, int y, int z,
+                                              unsigned long long *bar) {
+  if constexpr (N == 3) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+  }
+}
+
 template <int N, int DEG>
 struct EvalSmem {
   float tile[TileCfg<N, DEG>::FLOATS];
@@ -1045,6 +1083,7 @@ struct EvalSmem {
     int brick, max_cnt;
   } meta[2];
   int next_blk;
+  unsigned long long tile_bar;  // mbarrier of the tensor-map tile copy
 };
 
 template <int N, int DEG, bool GRAD>
@@ -1053,11 +1092,12 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
                                                                    const unsigned *__restrict__ start,
                                                                    const unsigned *__restrict__ item_start,
                                                                    const float4 *__restrict__ rec,
-                                                                   typename Uns<GRAD>::Rec *__restrict__ res) {
+                                                                   typename Uns<GRAD>::Rec *__restrict__ res,
+                                                                   const __grid_constant__ CUtensorMap tmap) {
   using TC = TileCfg<N, DEG>;
   using Bk = Brick<N>;
   constexpr int L = TC::L;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<EvalSmem<N, DEG> *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kEvalThreads / 32;
@@ -1125,6 +1165,8 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
     }
   };
   if (warp == 0 && it_lo < it_hi) load_meta(it_lo, 0);
+  unsigned tile_phase = 0;
+  if (G.tma && tid == 0) tile_bar_init(&sm.tile_bar);  // visible to all after the first barrier of the item loop
 
   for (unsigned item = it_lo; item < it_hi; ++item) {
     const int slot = (int)((item - it_lo) & 1u);
@@ -1150,6 +1192,24 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
       o[1] = by * Bk::BY;
       o[2] = bz * Bk::BZ;
       constexpr int TDIM[3] = {TC::TX, TC::TY, TC::TZ};
+      // one tensor-map copy when no axis of this tile wraps around a periodic boundary (C3: 72 % of the bricks): the
+      // box starts tshift columns early so that both staging paths share the tile layout; outside the array -> zeros
+      bool by_tma = G.tma != 0;
+      int org[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        org[d] = o[d] + G.fmin[d] - (P.periodic[d] ? 1 : P.coef_first[d]);
+        if (P.periodic[d] && (org[d] < 0 || org[d] + TDIM[d] > P.n[d])) by_tma = false;
+      }
+      if (by_tma) {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous tile's reads are behind the barrier
+          tile_bar_expect(&sm.tile_bar, (unsigned)(TC::FLOATS * sizeof(float)));
+          tile_tma_load<N>(sm.tile, &tmap, org[0] - G.tshift, org[1], org[2], &sm.tile_bar);
+        }
+        tile_bar_wait(&sm.tile_bar, tile_phase);
+        tile_phase ^= 1u;
+      } else {
       for (int e = tid; e < 3 * TC::MAXT; e += kEvalThreads) {  // per-axis offset tables, once per brick
         const int d = e / TC::MAXT, l = e % TC::MAXT;
         if (d < N && l < TDIM[d]) {
@@ -1245,6 +1305,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
       }
 #endif
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }  // !by_tma
     }
     __syncthreads();
     if (warp == 0 && item + 1 < it_hi) load_meta(item + 1, slot ^ 1);  // its latency hides behind the other warps' blocks
@@ -1361,6 +1422,50 @@ __global__ void __launch_bounds__(kEvalThreads, 1) ord_eval_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------ host
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+static std::atomic<uint64_t> g_tma_calls{0};  // ordered calls whose tiles went through the tensor map
+static int g_ord_tma = 1;  // b200itp_eval_sorted_set_tma(0): stage every tile with cp.async (tests compare the two)
+
+// Tensor map of the coefficient array for boxes of one brick + halo (TileCfg); false: the array does not qualify
+// (rows not 16-byte multiples, unaligned base, encoder unavailable) and every tile is staged with cp.async.
+template <int N, int DEG>
+static bool make_tile_map(const EvalParams &P, const b200itp_desc *D, CUtensorMap *map) {
+  using TC = TileCfg<N, DEG>;
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || !g_ord_tma) return false;
+  if (reinterpret_cast<uintptr_t>(P.coefs) % 16 != 0) return false;
+  cuuint64_t dims[3] = {1, 1, 1}, strides[2] = {0, 0};
+  cuuint32_t box[3] = {(cuuint32_t)TC::PX, (cuuint32_t)TC::TY, (cuuint32_t)TC::TZ}, est[3] = {1, 1, 1};
+  for (int d = 0; d < N; ++d) {
+    dims[d] = (cuuint64_t)D->size[d];
+    if (box[d] > 256) return false;
+    if (d > 0) {
+      if (P.stride[d] % 4 != 0) return false;  // byte strides must be multiples of 16
+      strides[d - 1] = (cuuint64_t)P.stride[d] * sizeof(float);
+    }
+  }
+  if (P.stride[0] != 1) return false;
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)N, const_cast<void *>(P.coefs), dims, strides, box,
+                         est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 struct OrdLayout {
   size_t rec1, rec2, hist, start, sums, cursor0, chunk_mid, cursor1, chunk_start, item_start, cursorA, cursorB, total;
 };
@@ -1433,6 +1538,7 @@ static bool ord_geometry(const EvalParams &P, const b200itp_desc *D, OrdGeom &G)
   // array column (0-based) of tile coordinate 0 on axis 1, modulo 4 (brick origins are multiples of 4)
   const int c0 = G.fmin[0] - (P.periodic[0] ? 1 : P.coef_first[0]);
   G.tshift = ((c0 % 4) + 4) % 4;
+  G.tma = 0;
   return true;
 }
 
@@ -1560,7 +1666,11 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   if (cudaEvent_t ev = take_coefs_event()) B200_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));
   {
     StageScope sc(GRAD ? "ord_eval_gradient" : "ord_eval", st);
-    ord_eval_kernel<N, DEG, GRAD><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    G.tma = make_tile_map<N, DEG>(P, D, &tmap) ? 1 : 0;
+    if (G.tma) g_tma_calls.fetch_add(1);
+    ord_eval_kernel<N, DEG, GRAD><<<sms, kEvalThreads, smem_eval, st>>>(P, G, start, pl.item_start, rec2, res, tmap);
   }
   const Rec *last = res;
   if (P.nq > (1LL << U::SA)) {
@@ -1597,6 +1707,12 @@ static std::atomic<uint64_t> g_ordered_calls{0};  // calls served by the ordered
 using namespace b200itp;
 
 extern "C" int64_t b200itp_eval_sorted_min_queries(void) { return g_sorted_min_queries; }
+extern "C" uint64_t b200itp_eval_sorted_tma_calls(void) { return g_tma_calls.load(); }
+extern "C" int b200itp_eval_sorted_set_tma(int on) {
+  const int prev = g_ord_tma;
+  g_ord_tma = on ? 1 : 0;
+  return prev;
+}
 extern "C" uint64_t b200itp_eval_sorted_ordered_calls(void) { return g_ordered_calls.load(); }
 extern "C" void b200itp_eval_sorted_set_min_queries(int64_t n) {
   g_sorted_min_queries = n < 1 ? 1 : n;

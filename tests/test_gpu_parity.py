@@ -1285,3 +1285,49 @@ def test_ordered_pipeline_unaligned_coordinate_arrays_and_odd_counts(pkg):
             assert torch.equal(got, m.evaluate_direct(itp, *coords)), (nq, off)
     finally:
         L.b200itp_eval_sorted_set_min_queries(prev)
+
+
+def test_ordered_pipeline_tensor_map_tiles_equal_cp_async_tiles(pkg):
+    """Brick tiles fetched by one tensor-map bulk copy (cp.async.bulk.tensor: interior bricks of periodic axes, every
+    brick of non-periodic ones, out-of-array parts zero-filled) or staged with cp.async give the same bits, equal to
+    the direct kernel's; arrays whose rows are not 16-byte multiples never take the tensor-map path."""
+    import torch
+    m = pkg
+    L = m._lib.lib()
+    rng = np.random.default_rng(31)
+    prev = L.b200itp_eval_sorted_min_queries()
+    L.b200itp_eval_sorted_set_min_queries(1)
+    try:
+        cases = [((128, 100, 52), m.BSpline(m.Cubic(m.Periodic(m.OnGrid())))),       # interior and wrapping bricks
+                 ((62, 40, 30), m.BSpline(m.Cubic(m.Flat(m.OnCell())))),             # padded to 64 x 42 x 32: every brick
+                 ((126, 70, 20), m.BSpline(m.Quadratic(m.Reflect(m.OnCell())))),     # padded to 128 x 72 x 22
+                 ((400, 300), m.BSpline(m.Cubic(m.Periodic(m.OnCell())))),           # 2-D, fmin = -1
+                 ((254, 200), m.BSpline(m.Quadratic(m.Line(m.OnGrid())))),           # 2-D padded to 256 x 202
+                 ((61, 45, 33), m.BSpline(m.Cubic(m.Line(m.OnGrid()))))]             # 63-wide rows: never by tensor map
+        for shape, it in cases:
+            A = rng.standard_normal(shape).astype(np.float32)
+            itp = m.interpolate(A, it)
+            nq = 150_000
+            coords = []
+            for (lb, ub) in itp.bounds():
+                x = rng.uniform(float(lb), float(ub), nq).astype(np.float32)
+                x[:2] = [lb, ub]
+                coords.append(np.clip(x, np.float32(lb), np.float32(ub)))
+            ref = m.evaluate_direct(itp, *coords)
+            gref = m.gradient_direct(itp, *coords)
+            for on in (1, 0):
+                was = L.b200itp_eval_sorted_set_tma(on)
+                try:
+                    n0 = L.b200itp_eval_sorted_ordered_calls()
+                    t0 = L.b200itp_eval_sorted_tma_calls()
+                    got = itp(*coords)
+                    ggot = m.gradient(itp, *coords)
+                    assert L.b200itp_eval_sorted_ordered_calls() == n0 + 2
+                    by_map = L.b200itp_eval_sorted_tma_calls() - t0
+                    assert by_map == (2 if on and shape[0] != 61 else 0), (shape, on, by_map)
+                finally:
+                    L.b200itp_eval_sorted_set_tma(was)
+                assert torch.equal(got, ref), (shape, it, on)
+                assert torch.equal(ggot, gref), (shape, it, on)
+    finally:
+        L.b200itp_eval_sorted_set_min_queries(prev)
