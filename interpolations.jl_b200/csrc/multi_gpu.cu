@@ -113,46 +113,6 @@ inline void split(int64_t n, int world, int r, int64_t &lo, int64_t &hi) {
   hi = lo + base + (r < rem ? 1 : 0);
 }
 
-// copy of a box of nx x ny x nz elements between two column-major arrays with different y / z pitches
-template <typename V>
-__global__ void __launch_bounds__(256) box_copy_kernel(const V *__restrict__ src, V *__restrict__ dst, long long nxv,
-                                                       long long ny, long long nz, long long ssy, long long ssz,
-                                                       long long dsy, long long dsz) {
-  const long long rows = ny * nz;
-  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
-    const long long y = row % ny, z = row / ny;
-    const V *s = src + y * ssy + z * ssz;
-    V *d = dst + y * dsy + z * dsz;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxv; i += (long long)gridDim.x * blockDim.x)
-      d[i] = s[i];
-  }
-}
-
-// pitches in ELEMENTS of es bytes
-int box_copy(int dev, const void *src, void *dst, int es, int64_t nx, int64_t ny, int64_t nz, int64_t ssy, int64_t ssz,
-             int64_t dsy, int64_t dsz, cudaStream_t st) {
-  if (nx == 0 || ny == 0 || nz == 0) return 0;
-  const int sms = sm_count(dev);
-  const bool v16 = ((nx * es) % 16 == 0) && ((ssy * es) % 16 == 0) && ((ssz * es) % 16 == 0) && ((dsy * es) % 16 == 0) &&
-                   ((dsz * es) % 16 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-  const long long rows = ny * nz;
-  if (v16) {
-    const long long k = 16 / es, nxv = nx / k;
-    dim3 grid((unsigned)std::min<long long>((nxv + 255) / 256, 8), (unsigned)std::min<long long>(rows, (long long)sms * 16));
-    box_copy_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, nxv, ny, nz, ssy / k, ssz / k, dsy / k,
-                                                  dsz / k);
-  } else if (es == 4) {
-    dim3 grid((unsigned)std::min<long long>((nx + 255) / 256, 8), (unsigned)std::min<long long>(rows, (long long)sms * 16));
-    box_copy_kernel<float><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, nx, ny, nz, ssy, ssz, dsy, dsz);
-  } else {
-    dim3 grid((unsigned)std::min<long long>((nx + 255) / 256, 8), (unsigned)std::min<long long>(rows, (long long)sms * 16));
-    box_copy_kernel<double><<<grid, 256, 0, st>>>((const double *)src, (double *)dst, nx, ny, nz, ssy, ssz, dsy, dsz);
-  }
-  count_launch();
-  B200_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 // All peers' blocks in ONE launch per device (the host thread drives every device: a launch per peer made the
 // 8-GPU prefilter launch-bound).  y-ranges y0[h] .. y0[h+1] tile [0, ny); block h of the peer-major / rank-major buffer
 // starts at element off[h] and is the dense box (nx, yl_h, nzb).
