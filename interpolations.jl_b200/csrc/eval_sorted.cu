@@ -241,6 +241,10 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
 #ifndef ORD_CG_U
 #define ORD_CG_U 1
 #endif
+#ifndef ORD_FINE_SHARE
+#define ORD_FINE_SHARE 2
+#endif
+constexpr int kFineShare = ORD_FINE_SHARE;  // of every 8 queries: (brick, class) reduction issued by the group-count pass
 #ifndef ORD_CG_THREADS
 #define ORD_CG_THREADS 256
 #endif
@@ -249,7 +253,8 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
 #endif
 template <int N, int DEG, bool WRAP>
 __global__ void __launch_bounds__(ORD_CG_THREADS) ord_count_groups_kernel(const __grid_constant__ EvalParams P, const OrdGeom G,
-                                                               unsigned *__restrict__ ghist) {
+                                                               unsigned *__restrict__ ghist,
+                                                               unsigned *__restrict__ fine_hist) {
   __shared__ unsigned sh[kMaxBins];
   for (int i = threadIdx.x; i < kMaxBins; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -261,6 +266,9 @@ __global__ void __launch_bounds__(ORD_CG_THREADS) ord_count_groups_kernel(const 
     int brick, cls;
     locate<N, DEG>(P, G, x, brick, cls);
     atomicAdd(&sh[brick / kGroupBricks], 1u);
+    // this pass is issue-bound with an idle LSU: it takes the (brick, class) reductions of kFineShare of every 8
+    // queries off the first split, whose shared-memory traffic they would queue behind
+    if (kFineShare > 0 && ((unsigned)q & 7u) < (unsigned)kFineShare) atomicAdd(fine_hist + (brick * kClasses + cls), 1u);
   };
   const float *c0 = reinterpret_cast<const float *>(P.coords[0]);
   const float *c1 = reinterpret_cast<const float *>(P.coords[1]);
@@ -772,7 +780,9 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
         check_query<N, WRAP>(P, G, x, valid);
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
-        if constexpr (COUNT) atomicAdd(fine_hist + (brick * kClasses + cls), 1u);  // result unused: RED
+        if constexpr (COUNT) {  // result unused: RED (the group-count pass took the first kFineShare of every 8)
+          if ((q & 7u) >= (unsigned)kFineShare) atomicAdd(fine_hist + (brick * kClasses + cls), 1u);
+        }
         key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float(q));
       }
@@ -1613,8 +1623,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
     {
       StageScope sc("ord_count", st);
       const int gblocks = (int)std::min<long long>((P.nq + ORD_CG_THREADS - 1) / ORD_CG_THREADS, (long long)sms * ORD_CG_MULT);
-      if (G.wrapped) ord_count_groups_kernel<N, DEG, true><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist);
-      else ord_count_groups_kernel<N, DEG, false><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist);
+      if (G.wrapped) ord_count_groups_kernel<N, DEG, true><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist, hist);
+      else ord_count_groups_kernel<N, DEG, false><<<gblocks, ORD_CG_THREADS, 0, st>>>(P, G, ghist, hist);
     }
     {
       StageScope sc("ord_scan_plan", st);
