@@ -84,12 +84,18 @@ constexpr int kChunk8 = 8192;       // 8-byte records
 // Unsort of the results: values travel as {q, value} (8 bytes), gradients as {q, g1, g2, g3} (16 bytes).  Final windows
 // of 2^SB results are permuted in shared memory (values: 2^14 x 4 B = 64 KB; gradients: 2^13 x N x 4 B <= 96 KB); level A
 // bins hold 512 windows each.
+#ifndef ORD_SB_VAL
+#define ORD_SB_VAL 14
+#endif
+#ifndef ORD_SAB
+#define ORD_SAB 8  // level-B bins per level-A bin: 2^8 (measured 9 -> 8: unsort A + B 8.25 -> 8.04 ms per 1e9 results)
+#endif
 template <bool GRAD>
 struct Uns {
   using Rec = typename std::conditional<GRAD, uint4, uint2>::type;
   static constexpr int S = GRAD ? kChunk16 : kChunk8;
-  static constexpr int SB = GRAD ? 13 : 14;
-  static constexpr int SA = SB + 9;
+  static constexpr int SB = GRAD ? 13 : ORD_SB_VAL;
+  static constexpr int SA = SB + (GRAD ? 9 : ORD_SAB);
 };
 #ifndef ORD_EVAL_THREADS
 #define ORD_EVAL_THREADS 768
@@ -1560,7 +1566,8 @@ static int run_ordered(int dev, EvalParams &P, const b200itp_desc *D, void *out,
   *done = false;
   OrdGeom G;
   if (!ord_geometry<N, DEG>(P, D, G)) return 0;
-  if (P.nq > (GRAD ? 0x7ffffff0LL : 0xfffffff0LL)) return 0;  // level A has at most 512 bins of 2^SA results
+  // level A has at most kMaxBins bins of 2^SA results (2^31 for both record types); larger calls: the direct kernel
+  if (P.nq > std::min<long long>(0xfffffff0LL, ((long long)kMaxBins << U::SA) - 16)) return 0;
   const OrdLayout Lo = ord_layout(P.nq, G.nfinal, G.nbricks, G.ngroups);
   if (!scratch || scratch_bytes < Lo.total || ((uintptr_t)scratch % 256) != 0) return 0;
   unsigned char *sb = reinterpret_cast<unsigned char *>(scratch);
