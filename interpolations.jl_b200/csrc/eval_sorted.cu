@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(256) ord_count_kernel(const __grid_constant__ 
 #ifndef ORD_CG_U
 #define ORD_CG_U 1
 #endif
+#ifndef ORD_RED_LATE
+#define ORD_RED_LATE 0  // 1: the first split issues its reductions after the chunk's copy-out (measured: 9.3 -> 10.5 ms)
+#endif
 #ifndef ORD_FINE_SHARE
 #define ORD_FINE_SHARE 2
 #endif
@@ -776,6 +779,11 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
     const unsigned cnt = FULL ? (unsigned)kChunk16 : nq - base;
     float4 r[RPT];
     unsigned key[RPT];
+#if ORD_RED_LATE
+    unsigned fk[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) fk[j] = 0xffffffffu;
+#endif
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const unsigned q = base + j * kSplitThreads + threadIdx.x;
@@ -787,7 +795,11 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
         int brick, cls;
         locate<N, DEG>(P, G, x, brick, cls);
         if constexpr (COUNT) {  // result unused: RED (the group-count pass took the first kFineShare of every 8)
+#if ORD_RED_LATE
+          fk[j] = ((q & 7u) >= (unsigned)kFineShare) ? (unsigned)(brick * kClasses + cls) : 0xffffffffu;
+#else
           if ((q & 7u) >= (unsigned)kFineShare) atomicAdd(fine_hist + (brick * kClasses + cls), 1u);
+#endif
         }
         key[j] = SUPER ? (unsigned)(brick / (kGroupBricks * kMaxBins)) : (unsigned)(brick / kGroupBricks);
         r[j] = make_float4(x[0], x[1], x[2], __uint_as_float(q));
@@ -795,6 +807,13 @@ __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas) ord_split1_kerne
     }
     if (kPrefetch) fetch(ch + gridDim.x);
     block_split<FULL, float4, kChunk16>(sm, r, key, SUPER ? G.nsuper : G.ngroups, cnt, cursor1, rec1);
+#if ORD_RED_LATE
+    if constexpr (COUNT) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (fk[j] != 0xffffffffu) atomicAdd(fine_hist + fk[j], 1u);
+    }
+#endif
   };
   if (kPrefetch) fetch(blockIdx.x);
   for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
