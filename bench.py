@@ -380,6 +380,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--configs", type=int, default=1, help="also run C1, C2, C4, C5")
     ap.add_argument("--c5-queries", type=int, default=10**9)
+    ap.add_argument("--lead-deficit", type=int, default=14_000_000,
+                    help="N > 1: queries rank 0 (prefilter + broadcast source) gets fewer than each other rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -480,8 +482,13 @@ def main():
 
     # ---- headline: 1e9 queries in total, sharded (strong scaling); every kernel launch of the timed steps is bracketed
     #      by CUDA events on the launching stream (b200itp_profile_*): the roofline's per-kernel durations
-    lo, hi = shard(args.queries, world, rank)
+    # rank 0 also prefilters the volume and feeds the broadcast while its own count / split kernels run (+0.6 ms of
+    # device time per step, whatever N): it takes --lead-deficit fewer queries than each other rank
+    from interpolations_jl_b200 import parallel as _par
+    lead = min(args.lead_deficit, args.queries // (4 * world)) if world > 1 else 0
+    lo, hi = _par.shard_bounds_lead(args.queries, world, rank, lead)
     nq = hi - lo
+    nq_others = (lambda b: b[1] - b[0])(_par.shard_bounds_lead(args.queries, world, world - 1, lead))
     coords = synthetic_queries(torch, dev, nq, rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -693,12 +700,15 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": C3_WORKLOAD, "queries_per_step": args.queries, "queries_per_gpu_per_step": nq,
+                       "queries_per_gpu_per_step_other_ranks": nq_others,
+                       "sharding": "contiguous chunks in rank order; rank 0 (prefilter + broadcast source) takes "
+                                   f"{lead} fewer queries than each other rank" if world > 1 else "one rank",
                        "call": "itp(xs, ys, zs) (the drop-in broadcast; served by the ordered pipeline)",
                        "l2": "inputs larger than L2 (coefficients 512 MiB, coordinates 12 B/query); the small configs "
                              "flush the L2 between timed iterations",
                        "parallelism": f"query-sharded x{world} (fixed total), coefficients replicated by NCCL broadcast"},
             "prefilter_gbs": roof_pre["achieved"], "prefilter_ms": pre_ms,
-            "eval_gevals_kernel": nq * world / (eval_ms * 1e-3) / 1e9,
+            "eval_gevals_kernel": nq / (eval_ms * 1e-3) / 1e9 * world,  # rank 0's rate x N
             "roofline": roof, "roofline_prefilter": roof_pre, "weak_scaling": weak, "prefilter_sharded": sharded,
             "configs": configs, "e2e": e2e,
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,

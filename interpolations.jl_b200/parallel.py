@@ -44,6 +44,20 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_bounds_lead(n: int, world: int, rank: int, lead_deficit: int = 0) -> Tuple[int, int]:
+    """`shard_bounds` with a lighter first chunk: rank 0 — the rank that also prefilters the volume and feeds the
+    coefficient broadcast while its own count / split kernels run — gets `lead_deficit` fewer queries than each of
+    the other ranks, so that all ranks finish together.  Chunks stay contiguous and in rank order."""
+    n, world, d = int(n), int(world), int(lead_deficit)
+    if world <= 1 or d <= 0:
+        return shard_bounds(n, world, rank)
+    n0 = max(0, (n - (world - 1) * d) // world)
+    if rank == 0:
+        return 0, n0
+    lo, hi = shard_bounds(n - n0, world - 1, rank - 1)
+    return n0 + lo, n0 + hi
+
+
 def shard_queries(xs: Sequence, world: int, rank: int):
     """The rank's chunk of every coordinate array (1-D, equal lengths): `itp.(xs...)` over the full arrays is the
     concatenation of the per-rank results in rank order."""

@@ -97,3 +97,23 @@ def test_shard_bounds_cover_range(pkg):
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_bounds_lead_gives_rank0_a_lighter_contiguous_chunk(pkg):
+    """Rank 0 prefilters and feeds the broadcast: `shard_bounds_lead` hands it `lead_deficit` fewer queries than each
+    other rank; the chunks stay contiguous, ordered, and cover the range."""
+    from interpolations_jl_b200 import parallel as par
+    for n in (0, 7, 1000, 10**9):
+        for w in (1, 2, 3, 8):
+            for d in (0, 10, 14_000_000):
+                b = [par.shard_bounds_lead(n, w, r, d) for r in range(w)]
+                assert b[0][0] == 0 and b[-1][1] == n
+                assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+                sizes = [hi - lo for lo, hi in b]
+                assert all(s >= 0 for s in sizes)
+                if w > 1:
+                    assert max(sizes[1:]) - min(sizes[1:]) <= 1
+                    if d > 0 and n >= w * d:
+                        assert d - 1 <= sizes[1] - sizes[0] <= d + 1, (n, w, d, sizes)
+                if d == 0:
+                    assert b == [par.shard_bounds(n, w, r) for r in range(w)]
