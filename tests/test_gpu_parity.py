@@ -618,6 +618,20 @@ def test_sharded_single_rank(pkg):
             assert torch.equal(itp_s.coefs, itp_1.coefs), it
             q = [rng.uniform(1, s, 1000).astype(np.float32) for s in A.shape]
             assert torch.equal(itp_s(*q), itp_1(*q))
+        # replication on the high-priority side stream: the object carries the event the next evaluation waits for
+        L = m._lib.lib()
+        prev = L.b200itp_eval_sorted_min_queries()
+        L.b200itp_eval_sorted_set_min_queries(1)
+        try:
+            rep = par.broadcast_interpolant(itp_1, 0, device=0, overlap=True)
+            assert getattr(rep, "ready_event", None) is not None
+            qq = [rng.uniform(1, s, 50_000).astype(np.float32) for s in A.shape]
+            n0 = L.b200itp_eval_sorted_ordered_calls()
+            got = rep(*qq)
+            assert L.b200itp_eval_sorted_ordered_calls() == n0 + 1
+            assert torch.equal(got, m.evaluate_direct(itp_1, *qq))
+        finally:
+            L.b200itp_eval_sorted_set_min_queries(prev)
     finally:
         dist.destroy_process_group()
 
