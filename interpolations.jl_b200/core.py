@@ -417,14 +417,11 @@ def _has_prefiltering_system(it: BSpline) -> bool:
     return True
 
 
-def _check_uniform_spec(it, its):
-    """`interpolate(A, BSpline(Cubic(Reflect(OnGrid()))))`: the single-spec method calls
-    `A_ldiv_B_md!(ret, nothing, ...)` and throws (prefiltering.jl:49-59); only the per-axis TUPLE method skips axes
-    without a system (prefiltering.jl:108-122)."""
-    if isinstance(it, BSpline):
-        for i in its[:1]:
-            if i.degree.code in (CUBIC, QUADRATIC) and not _has_prefiltering_system(i):
-                raise TypeError(f"no prefiltering system is defined for {i} (the reference throws a MethodError)")
+# A Cubic / Quadratic boundary condition the reference has no `prefiltering_system` method for (`Cubic(Reflect)`):
+# `prefiltering_system(::Any...)` returns `(nothing, nothing)` (prefiltering.jl:124) and
+# `A_ldiv_B_md!(dest, ::Nothing, src, dim, ::Nothing) = dest` (filter1d.jl:6) makes the axis pass a no-op in BOTH
+# `prefilter!` methods (single spec, prefiltering.jl:49-59, and per-axis tuple, :108-122): the reference returns the
+# padded, UNFILTERED array without an error, and so does the library (`_has_prefiltering_system` only reports it).
 
 
 def interpolate(A, it, device=None) -> BSplineInterpolation:
@@ -446,7 +443,6 @@ def interpolate(A, it, device=None) -> BSplineInterpolation:
     for d in range(N):  # is_singleton_ok b-splines.jl:114-121
         if shape[d] == 1 and its[d].degree.code != NOINTERP:
             raise ValueError(f"size {shape} is inconsistent with {it}, use NoInterp along singleton dimensions")
-    _check_uniform_spec(it, its)
     pad = [1 if needs_padding(i) else 0 for i in its]
     psize = tuple(shape[d] + 2 * pad[d] for d in range(N))
     code = F32 if src.dtype == torch.float32 else F64
@@ -485,7 +481,6 @@ def interpolate_inplace(A, it, device=None) -> BSplineInterpolation:
     for i in its:
         if not iscomplete(i):
             raise ValueError(f"OnGrid/OnCell is not supplied for some of the interpolation modes in {it}")
-    _check_uniform_spec(it, its)
     inset = [1 if needs_padding(i) else 0 for i in its]
     for d in range(N):
         if shape[d] - 2 * inset[d] < 1 or (shape[d] == 1 and its[d].degree.code != NOINTERP):

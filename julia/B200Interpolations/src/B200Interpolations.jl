@@ -33,7 +33,7 @@ import Interpolations: copy_with_padding
 import AxisAlgorithms: A_ldiv_B_md!
 using WoodburyMatrices: Woodbury
 
-export B200Array, b200, device_synchronize
+export B200Array, b200, device_synchronize, Comm, replicate, interpolate_sharded, evaluate_sharded
 
 # ------------------------------------------------------------------------------------------------ library
 const libb200itp = get(ENV, "B200ITP_LIB", "libb200itp")
@@ -122,6 +122,17 @@ function Base.Array(a::B200Array{T,N}) where {T,N}
     return h
 end
 Base.collect(a::B200Array) = Array(a)
+# `first(A)` is the one scalar read the reference makes on a coefficient array: `BSplineInterpolation(TWeights, A, it, axs)`
+# fixes the interpolant's element type with `typeof(zero(TWeights) * first(A))` (b-splines.jl:104-108)
+function Base.first(a::B200Array{T}) where {T}
+    isempty(a) && throw(BoundsError(a, 1))
+    h = Ref{T}()
+    check(ccall((:b200itp_memcpy_d2h, libb200itp), Cint, (Cint, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                a.dev, h, a.ptr, sizeof(T), C_NULL))
+    device_synchronize(a.dev)
+    return h[]
+end
+Base.first(a::OffsetArray{T,N,<:B200Array{T,N}}) where {T,N} = first(parent(a))
 Base.copy(a::B200Array) = B200Array(Array(a); dev=a.dev)   # (device-to-device copies go through the host: not on the hot path)
 function Base.copyto!(dest::B200Array{T,N}, src::B200Array{T,N}) where {T,N}
     size(dest) == size(src) || throw(DimensionMismatch("copyto!: sizes differ"))
@@ -193,7 +204,9 @@ end
 A_ldiv_B_md!(dest::B200Array, ::Nothing, src::B200Array, dim::Integer, b::AbstractVector) = copyto!(dest, src)  # filter1d.jl:6
 
 # `copy_with_padding(TC, A, it)` (prefiltering.jl:17-28): zero border of one cell on every padded axis, interior = A.
-function copy_with_padding(::Type{TC}, A::B200Array{T,N}, it) where {TC,T,N}
+# (`it` carries the reference method's own constraint: with it untyped the two methods would be ambiguous)
+function copy_with_padding(::Type{TC}, A::B200Array{T,N},
+                           it::Interpolations.DimSpec{Interpolations.InterpolationType}) where {TC,T,N}
     TC === T || throw(ArgumentError("B200Interpolations: coefficient type $TC differs from the array type $T"))
     indsA = axes(A)
     indspad = padded_axes(indsA, it)
@@ -520,5 +533,110 @@ function evalgrid(itp::AbstractInterpolation, vecs::AbstractVector...)
     return out
 end
 (itp::BSplineInterpolation{T,N,<:DeviceCoefs})(x::Vararg{AbstractVector,N}) where {T,N} = evalgrid(itp, x...)
+
+# ------------------------------------------------------------------------------------------------ several B200s
+# One Julia process drives the devices of one box (SURVEY §8e).  Evaluation needs no collective: queries are
+# independent, every device evaluates a contiguous chunk of the query arrays against its replica of the coefficients.
+
+"""
+    Comm(devs)
+
+NCCL communicator over the devices `devs` (0-based CUDA ordinals) of this box, driven by this process
+(`b200itp_comm_init`: `libnccl.so.2` is loaded at run time, `ncclCommInitAll`).  `close(comm)` destroys it.
+"""
+mutable struct Comm
+    ptr::Ptr{Cvoid}
+    devs::Vector{Cint}
+    function Comm(devs::AbstractVector{<:Integer})
+        d = Cint.(collect(devs))
+        p = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve d check(ccall((:b200itp_comm_init, libb200itp), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}),
+                                   length(d), d, p))
+        c = new(p[], d)
+        finalizer(close, c)
+        return c
+    end
+end
+function Base.close(c::Comm)
+    if c.ptr != C_NULL
+        ccall((:b200itp_comm_destroy, libb200itp), Cint, (Ptr{Cvoid},), c.ptr)
+        c.ptr = C_NULL
+    end
+    return nothing
+end
+Base.length(c::Comm) = length(c.devs)
+
+# the same interpolant around another coefficient buffer (what the reference's adapt_structure does, gpu_support.jl:4-8)
+rewrap(itp::BSplineInterpolation{T,N}, buf::B200Array) where {T,N} =
+    BSplineInterpolation{T,N}(itp.coefs isa OffsetArray ? OffsetArray(buf, itp.coefs.offsets) : buf, itp.parentaxes, itp.it)
+
+"""
+    replicate(comm, itp; root=1) -> Vector
+
+`itp` (coefficients on `comm.devs[root]`) on every device of the communicator, element `i` on `comm.devs[i]`: one NCCL
+broadcast of the coefficient array (`b200itp_bcast_coefs`; 512 MiB cross NVLink once).
+"""
+function replicate(comm::Comm, itp::BSplineInterpolation{T,N,<:DeviceCoefs}; root::Integer=1) where {T,N}
+    src = devarray(itp.coefs)
+    src.dev == comm.devs[root] || throw(ArgumentError("replicate: the coefficients live on device $(src.dev), not on comm.devs[$root]"))
+    bufs = [i == root ? src : B200Array{eltype(src),N}(undef, size(src); dev=comm.devs[i]) for i in 1:length(comm)]
+    ptrs = Ptr{Cvoid}[b.ptr for b in bufs]
+    GC.@preserve bufs ptrs check(ccall((:b200itp_bcast_coefs, libb200itp), Cint,
+                                       (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Csize_t),
+                                       comm.ptr, root - 1, ptrs, sizeof(eltype(src)) * length(src)))
+    return [rewrap(itp, b) for b in bufs]
+end
+
+"Contiguous, order-preserving split of `1:n` into `parts` ranges whose lengths differ by at most one."
+function shard_ranges(n::Integer, parts::Integer)
+    base, rem = divrem(n, parts)
+    los = [(r - 1) * base + min(r - 1, rem) for r in 1:parts]
+    return [(los[r] + 1):(los[r] + base + (r <= rem ? 1 : 0)) for r in 1:parts]
+end
+
+"""
+    interpolate_sharded(comm, A::Array{T,3}, it::BSpline) -> Vector
+
+`interpolate(A, it)` for a large 3-D array with the prefilter sharded over the devices of `comm`
+(`b200itp_prefilter_sharded`: z-slabs, local x / y passes, one all-to-all, local z pass, all-gather) — same pass order
+and systems as the reference (prefiltering.jl:49-59), same bits as the single-device prefilter.  Returns one
+interpolant per device, each with the full coefficient array, ready for `evaluate_sharded`.  Boundary conditions that
+pad the array (`padded_axes != axes(A)`) are not sharded: use `replicate(comm, interpolate(b200(A), it))`.
+"""
+function interpolate_sharded(comm::Comm, A::Array{T,3}, it::BSpline) where {T<:Union{Float32,Float64}}
+    Interpolations.padded_axes(axes(A), it) == axes(A) ||
+        throw(ArgumentError("interpolate_sharded: $it pads the array; prefilter on one device and `replicate`"))
+    G = length(comm)
+    zs = shard_ranges(size(A, 3), G)
+    slabs = [B200Array(A[:, :, zs[i]]; dev=comm.devs[i]) for i in 1:G]
+    full = [B200Array{T,3}(undef, size(A); dev=comm.devs[i]) for i in 1:G]
+    sp, fp = Ptr{Cvoid}[s.ptr for s in slabs], Ptr{Cvoid}[f.ptr for f in full]
+    codes = axis_codes(it)
+    deg, bcs, gts = fill(codes[1], 3), fill(codes[2], 3), fill(codes[3], 3)
+    sz = Int64[size(A)...]
+    ms = zeros(Cdouble, 2)
+    GC.@preserve slabs full sp fp check(ccall((:b200itp_prefilter_sharded, libb200itp), Cint,
+                                              (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Ptr{Int32},
+                                               Ptr{Int32}, Ptr{Int32}, Ptr{Cdouble}),
+                                              comm.ptr, sp, fp, dtype_code(T), sz, deg, bcs, gts, ms))
+    TW = Interpolations.tweight(A)
+    Tout = typeof(zero(TW) * zero(T))
+    return [BSplineInterpolation{Tout,3}(f, axes(A), it) for f in full]
+end
+
+"""
+    evaluate_sharded(itps, xs...) -> Vector
+
+`itp.(xs...)` with the queries sharded over the replicas `itps` (one per device, from `replicate` or
+`interpolate_sharded`): replica `i` evaluates the `i`-th contiguous chunk of the coordinate vectors on its own task;
+the result is the concatenation in order, i.e. exactly `itps[1].(xs...)`.
+"""
+function evaluate_sharded(itps::AbstractVector, xs::AbstractVector...)
+    n = length(first(xs))
+    all(x -> length(x) == n, xs) || throw(DimensionMismatch("evaluate_sharded: coordinate vectors of different lengths"))
+    rs = shard_ranges(n, length(itps))
+    tasks = [Threads.@spawn Array(itps[i].(map(x -> view(x, rs[i]), xs)...)) for i in eachindex(itps)]
+    return reduce(vcat, map(fetch, tasks))
+end
 
 end # module

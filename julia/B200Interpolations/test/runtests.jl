@@ -80,3 +80,24 @@ end
         @test eltype(b200(obj)) === Float64
     end
 end
+
+@testset "several devices: replicate, sharded prefilter, sharded evaluation" begin
+    # needs at least two B200s; one process drives them through the library's NCCL entry points
+    ndev = parse(Int, get(ENV, "B200ITP_TEST_DEVICES", "1"))
+    if ndev >= 2
+        comm = Comm(0:ndev-1)
+        A = rand(Float32, 64, 48, 40)
+        it = BSpline(Cubic(Periodic(OnGrid())))
+        cpu = interpolate(A, it)
+        one = interpolate(b200(A), it)
+        xs = ntuple(d -> Float32.(1 .+ (size(A, d) - 1) .* rand(100_003)), 3)
+        ref = collect(one.(xs...))
+        @test evaluate_sharded(replicate(comm, one), xs...) == ref          # broadcast replicas
+        sharded = interpolate_sharded(comm, A, it)                           # slab-sharded prefilter
+        @test all(s -> Array(B200Interpolations.devarray(s.coefs)) == Array(B200Interpolations.devarray(one.coefs)), sharded)
+        @test evaluate_sharded(sharded, xs...) == ref
+        @test maximum(abs.(ref .- cpu.(xs...))) <= 1f-4 * maximum(abs.(A))
+        @test_throws ArgumentError interpolate_sharded(comm, A, BSpline(Cubic(Flat(OnCell()))))
+        close(comm)
+    end
+end

@@ -1345,3 +1345,26 @@ def test_ordered_pipeline_tensor_map_tiles_equal_cp_async_tiles(pkg):
                 assert torch.equal(ggot, gref), (shape, it, on)
     finally:
         L.b200itp_eval_sorted_set_min_queries(prev)
+
+
+def test_spec_without_prefiltering_system_is_left_unfiltered(pkg, orc):
+    """`Cubic(Reflect(...))` has no `prefiltering_system` method: the reference falls back to `(nothing, nothing)`
+    (prefiltering.jl:124) and `A_ldiv_B_md!(dest, ::Nothing, src, dim, ::Nothing) = dest` (filter1d.jl:6), i.e.
+    `interpolate` returns the zero-padded samples as coefficients, for the single spec and inside a tuple alike."""
+    m = pkg
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((9, 7)).astype(np.float32)
+    refl = m.BSpline(m.Cubic(m.Reflect(m.OnGrid())))
+    for it in (refl, (refl, m.BSpline(m.Cubic(m.Line(m.OnGrid()))))):
+        itp = m.interpolate(A, it)
+        ref = orc.interpolate(A, it)
+        got = itp.coefs_array()
+        want = ref.coefs.reshape(ref.size, order="F")
+        assert got.shape == want.shape == (11, 9)
+        if it is refl:
+            assert np.array_equal(got[1:-1, 1:-1], A) and not got[0].any() and not got[:, 0].any()
+            assert np.array_equal(got, want)
+        else:
+            assert rel_err(got, want) <= TOL[np.dtype(np.float32)]
+        q = [rng.uniform(2, n - 1, 200).astype(np.float32) for n in A.shape]
+        check_eval(m, orc, itp, q)

@@ -94,7 +94,8 @@ def test_every_ccall_matches_the_header():
     for need in ("b200itp_malloc", "b200itp_free", "b200itp_memcpy_h2d", "b200itp_memcpy_d2h", "b200itp_sync",
                  "b200itp_copy_with_padding", "b200itp_prefilter_axis", "b200itp_eval", "b200itp_eval_sorted",
                  "b200itp_eval_sorted_scratch_bytes", "b200itp_gradient_sorted", "b200itp_hessian", "b200itp_eval_grid",
-                 "b200itp_eval_grid_scratch_bytes", "b200itp_out_dtype", "b200itp_last_error"):
+                 "b200itp_eval_grid_scratch_bytes", "b200itp_out_dtype", "b200itp_last_error",
+                 "b200itp_comm_init", "b200itp_comm_destroy", "b200itp_bcast_coefs", "b200itp_prefilter_sharded"):
         assert need in seen, need
 
 
@@ -149,5 +150,6 @@ def test_reference_gpu_cases_are_covered():
     t = open(os.path.join(ROOT, "julia", "B200Interpolations", "test", "runtests.jl")).read()
     for needle in ("BSpline(Cubic(Line(OnGrid())))", "BSpline(Linear())", "extrapolate(sitp, Flat())", "extrapolate(sitp, 0.0)",
                    "Interpolations.gradient", "Interpolations.hessian", "cpu == collect(on_host_args) == collect(on_dev_args)",
-                   "adapt(Array{Float32}, obj)", "b200itp_prefilter_set_strict"):
+                   "adapt(Array{Float32}, obj)", "b200itp_prefilter_set_strict", "evaluate_sharded(replicate(comm, one), xs...)",
+                   "interpolate_sharded(comm, A, it)"):
         assert needle in t, needle
