@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>
@@ -59,14 +60,18 @@ int sm_count(int dev);
 bool stage_timing_enabled();
 void stage_begin(const char *name, cudaStream_t st);
 void stage_end(cudaStream_t st);
+// Every stage is also an NVTX range on the launching host thread (header-only NVTX 3: no-ops unless a profiler
+// injected itself), so an nsys / ncu timeline shows the same names as b200itp_profile_get.
 struct StageScope {
   cudaStream_t st;
   bool on;
   StageScope(const char *name, cudaStream_t s) : st(s), on(stage_timing_enabled()) {
+    nvtxRangePushA(name);
     if (on) stage_begin(name, st);
   }
   ~StageScope() {
     if (on) stage_end(st);
+    nvtxRangePop();
   }
 };
 
