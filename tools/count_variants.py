@@ -1,3 +1,5 @@
+"""C3 ordered evaluation, 1e9 queries: ord_count / ord_split1 stage times and the stage sum for one build of the library
+(B200ITP_LIB selects the build: sweeps of ORD_CG_* and ORD_FINE_SHARE)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

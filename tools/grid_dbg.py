@@ -1,3 +1,4 @@
+"""Debug driver of the separable grid evaluation (small case against the pointwise kernel)."""
 import sys
 sys.path.insert(0, ".")
 import b200_loader, torch

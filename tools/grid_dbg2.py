@@ -1,3 +1,4 @@
+"""Debug driver of the separable grid evaluation against the CPU oracle."""
 import sys, os
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,3 +1,4 @@
+"""Stage times (b200itp_profile_*) of one C3 ordered evaluation call."""
 import sys
 sys.path.insert(0,".")
 import b200_loader, torch

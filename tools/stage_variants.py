@@ -1,3 +1,5 @@
+"""C3 ordered evaluation, 1e9 queries: every stage time and the stage sum for one build of the library (B200ITP_LIB
+selects the build: sweeps of ORD_SB_VAL / ORD_SAB, ORD_RED_LATE ...), checked against the direct kernel on two slices."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -1,3 +1,5 @@
+"""A/B of the tensor-map tile copy of ord_eval_kernel in ONE process (b200itp_eval_sorted_set_tma): 1.25e8 and 1e9
+queries on the C3 volume."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
